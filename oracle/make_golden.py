@@ -1,0 +1,254 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (/root/reference, via oracle/ref_shim.py).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference tree is not on the GPU box):
+
+    python oracle/make_golden.py
+
+Every fixture stores the exact inputs next to the reference's outputs so that the tests never need the reference.
+Covers SURVEY.md section 8(c) items (i)-(vii).
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, vlgp_oracle as orc  # noqa: E402
+from vlgp_b200.synth import make_trials  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def build_problem(ref, seed, n_trials, T, N, L, lik=None, window=None, **cfgkw):
+    """Reference-format (trials, params, config) with random but reproducible state (no FactorAnalysis)."""
+    rng = np.random.default_rng(seed)
+    trials = make_trials(n_trials, T, N, L, seed=seed + 1000)
+    config = ref.preprocess.get_config(**cfgkw)
+    kwargs = {"omega_bound": config["omega_bound"]}
+    if lik is not None:
+        kwargs["lik"] = lik
+    params = ref.preprocess.get_params(trials, L, **kwargs)
+    params["a"] = 0.3 * rng.standard_normal((L, N))
+    params["b"] = np.log(np.maximum(np.mean(np.concatenate([t["y"] for t in trials]), axis=0, keepdims=True), 1e-2))
+    params["noise"] = 0.5 + rng.random(N)
+    params["omega"] = np.exp(rng.uniform(np.log(2e-3), np.log(4e-2), L))
+    for t in trials:
+        n = t["y"].shape[0]
+        if lik is not None:
+            gauss = np.asarray(lik) == "gaussian"
+            t["y"][:, gauss] = t["y"][:, gauss] + 0.3 * rng.standard_normal((n, int(gauss.sum())))
+        t["mu"] = 0.5 * rng.standard_normal((n, L))
+        t["x"] = np.ones((n, 1, N))
+        t["w"] = np.zeros((n, L))
+        t["v"] = np.zeros((n, L))
+    ref.preprocess.fill_params(params)
+    ref.preprocess.fill_trials(trials)
+    ref.gp.make_cholesky(trials, params, config)
+    ref.core.update_w(trials, params, config)
+    ref.core.update_v(trials, params, config)
+    if window:
+        config["window"] = window
+        np.random.seed(seed)
+        segs = ref.util.cut_trials(trials, params, config)
+        segs = [copy.deepcopy(s) for s in segs]     # de-alias (hard part 3)
+        ref.gp.make_cholesky(segs, params, config)
+        ref.preprocess.fill_trials(segs)
+        return segs, params, config
+    return trials, params, config
+
+
+def pack_state(prefix, trials, params):
+    d = {}
+    d[prefix + "mu"] = np.stack([t["mu"] for t in trials])
+    d[prefix + "v"] = np.stack([t["v"] for t in trials])
+    d[prefix + "w"] = np.stack([t["w"] for t in trials])
+    d[prefix + "dmu"] = np.stack([t["dmu"] for t in trials])
+    for k in ("a", "b", "noise", "omega", "sigma", "da", "db"):
+        d[prefix + k] = np.array(params[k])
+    return d
+
+
+def golden_ichol(ref):
+    out = {}
+    for n in (50, 200, 500, 1000, 2000):
+        for om in (5e-4, 5e-3, 5e-2):
+            G = ref.math.ichol_gauss(n, om, 50)
+            G2, piv = orc.ichol_gauss(n, om, 50, return_pivots=True)
+            assert np.array_equal(G, G2), "oracle ichol differs bitwise from reference at n=%d omega=%g" % (n, om)
+            key = "n%d_w%g" % (n, om)
+            out[key + "_piv"] = piv
+            out[key + "_ncol"] = np.array(int((np.abs(G).sum(axis=0) > 0).sum()))
+            if n <= 200:
+                out[key + "_G"] = G
+            else:
+                out[key + "_Grows"] = G[::25]           # every 25th row
+                out[key + "_colsum"] = G.sum(axis=0)
+                out[key + "_diagK"] = np.sum(G * G, axis=1)
+    # the reference's own known-answer test (tests/test_math.py:7-14) at a smaller n: full-rank factor reproduces K
+    G = ref.math.ichol_gauss(60, 1.0, 60)
+    out["fullrank_n60_G"] = G
+    np.savez_compressed(os.path.join(OUT, "ichol.npz"), **out)
+    print("ichol.npz", len(out))
+
+
+def golden_estep(ref):
+    out = {}
+    cases = {
+        "poisson": dict(seed=1, n_trials=3, T=100, N=12, L=2, lik=None),
+        "mixed": dict(seed=2, n_trials=2, T=100, N=9, L=3, lik=["poisson"] * 5 + ["gaussian"] * 4),
+    }
+    for name, kw in cases.items():
+        for niter in (1, 25):
+            segs, params, config = build_problem(ref, window=50, Eniter=niter, **kw)
+            p = "%s_it%d_" % (name, niter)
+            out[p + "y"] = np.stack([s["y"] for s in segs])
+            out[p + "poisson"] = np.asarray(params["likelihood"]) == "poisson"
+            out[p + "G"] = params["cholesky"][50]
+            out.update(pack_state(p + "in_", segs, params))
+            ref.core.estep(segs, params, config)
+            out.update(pack_state(p + "out_", segs, params))
+    # MAP variant (method != "VB": v is left untouched, core.py:105)
+    segs, params, config = build_problem(ref, window=50, Eniter=3, method="MAP", **cases["poisson"])
+    p = "map_it3_"
+    out[p + "y"] = np.stack([s["y"] for s in segs])
+    out[p + "poisson"] = np.asarray(params["likelihood"]) == "poisson"
+    out[p + "G"] = params["cholesky"][50]
+    out.update(pack_state(p + "in_", segs, params))
+    ref.core.estep(segs, params, config)
+    out.update(pack_state(p + "out_", segs, params))
+    np.savez_compressed(os.path.join(OUT, "estep.npz"), **out)
+    print("estep.npz", len(out))
+
+
+def golden_mstep(ref):
+    out = {}
+    cases = {
+        "poisson": dict(seed=3, n_trials=3, T=100, N=12, L=2, lik=None),
+        "mixed": dict(seed=4, n_trials=2, T=100, N=9, L=3, lik=["poisson"] * 5 + ["gaussian"] * 4),
+    }
+    for name, kw in cases.items():
+        for niter in (1, 25):
+            segs, params, config = build_problem(ref, window=50, Eniter=2, Mniter=niter, **kw)
+            ref.core.estep(segs, params, config)    # realistic v, w
+            p = "%s_it%d_" % (name, niter)
+            out[p + "y"] = np.stack([s["y"] for s in segs])
+            out[p + "poisson"] = np.asarray(params["likelihood"]) == "poisson"
+            out.update(pack_state(p + "in_", segs, params))
+            ref.core.mstep(segs, params, config)
+            out.update(pack_state(p + "out_", segs, params))
+    np.savez_compressed(os.path.join(OUT, "mstep.npz"), **out)
+    print("mstep.npz", len(out))
+
+
+def golden_hstep(ref):
+    out = {}
+    segs, params, config = build_problem(ref, seed=5, n_trials=4, T=100, N=12, L=2, window=50, Eniter=5)
+    ref.core.estep(segs, params, config)
+    mu = np.stack([s["mu"] for s in segs])
+    w = np.stack([s["w"] for s in segs])
+    out["mu"], out["w"] = mu, w
+    t = np.arange(50) * 1.0
+    omegas = np.array([1e-3, 7e-3, 4e-2])
+    out["omegas"] = omegas
+    mask = np.array([0, 1, 0])
+    for l in range(2):
+        vals, grads = [], []
+        for om in omegas:
+            hyper = np.array([1.0, om, 1e-4])
+            S = ref.gp.construct_posterior_cov(t, w[:, :, l].T, hyper)
+            ll, dll = ref.gp.elbo(hyper, mask, t, mu[:, :, l].T, S)
+            vals.append(ll)
+            grads.append(dll)
+        out["ll_l%d" % l] = np.array(vals)
+        out["dll_l%d" % l] = np.array(grads)
+        initial = (1.0, params["omega"][l], 1e-4)
+        bounds = ((1e-3, 1), config["omega_bound"], (1e-4 / 2, 1e-4 * 2))
+        opt, fun = ref.gp.optimze1d(t, mu[:, :, l].T, w[:, :, l].T, initial, bounds, mask=mask)
+        out["opt_l%d" % l] = np.asarray(opt)
+        out["fun_l%d" % l] = np.asarray(fun)
+    out["omega0"] = np.array(params["omega"])
+    # whole hstep (gp.optimize) on the same segments
+    ref.core.hstep(segs, params, config)
+    out["omega_after"] = np.array(params["omega"])
+    out["sigma_after"] = np.array(params["sigma"])
+    out["G_after"] = params["cholesky"][50]
+    np.savez_compressed(os.path.join(OUT, "hstep.npz"), **out)
+    print("hstep.npz", len(out))
+
+
+def golden_update_wv(ref):
+    out = {}
+    trials, params, config = build_problem(ref, seed=6, n_trials=2, T=1000, N=12, L=2)
+    out["y"] = np.stack([t["y"] for t in trials]).astype(np.uint8)
+    assert np.array_equal(out["y"], np.stack([t["y"] for t in trials]))
+    # build_problem already ran update_w / update_v once from v = 0: run a second round so v enters w
+    for k in ("mu",):
+        out["in_" + k] = np.stack([t[k] for t in trials])
+    out["in_v"] = np.stack([t["v"] for t in trials])
+    for k in ("a", "b", "noise", "omega", "sigma"):
+        out[k] = np.array(params[k])
+    ref.core.update_w(trials, params, config)
+    ref.core.update_v(trials, params, config)
+    out["out_w"] = np.stack([t["w"] for t in trials])
+    out["out_v"] = np.stack([t["v"] for t in trials])
+    # a short full-trial E-step (the final ``infer`` regime: T x 50 factor)
+    config["Eniter"] = 3
+    ref.core.estep(trials, params, config)
+    out["infer_mu"] = np.stack([t["mu"] for t in trials])
+    out["infer_v"] = np.stack([t["v"] for t in trials])
+    out["infer_w"] = np.stack([t["w"] for t in trials])
+    out["infer_dmu"] = np.stack([t["dmu"] for t in trials])
+    np.savez_compressed(os.path.join(OUT, "update_wv.npz"), **out)
+    print("update_wv.npz", len(out))
+
+
+def golden_vem(ref):
+    out = {}
+    segs, params, config = build_problem(ref, seed=7, n_trials=4, T=100, N=10, L=2, window=50,
+                                         max_iter=3, min_iter=3)
+    out["y"] = np.stack([s["y"] for s in segs])
+    out.update(pack_state("in_", segs, params))
+    ref.core.vem(segs, params, config)
+    out.update(pack_state("out_", segs, params))
+    out["n_it"] = np.array(config["runtime"]["it"])
+    np.savez_compressed(os.path.join(OUT, "vem.npz"), **out)
+    print("vem.npz", len(out))
+
+
+def golden_fit(ref):
+    out = {}
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    out["y"] = np.stack([t["y"] for t in trials]).astype(np.uint8)
+    np.random.seed(0)
+    res = ref.fit(trials, 3, max_iter=3, min_iter=3)
+    out["mu"] = np.stack([t["mu"] for t in res["trials"]])
+    out["v"] = np.stack([t["v"] for t in res["trials"]])
+    out["w"] = np.stack([t["w"] for t in res["trials"]])
+    for k in ("a", "b", "noise", "omega", "sigma"):
+        out[k] = np.array(res["params"][k])
+    for k in ("a", "b", "omega"):
+        out["initial_" + k] = np.array(res["params"]["initial"][k])
+    np.savez_compressed(os.path.join(OUT, "fit_tutorial.npz"), **out)
+    print("fit_tutorial.npz", len(out))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    import vlgp.preprocess, vlgp.core, vlgp.gp, vlgp.math, vlgp.util  # noqa: F401,E401
+    golden_ichol(ref)
+    golden_estep(ref)
+    golden_mstep(ref)
+    golden_hstep(ref)
+    golden_update_wv(ref)
+    golden_vem(ref)
+    golden_fit(ref)
+
+
+if __name__ == "__main__":
+    main()
