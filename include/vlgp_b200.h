@@ -1,0 +1,137 @@
+/*
+ * vlgp_b200.h -- C ABI of libvlgp_b200.so, the B200 (sm_100a) variational-EM engine behind vlgp.fit().
+ *
+ * The reference (catniplab/vlgp) has no FFI: its seam is a set of Python functions with the signature
+ * (trials, params, config) that mutate three dicts in place (vlgp/api.py:7-11 binds them by name).  Each entry point
+ * below replaces the arithmetic of one of those functions; the Python host (vlgp_b200/*.py) packs the dicts into the
+ * flat buffers these calls take and unpacks the results into the same dict keys.  All entry points are batched over
+ * trials x latents, take plain pointers and sizes, never throw, and return 0 on success or a negative vlgp_status
+ * (message via vlgp_last_error).  Host pointers are borrowed for the duration of the call; device memory is owned by
+ * the context.  One host thread drives one context; one context drives one GPU.
+ *
+ * Layout conventions (identical to the reference's NumPy arrays, C-contiguous, float64 on the host):
+ *   bins of all trials of a "trial set" are concatenated in trial order: nbin = sum(lengths)
+ *   y            nbin x N          (float64, or uint8 when every count is an integer in [0,255])
+ *   mu,v,w,dmu   nbin x L
+ *   a, da        L x N             (params["a"], params["da"])
+ *   b, db        N                 (params["b"][0,:]; xdim == 1 with an all-ones regressor, vlgp/preprocess.py:43-44)
+ *   noise        N
+ *   G            L x length x rank (params["cholesky"][length], vlgp/gp.py:150-162)
+ */
+#ifndef VLGP_B200_H
+#define VLGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VLGP_API __attribute__((visibility("default")))
+#else
+#define VLGP_API
+#endif
+
+typedef struct vlgp_ctx vlgp_ctx;
+
+enum vlgp_status {
+    VLGP_OK = 0,
+    VLGP_ERR_ARG = -1,      /* bad argument / call order */
+    VLGP_ERR_CUDA = -2,     /* CUDA runtime error (message has the call site) */
+    VLGP_ERR_NCCL = -3,     /* NCCL error or libnccl could not be loaded */
+    VLGP_ERR_NOMEM = -4,
+    VLGP_ERR_UNSUPPORTED = -5
+};
+
+enum vlgp_ydtype { VLGP_Y_F64 = 0, VLGP_Y_U8 = 1 };
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------------------- */
+VLGP_API int vlgp_create(int device, vlgp_ctx **out);
+VLGP_API int vlgp_destroy(vlgp_ctx *ctx);
+/* Last error message of this context (or of the failed vlgp_create when ctx == NULL). */
+VLGP_API const char *vlgp_last_error(const vlgp_ctx *ctx);
+VLGP_API int vlgp_device_info(vlgp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, uint64_t *total_mem, char name[128]);
+VLGP_API int vlgp_sync(vlgp_ctx *ctx);
+/* CUDA-event timer on the context's stream (the stream every kernel of this library is launched on). */
+VLGP_API int vlgp_timer_start(vlgp_ctx *ctx);
+VLGP_API int vlgp_timer_stop(vlgp_ctx *ctx, float *elapsed_ms);
+/* counters[0] = kernels launched by this library since vlgp_create, [1] = r x r SPD solves (E-step),
+ * [2] = W x W factorisations (H-step), [3] = NCCL collectives issued. */
+VLGP_API int vlgp_counters(vlgp_ctx *ctx, int64_t counters[4]);
+
+/* ---- model: replaces params["a","b","noise","sigma","omega","likelihood","rank","gp_noise","dt"] ---------------- */
+/* get_params, vlgp/preprocess.py:49-81.  poisson_mask[n] != 0 -> Poisson channel, 0 -> Gaussian. */
+VLGP_API int vlgp_set_model(vlgp_ctx *ctx, int n_neurons, int n_latents, int rank, const uint8_t *poisson_mask,
+                   double gp_noise, double dt);
+/* Any pointer may be NULL (left unchanged / not returned). */
+VLGP_API int vlgp_set_params(vlgp_ctx *ctx, const double *a, const double *b, const double *noise, const double *sigma,
+                    const double *omega);
+VLGP_API int vlgp_get_params(vlgp_ctx *ctx, double *a, double *b, double *noise, double *da, double *db, double *sigma,
+                    double *omega);
+
+/* ---- trial sets: replaces the list of trial dicts ------------------------------------------------------------------ */
+VLGP_API int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int *set_id);
+VLGP_API int vlgp_trials_free(vlgp_ctx *ctx, int set_id);
+VLGP_API int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydtype);
+VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w);
+VLGP_API int vlgp_trials_get_state(vlgp_ctx *ctx, int set_id, double *mu, double *v, double *w, double *dmu);
+
+/* ---- prior factor: gp.make_cholesky (vlgp/gp.py:150-162) over math.ichol_gauss (vlgp/math.py:76-126) ------------- */
+VLGP_API int vlgp_make_cholesky(vlgp_ctx *ctx, int set_id);
+/* G: L x length x rank; pivots: L x rank (-1 padded); ncol: L.  Any of the three may be NULL. */
+VLGP_API int vlgp_get_cholesky(vlgp_ctx *ctx, int set_id, int length, double *G, int32_t *pivots, int32_t *ncol);
+/* Inject a factor (tests: decouple E-step parity from pivot parity). */
+VLGP_API int vlgp_set_cholesky(vlgp_ctx *ctx, int set_id, int length, const double *G);
+
+/* ---- E-step: core.estep / infer_single_trial (vlgp/core.py:22-126), update_w (:419-442), update_v (:445-471) ------ */
+/* n_failed: number of (trial, latent, iteration) r x r systems that were not positive definite (their update is
+ * skipped exactly like the reference's except-branches, vlgp/core.py:92-94,112). */
+VLGP_API int vlgp_estep(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, int *n_failed);
+VLGP_API int vlgp_update_w(vlgp_ctx *ctx, int set_id);
+VLGP_API int vlgp_update_v(vlgp_ctx *ctx, int set_id, int *n_failed);
+
+/* ---- M-step: core.mstep (vlgp/core.py:129-249) --------------------------------------------------------------------- */
+/* n_fallback: number of per-neuron Newton systems that fell back to the gradient step (vlgp/core.py:194-198). */
+VLGP_API int vlgp_mstep(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double eps, double learning_rate,
+               double da_bound, double db_bound, int *n_fallback);
+
+/* ---- H-step objective: gp.construct_posterior_cov + gp.elbo (vlgp/gp.py:12-62,126-147) --------------------------- */
+/* Once per H-step (mu, w fixed during it): per-latent second moments of mu over the segments (all of length W). */
+VLGP_API int vlgp_hstep_prepare(vlgp_ctx *ctx, int set_id);
+/* hyper = (sigma^2, omega, eps) (already exponentiated).  Returns ll and d ll / d log(omega) (the only slot the
+ * reference's mask [0,1,0] keeps, vlgp/gp.py:16,85).  info != 0: K is not positive definite (vlgp/gp.py:17-20,132). */
+VLGP_API int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyper[3], double *ll, double *dll,
+                         int *info);
+
+/* ---- constraints and convergence bookkeeping (vlgp/core.py:300-305,350-354,366-416) ------------------------------ */
+/* mu <- (mu - shift) @ M for every bin; shift (L) and M (L x L, row-major) may be NULL (0 / identity). */
+VLGP_API int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M);
+/* out[0] = sum mu^2, out[1] = sum dmu^2 over all bins and latents (summed over ranks when a communicator is set). */
+VLGP_API int vlgp_norms(vlgp_ctx *ctx, int set_id, double out[2]);
+/* Per-latent sum(mu), sum(mu^2) and the bin count (summed over ranks when a communicator is set). */
+VLGP_API int vlgp_latent_moments(vlgp_ctx *ctx, int set_id, double *sum, double *sumsq, int64_t *count);
+
+/* ---- multi-GPU: one process per GPU, NCCL sum-allreduce of the M-/H-step sufficient statistics ------------------- */
+VLGP_API int vlgp_comm_unique_id(vlgp_ctx *ctx, const char *libnccl_path, char id[128]);
+VLGP_API int vlgp_comm_init(vlgp_ctx *ctx, const char *libnccl_path, int rank, int n_ranks, const char id[128]);
+/* In-place allreduce of a small host buffer through the device (op: 0 = sum, 1 = max). */
+VLGP_API int vlgp_comm_allreduce(vlgp_ctx *ctx, double *buf, int n, int op);
+
+/* ---- measurement helpers (used by bench.py only) ------------------------------------------------------------------ */
+/* Measured FP64 FMA peak (TFLOP/s) of this GPU with a register-resident DFMA loop, and with mma.sync.m8n8k4.f64. */
+VLGP_API int vlgp_peak_fp64(vlgp_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+/* Measured device-to-device copy bandwidth (GB/s, read + write bytes) on a buffer of nbytes. */
+VLGP_API int vlgp_peak_hbm(vlgp_ctx *ctx, uint64_t nbytes, double *gbs);
+/* Write nbytes (> L2) to evict the L2 between timed iterations. */
+VLGP_API int vlgp_flush_l2(vlgp_ctx *ctx);
+/* Average device time (ms) per launch of the kernel classes, accumulated with CUDA events when profiling is on:
+ * which: 0 = E-step, 1 = M-step statistics, 2 = H-step per-segment kernel, 3 = ichol.  n = launches accumulated. */
+VLGP_API int vlgp_profile_enable(vlgp_ctx *ctx, int on);
+VLGP_API int vlgp_profile_get(vlgp_ctx *ctx, int which, double *total_ms, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLGP_B200_H */

@@ -1,0 +1,104 @@
+"""CPU-only checks of the C-ABI boundary: the shared library builds/loads, exports exactly the symbols that
+include/vlgp_b200.h declares, the ctypes table covers all of them, and the product path fails loudly (no CPU
+fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "vlgp_b200.h")).read()
+    return sorted(set(re.findall(r"VLGP_API\s+[\w\s\*]+?\b(vlgp_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from vlgp_b200 import _lib, build
+
+    if not os.path.exists(_lib.lib_path()):
+        build.build()
+    return _lib.lib_path()
+
+
+def test_header_symbols_are_exported(libpath):
+    names = _declared()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(libpath)
+    for n in names:
+        assert hasattr(lib, n), "libvlgp_b200.so does not export %s" % n
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (vlgp_\w+)", out)))
+    assert exported == names, "exported symbols differ from the header: %s" % (set(exported) ^ set(names))
+
+
+def test_ctypes_table_matches_header(libpath):
+    from vlgp_b200 import _lib
+
+    assert sorted(_lib.EXPORTS) == _declared()
+    _lib.load()
+
+
+def test_no_cpu_fallback(libpath):
+    """Without a CUDA device every entry point raises; nothing is computed on the host."""
+    from vlgp_b200 import _lib, engine, core
+
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    rc = lib.vlgp_create(0, ctypes.byref(ctx))
+    if rc == 0:
+        lib.vlgp_destroy(ctx)
+        pytest.skip("a GPU is present")
+    assert rc < 0 and lib.vlgp_last_error(None)
+    engine.reset_engine()
+    trials = [dict(y=np.zeros((50, 4)), mu=np.zeros((50, 2)), v=np.zeros((50, 2)), w=np.zeros((50, 2)))]
+    params = dict(a=np.zeros((2, 4)), b=np.zeros((1, 4)), noise=np.ones(4), sigma=np.ones(2), omega=np.full(2, 1e-2),
+                  likelihood=np.array(["poisson"] * 4), zdim=2, ydim=4, xdim=1, rank=50, gp_noise=1e-4, dt=1)
+    from vlgp_b200.preprocess import get_config
+
+    with pytest.raises(_lib.VlgpNativeError):
+        core.estep(trials, params, get_config())
+    with pytest.raises(_lib.VlgpNativeError):
+        core.mstep(trials, params, get_config())
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    from vlgp_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setenv("VLGP_B200_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.VlgpNativeError):
+        _lib.load()
+
+
+def test_host_surface_matches_reference_defaults():
+    from vlgp_b200.preprocess import get_config, get_params
+    from oracle import vlgp_oracle as orc
+
+    cfg = get_config(max_iter=7, bogus=1)
+    ref = orc.default_config(max_iter=7)
+    assert cfg == ref and "bogus" not in cfg
+    p = get_params([dict(y=np.zeros((10, 4)))], 2, omega_bound=cfg["omega_bound"], lik="gaussian", history=0)
+    assert p["xdim"] == 1 and p["rank"] == 50 and list(p["likelihood"]) == ["gaussian"] * 4
+    assert np.allclose(p["omega"], 5e-2)
+
+
+def test_cut_trials_views_and_rng_stream():
+    from vlgp_b200.util import cut_trials
+    from oracle import vlgp_oracle as orc
+
+    T = 230
+    tr = dict(y=np.zeros((T, 3)), x=np.ones((T, 1, 3)), mu=np.arange(T * 2.0).reshape(T, 2), w=np.zeros((T, 2)),
+              v=np.zeros((T, 2)))
+    np.random.seed(3)
+    segs = cut_trials([tr], {}, {"window": 50})
+    np.random.seed(3)
+    starts = orc.cut_trial_starts(T, 50)
+    assert [int(s["mu"][0, 0]) // 2 for s in segs] == starts.tolist()
+    assert all(np.shares_memory(s["mu"], tr["mu"]) for s in segs)
+    assert segs.dtype == object and all(s["y"].shape == (50, 3) for s in segs)

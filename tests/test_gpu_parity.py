@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path (through the ctypes C ABI) against the golden vectors of the unmodified reference
+(tests/golden/*.npz, made by oracle/make_golden.py) and against the NumPy oracle on seeded inputs.
+
+Tolerances (fp64 device arithmetic, stated per SURVEY.md section 8(c)):
+  single step (E-step, M-step, update_w/v):  <= 1e-10 relative to the largest entry of the reference output
+  H-step objective:                          ll <= 1e-9 relative, dll <= 1e-7 relative (K has condition number ~1e6)
+  three vem iterations / full fit:           <= 1e-5 relative on posterior means (north-star tolerance)
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def vl():
+    import vlgp_b200
+    from vlgp_b200 import core, gp, engine  # noqa: F401
+
+    engine.get_engine()        # fail loudly here if the native library / GPU is missing
+    return vlgp_b200
+
+
+def _segs(g, p, names=("mu", "v", "w", "dmu")):
+    n = g[p + "in_mu"].shape[0]
+    N = g[p + "y"].shape[2]
+    return [dict(y=g[p + "y"][i].astype(float), x=np.ones((g[p + "y"].shape[1], 1, N)),
+                 **{k: g[p + "in_" + k][i].copy() for k in names}) for i in range(n)]
+
+
+def _params(g, p, poisson=None):
+    poisson = g[p + "poisson"] if poisson is None else poisson
+    a = g[p + "in_a"].copy()
+    return dict(a=a, b=g[p + "in_b"].copy(), noise=g[p + "in_noise"].copy(), omega=g[p + "in_omega"].copy(),
+                sigma=g[p + "in_sigma"].copy(), da=np.zeros_like(a), db=np.zeros_like(g[p + "in_b"]),
+                likelihood=np.where(poisson, "poisson", "gaussian"), zdim=a.shape[0], ydim=a.shape[1], xdim=1,
+                rank=50, gp_noise=1e-4, dt=1)
+
+
+def _cfg(**kw):
+    from vlgp_b200.preprocess import get_config
+
+    return get_config(**kw)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def test_ichol_pivots_and_factor(vl):
+    from vlgp_b200.gp import make_cholesky
+    from oracle import vlgp_oracle as orc
+
+    g = load_golden("ichol")
+    omegas = np.array([5e-4, 5e-3, 5e-2])
+    eng = __import__("vlgp_b200.engine", fromlist=["get_engine"]).get_engine()
+    params = dict(ydim=3, zdim=3, xdim=1, rank=50, gp_noise=1e-4, dt=1, likelihood=np.array(["poisson"] * 3),
+                  sigma=np.ones(3), omega=omegas)
+    eng.ensure_model(params)
+    eng.push_params(params, which=("sigma", "omega"))
+    for n in (50, 200, 500, 1000, 2000):
+        with eng.new_trials([n]) as ts:
+            ts.make_cholesky()
+            G, piv, ncol = ts.get_cholesky(n, with_pivots=True)
+        for l, om in enumerate(omegas):
+            key = "n%d_w%g" % (n, om)
+            ref_piv = g[key + "_piv"]
+            assert int(ncol[l]) == int(g[key + "_ncol"]) == len(ref_piv), key
+            assert np.array_equal(piv[l, :len(ref_piv)], ref_piv), key
+            assert np.all(piv[l, len(ref_piv):] == -1)
+            Gref = orc.ichol_gauss(n, om, 50)
+            assert relerr(G[l], Gref) < 1e-12, key
+            if n <= 200:
+                assert relerr(G[l], g[key + "_G"]) < 1e-12
+    # sigma scaling and the drop-in surface
+    trials = [dict(y=np.zeros((50, 3))), dict(y=np.zeros((120, 3)))]
+    params["sigma"] = np.array([1.0, 0.5, 2.0])
+    make_cholesky(trials, params, None)
+    assert sorted(params["cholesky"]) == [50, 120] and params["cholesky"][120].shape == (3, 120, 50)
+    for l in range(3):
+        assert relerr(params["cholesky"][120][l], orc.ichol_gauss(120, omegas[l], 50) * params["sigma"][l]) < 1e-12
+
+
+def test_ichol_known_answer_full_rank(vl):
+    """The reference's own known-answer test (tests/test_math.py:7-14) at rank 60 <= VLGP_MAX_RANK: G G' == K."""
+    eng = __import__("vlgp_b200.engine", fromlist=["get_engine"]).get_engine()
+    n, omega = 60, 1.0
+    params = dict(ydim=2, zdim=1, xdim=1, rank=60, gp_noise=1e-4, dt=1, likelihood=np.array(["poisson"] * 2),
+                  sigma=np.ones(1), omega=np.array([omega]))
+    eng.ensure_model(params)
+    eng.push_params(params, which=("sigma", "omega"))
+    with eng.new_trials([n]) as ts:
+        ts.make_cholesky()
+        G = ts.get_cholesky(n)[0]
+    K = np.exp(-omega * (np.arange(n)[:, None] - np.arange(n)[None, :]) ** 2)
+    assert np.allclose(K, G @ G.T)
+    assert relerr(G, load_golden("ichol")["fullrank_n60_G"]) < 1e-10
+
+
+@pytest.mark.parametrize("case", ["poisson_it1", "poisson_it25", "mixed_it1", "mixed_it25", "map_it3"])
+def test_estep_golden(vl, case):
+    from vlgp_b200 import core
+
+    g = load_golden("estep")
+    p = case + "_"
+    segs = _segs(g, p)
+    params = _params(g, p)
+    params["cholesky"] = {50: g[p + "G"]}
+    cfg = _cfg(Eniter=int(case.split("it")[1]), method="MAP" if case.startswith("map") else "VB")
+    core.estep(segs, params, cfg)
+    for k in ("mu", "v", "w", "dmu"):
+        got = np.stack([s[k] for s in segs])
+        scale = g[p + "out_mu"] if k == "dmu" else g[p + "out_" + k]
+        assert np.max(np.abs(got - g[p + "out_" + k])) <= STEP_TOL * np.max(np.abs(scale)), k
+
+
+@pytest.mark.parametrize("case", ["poisson_it1", "poisson_it25", "mixed_it1", "mixed_it25"])
+def test_mstep_golden(vl, case):
+    from vlgp_b200 import core
+
+    g = load_golden("mstep")
+    p = case + "_"
+    segs = _segs(g, p)
+    params = _params(g, p)
+    cfg = _cfg(Mniter=int(case.split("it")[1]))
+    core.mstep(segs, params, cfg)
+    for k in ("a", "b", "noise", "da", "db"):
+        assert relerr(params[k], g[p + "out_" + k]) < STEP_TOL, k
+    assert params["b"].shape == g[p + "out_b"].shape
+
+
+def test_hstep_objective_golden(vl):
+    from vlgp_b200.core import Session
+
+    g = load_golden("hstep")
+    n = g["mu"].shape[0]
+    segs = [dict(y=np.zeros((50, 2)), mu=g["mu"][i].copy(), w=g["w"][i].copy(), v=np.zeros((50, 2))) for i in range(n)]
+    params = dict(a=np.zeros((2, 2)), b=np.zeros((1, 2)), noise=np.ones(2), omega=g["omega0"].copy(), sigma=np.ones(2),
+                  likelihood=np.array(["poisson"] * 2), zdim=2, ydim=2, xdim=1, rank=50, gp_noise=1e-4, dt=1)
+    with Session(segs, params, upload_factors=False) as s:
+        s.ts.hstep_prepare()
+        for l in range(2):
+            for i, om in enumerate(g["omegas"]):
+                ll, dll, info = s.ts.hstep_objective(l, np.array([1.0, om, 1e-4]))
+                assert info == 0
+                assert abs(ll - g["ll_l%d" % l][i]) < 1e-9 * abs(g["ll_l%d" % l][i])
+                assert abs(dll - g["dll_l%d" % l][i][1]) < 1e-7 * max(abs(g["dll_l%d" % l][i][1]), 1.0)
+
+
+def test_hstep_whole_golden(vl):
+    from vlgp_b200 import core
+
+    g = load_golden("hstep")
+    n = g["mu"].shape[0]
+    segs = [dict(y=np.zeros((50, 2)), mu=g["mu"][i].copy(), w=g["w"][i].copy(), v=np.zeros((50, 2))) for i in range(n)]
+    params = dict(a=np.zeros((2, 2)), b=np.zeros((1, 2)), noise=np.ones(2), omega=g["omega0"].copy(), sigma=np.ones(2),
+                  likelihood=np.array(["poisson"] * 2), zdim=2, ydim=2, xdim=1, rank=50, gp_noise=1e-4, dt=1)
+    cfg = _cfg()
+    core.hstep(segs, params, cfg)
+    assert relerr(params["omega"], g["omega_after"]) < 1e-6
+    assert relerr(params["sigma"], g["sigma_after"]) < 1e-12
+    Gd = params["cholesky"][50]
+    assert relerr(Gd @ Gd.transpose(0, 2, 1), g["G_after"] @ g["G_after"].transpose(0, 2, 1)) < 1e-5
+
+
+def test_update_w_v_and_long_trial_estep_golden(vl):
+    from vlgp_b200 import core
+    from vlgp_b200.gp import make_cholesky
+
+    g = load_golden("update_wv")
+    y = g["y"].astype(float)
+    N = y.shape[2]
+    trials = [dict(y=y[i], x=np.ones((y.shape[1], 1, N)), mu=g["in_mu"][i].copy(), v=g["in_v"][i].copy())
+              for i in range(y.shape[0])]
+    L = g["a"].shape[0]
+    params = dict(a=g["a"].copy(), b=g["b"].copy(), noise=g["noise"].copy(), omega=g["omega"].copy(),
+                  sigma=g["sigma"].copy(), zdim=L, ydim=N, xdim=1, rank=50, gp_noise=1e-4, dt=1,
+                  likelihood=np.array(["poisson"] * N))
+    cfg = _cfg(Eniter=3)
+    make_cholesky(trials, params, cfg)
+    core.update_w(trials, params, cfg)
+    core.update_v(trials, params, cfg)
+    assert relerr(np.stack([t["w"] for t in trials]), g["out_w"]) < STEP_TOL
+    assert relerr(np.stack([t["v"] for t in trials]), g["out_v"]) < STEP_TOL
+    for t in trials:
+        t["dmu"] = np.zeros_like(t["mu"])
+    core.estep(trials, params, cfg)
+    for k in ("mu", "v", "w", "dmu"):
+        scale = g["infer_mu"] if k == "dmu" else g["infer_" + k]
+        assert np.max(np.abs(np.stack([t[k] for t in trials]) - g["infer_" + k])) < STEP_TOL * np.max(np.abs(scale)), k
+
+
+def test_vem_three_iterations_golden(vl):
+    from vlgp_b200 import core
+    from vlgp_b200.gp import make_cholesky
+
+    g = load_golden("vem")
+    segs = _segs(g, "")
+    N = g["y"].shape[2]
+    params = _params(g, "", poisson=np.ones(N, bool))
+    cfg = _cfg(max_iter=3, min_iter=3)
+    make_cholesky(segs, params, cfg)
+    core.vem(segs, params, cfg)
+    assert cfg["runtime"]["it"] == int(g["n_it"])
+    assert len(cfg["runtime"]["em_elapsed"]) == 3
+    assert relerr(params["omega"], g["out_omega"]) < 1e-5
+    for k in ("a", "b"):
+        assert relerr(params[k], g["out_" + k]) < 1e-5, k
+    assert relerr(np.stack([s["mu"] for s in segs]), g["out_mu"]) < 1e-5
+    assert relerr(np.stack([s["v"] for s in segs]), g["out_v"]) < 1e-5
+
+
+def test_fit_tutorial_golden(vl):
+    """Whole fit() on BASELINE config 1 (10 x 200 x 30 x 3) against the reference run with the same global seed."""
+    from vlgp_b200.synth import make_trials
+
+    g = load_golden("fit_tutorial")
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    assert np.array_equal(np.stack([t["y"] for t in trials]), g["y"])
+    np.random.seed(0)
+    res = vl.fit(trials, 3, max_iter=3, min_iter=3)
+    assert set(res) == {"trials", "params", "config"}
+    assert relerr(res["params"]["initial"]["a"], g["initial_a"]) < 1e-9      # same FactorAnalysis initialisation
+    mu = np.stack([t["mu"] for t in res["trials"]])
+    assert relerr(mu, g["mu"]) < 1e-5
+    assert relerr(res["params"]["a"], g["a"]) < 1e-5
+    assert relerr(res["params"]["b"], g["b"]) < 1e-5
+    assert relerr(res["params"]["omega"], g["omega"]) < 1e-5
+    assert relerr(np.stack([t["v"] for t in res["trials"]]), g["v"]) < 1e-5
+    for k in ("a", "b", "noise", "sigma", "omega", "da", "db", "cholesky", "rank", "gp_noise", "dt", "likelihood",
+              "xdim", "ydim", "zdim", "transform", "initial"):
+        assert k in res["params"], k
+    for k in ("mu", "v", "w", "dmu", "x", "cut", "y", "ID"):
+        assert k in res["trials"][0], k
+    assert res["params"]["cholesky"][200].shape == (3, 200, 50)
+    assert set(res["config"]["runtime"]) >= {"it", "e_elapsed", "m_elapsed", "h_elapsed", "em_elapsed"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# seeded comparisons with the oracle at sizes it finishes in seconds, and properties at full size
+# ----------------------------------------------------------------------------------------------------------------------
+def _problem(seed, n_trials, T, N, L, lik=None, window=50):
+    from vlgp_b200.synth import make_trials
+    from oracle import vlgp_oracle as orc
+
+    rng = np.random.default_rng(seed)
+    trials = make_trials(n_trials, T, N, L, seed=seed + 100)
+    poisson = np.ones(N, bool) if lik is None else np.asarray(lik) == "poisson"
+    params = dict(a=0.3 * rng.standard_normal((L, N)), b=np.full((1, N), np.log(0.08)), noise=0.5 + rng.random(N),
+                  omega=np.exp(rng.uniform(np.log(2e-3), np.log(4e-2), L)), sigma=np.ones(L),
+                  likelihood=np.where(poisson, "poisson", "gaussian"), zdim=L, ydim=N, xdim=1, rank=50, gp_noise=1e-4,
+                  dt=1)
+    params["da"] = np.zeros_like(params["a"])
+    params["db"] = np.zeros_like(params["b"])
+    segs = []
+    for tr in trials:
+        for s in range(0, tr["y"].shape[0] - window + 1, window):
+            y = tr["y"][s:s + window].copy()
+            y[:, ~poisson] += 0.3 * rng.standard_normal((window, int((~poisson).sum())))
+            segs.append(dict(y=y, x=np.ones((window, 1, N)), mu=0.5 * rng.standard_normal((window, L)),
+                             v=np.zeros((window, L)), w=np.zeros((window, L)), dmu=np.zeros((window, L))))
+    params["cholesky"] = orc.make_cholesky([window], params["omega"], params["sigma"], 50)
+    orc.update_w(segs, params)
+    orc.update_v(segs, params, orc.default_config())
+    return segs, params
+
+
+@pytest.mark.parametrize("N,L,lik", [(100, 5, None), (37, 10, None), (20, 4, ["poisson"] * 12 + ["gaussian"] * 8)])
+def test_estep_mstep_vs_oracle_seeded(vl, N, L, lik):
+    from vlgp_b200 import core
+    from oracle import vlgp_oracle as orc
+
+    segs, params = _problem(11, 2, 150, N, L, lik)
+    cfg = _cfg(Eniter=4, Mniter=3)
+    s_ref, p_ref = copy.deepcopy(segs), copy.deepcopy(params)
+    orc.estep(s_ref, p_ref, cfg)
+    core.estep(segs, params, cfg)
+    for k in ("mu", "v", "w", "dmu"):
+        ref = np.stack([s[k] for s in s_ref])
+        scale = np.stack([s["mu"] for s in s_ref]) if k == "dmu" else ref
+        assert np.max(np.abs(np.stack([s[k] for s in segs]) - ref)) <= STEP_TOL * np.max(np.abs(scale)), k
+    orc.mstep(s_ref, p_ref, cfg)
+    core.mstep(segs, params, cfg)
+    for k in ("a", "b", "noise", "da", "db"):
+        assert relerr(params[k], p_ref[k]) < STEP_TOL, k
+
+
+def test_estep_config2_shape_subset_vs_oracle(vl):
+    """BASELINE config 2 shape (T=1000 trials cut in 50-bin windows, N=100, L=5): all 5120 segments run on the GPU; a
+    random subset of 6 segments is checked against the oracle, and every segment against invariants."""
+    from vlgp_b200 import core
+    from oracle import vlgp_oracle as orc
+
+    segs, params = _problem(5, 256, 1000, 100, 5)
+    assert len(segs) == 5120
+    cfg = _cfg(Eniter=25)
+    pick = np.random.default_rng(0).choice(len(segs), 6, replace=False)
+    s_ref = [copy.deepcopy(segs[i]) for i in pick]
+    orc.estep(s_ref, copy.deepcopy(params), cfg)
+    core.estep(segs, params, cfg)
+    for j, i in enumerate(pick):
+        for k in ("mu", "v", "w"):
+            assert relerr(segs[i][k], s_ref[j][k]) < STEP_TOL, (i, k)
+    v = np.stack([s["v"] for s in segs])
+    w = np.stack([s["w"] for s in segs])
+    prior_var = np.einsum("ltr,ltr->tl", params["cholesky"][50], params["cholesky"][50])
+    assert np.all(v > 0) and np.all(v <= prior_var[None] * (1 + 1e-12))     # posterior variance below the prior's
+    assert np.all(w > 0) and np.all(np.isfinite(np.stack([s["mu"] for s in segs])))
+    # idempotence of update_w / update_v at the E-step's fixed point of (w, v): recomputing w from (mu, v) reproduces it
+    w_before = w.copy()
+    core.update_w(segs, params, cfg)
+    assert relerr(np.stack([s["w"] for s in segs]), w_before) < 1e-6
+
+
+def test_overlapping_windows_and_unequal_lengths(vl):
+    """T not a multiple of the window (config 3 regime): segments overlap, state is written back through views, and
+    the final infer runs on trials of different lengths (one prior factor per unique length)."""
+    from vlgp_b200.synth import make_trials
+
+    trials = make_trials(3, (130, 170), 12, 2, seed=3)
+    lengths = [t["y"].shape[0] for t in trials]
+    assert len(set(lengths)) > 1
+    np.random.seed(1)
+    res = vl.fit(trials, 2, max_iter=2, min_iter=2)
+    assert sorted(res["params"]["cholesky"]) == sorted(set(lengths))
+    for t in res["trials"]:
+        assert t["mu"].shape == (t["y"].shape[0], 2) and np.all(np.isfinite(t["mu"])) and np.all(t["v"] > 0)
+
+
+def test_errors_are_loud(vl):
+    from vlgp_b200 import core
+    from vlgp_b200._lib import VlgpNativeError
+
+    segs, params = _problem(2, 1, 50, 6, 2)
+    del params["cholesky"]
+    with pytest.raises(KeyError):
+        core.estep(segs, params, _cfg())
+    segs[0]["x"] = np.zeros((50, 1, 6))
+    with pytest.raises(NotImplementedError):
+        core.mstep(segs, params, _cfg())
+    eng = __import__("vlgp_b200.engine", fromlist=["get_engine"]).get_engine()
+    with pytest.raises(VlgpNativeError):
+        eng._ck(eng.lib.vlgp_trials_free(eng.ctx, 12345), "trials_free")

@@ -1,0 +1,309 @@
+"""Variational-EM engine: the reference's ``(trials, params, config)`` in-place functions, executed on the GPU.
+
+Drop-in for vlgp/core.py: ``vem`` (:269-359), ``estep`` (:123-126), ``mstep`` (:129-249), ``hstep`` (:252-257),
+``infer`` (:260-266), ``update_w`` (:419-442), ``update_v`` (:445-471), ``constrain_loading`` (:392-416),
+``constrain_latent`` (:366-389).  Each function packs the dicts into a device ``Session``, calls the C ABI
+(include/vlgp_b200.h) and unpacks the result with the reference's aliasing rules: ``mu`` and ``v`` are updated IN
+PLACE (segments made by ``cut_trials`` are views of their trial), ``w`` and ``dmu`` are rebound.  ``vem`` keeps one
+session for the whole loop, so host<->device traffic is one upload before and one download after the iterations
+(plus the tiny parameter arrays every iteration).  There is no host implementation of any step: without the native
+library every function raises ``VlgpNativeError``.
+"""
+from __future__ import annotations
+
+import logging
+import time
+
+import numpy as np
+
+from .engine import Engine, TrialSet, get_engine, pack_y
+
+__all__ = ["vem", "estep", "mstep", "hstep", "infer", "update_w", "update_v", "constrain_loading", "constrain_latent",
+           "Session"]
+
+logger = logging.getLogger(__name__)
+
+
+def _echo(msg):
+    try:
+        import click
+
+        click.echo(msg)
+    except Exception:  # pragma: no cover
+        print(msg)
+
+
+class Session:
+    """Device copy of a list of trials plus the current parameters."""
+
+    def __init__(self, trials, params, engine: Engine = None, upload_factors=True):
+        self.eng = engine or get_engine()
+        eng = self.eng
+        eng.ensure_model(params)
+        eng.push_params(params)
+        self.n = len(trials)
+        lengths = [tr["y"].shape[0] for tr in trials]
+        for tr in trials:
+            x = tr.get("x")
+            if x is not None and (x.ndim != 3 or x.shape[1] != 1 or x.min() != 1 or x.max() != 1):
+                raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
+        self.ts: TrialSet = eng.new_trials(lengths)
+        try:
+            y, ydt = pack_y([tr["y"] for tr in trials])
+            self.ts.set_y(y, ydt)
+            L = eng.L
+
+            def cat(key):
+                parts = [tr[key] if tr.get(key) is not None else np.zeros((n, L)) for tr, n in zip(trials, lengths)]
+                return np.concatenate(parts, axis=0) if len(parts) > 1 else parts[0]
+
+            self.ts.set_state(cat("mu"), cat("v"), cat("w"))
+            chol = params.get("cholesky") if upload_factors else None
+            self.have_factors = False
+            if chol:
+                uniq = sorted(set(lengths))
+                if all(t in chol for t in uniq):
+                    for t in uniq:
+                        self.ts.set_cholesky(t, chol[t])
+                    self.have_factors = True
+        except Exception:
+            self.ts.free()
+            raise
+
+    def require_factors(self):
+        if not self.have_factors:
+            raise KeyError("params['cholesky'] lacks the prior factor of a trial length: call make_cholesky first")
+
+    def make_cholesky(self, params):
+        """Prior factors for this set's lengths from params['sigma'/'omega'], on device; mirrored into
+        params['cholesky'] (REPLACING the dict, like vlgp/gp.py:158)."""
+        self.eng.push_params(params, which=("sigma", "omega"))
+        self.ts.make_cholesky()
+        params["cholesky"] = {int(t): self.ts.get_cholesky(int(t)) for t in sorted(set(self.ts.lengths.tolist()))}
+        self.have_factors = True
+
+    def pull(self, trials, which=("mu", "v", "w", "dmu")):
+        st = self.ts.get_state(which)
+        for i, tr in enumerate(trials):
+            s0 = int(self.ts.starts[i])
+            s1 = s0 + int(self.ts.lengths[i])
+            for k in which:
+                val = st[k][s0:s1]
+                if k in ("mu", "v") and isinstance(tr.get(k), np.ndarray) and tr[k].shape == val.shape \
+                        and tr[k].dtype == np.float64:
+                    tr[k][...] = val            # in place: segment arrays are views of the parent trial
+                else:
+                    tr[k] = val.copy()
+
+    def close(self):
+        self.ts.free()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# single steps (stateless: upload, run, download)
+# ----------------------------------------------------------------------------------------------------------------------
+def estep(trials, params, config):
+    """Update the variational posterior q (E-step) of every trial."""
+    if config["Eniter"] < 1:
+        return
+    with Session(trials, params) as s:
+        s.require_factors()
+        nfail = s.ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+        if nfail:
+            logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
+        s.pull(trials)
+
+
+def infer(trials, params, config):
+    """E-step with Eniter := max_iter on the given (uncut) trials -- vlgp/core.py:260-266."""
+    niter = config["Eniter"]
+    config["Eniter"] = config["max_iter"]
+    t0 = time.perf_counter()
+    try:
+        estep(trials, params, config)
+    finally:
+        config["Eniter"] = niter
+    _echo("{:.2f}s".format(time.perf_counter() - t0))
+
+
+def update_w(trials, params, config):
+    with Session(trials, params, upload_factors=False) as s:
+        s.ts.update_w()
+        s.pull(trials, ("w",))
+    for tr in trials:
+        tr.setdefault("v", np.zeros_like(tr["mu"]))
+
+
+def update_v(trials, params, config):
+    if config["method"] != "VB":
+        return
+    for tr in trials:
+        tr.setdefault("w", np.zeros_like(tr["mu"]))
+        tr.setdefault("v", np.zeros_like(tr["mu"]))
+    with Session(trials, params) as s:
+        s.require_factors()
+        nfail = s.ts.update_v()
+        if nfail:
+            logger.error("Singular I + G'WG (%d systems)", nfail)
+        s.pull(trials, ("v",))
+
+
+def _mstep_dev(s: Session, params, config):
+    nfb = s.ts.mstep(config["Mniter"], config["use_hessian"], config["eps"], config["learning_rate"],
+                     config["da_bound"], config["db_bound"])
+    if nfb:
+        logger.error("M-step: %d Newton systems fell back to the gradient step", nfb)
+    s.eng.pull_params(params)
+
+
+def mstep(trials, params, config):
+    """Optimise loading and bias (M-step)."""
+    if config["Mniter"] < 1:
+        return
+    with Session(trials, params, upload_factors=False) as s:
+        _mstep_dev(s, params, config)
+
+
+def _hstep_dev(s: Session, trials, params, config):
+    from . import gp
+
+    gp._optimize_dev(s, params, config)
+
+
+def hstep(trials, params, config):
+    """GP hyperparameter update (H-step); also refreshes params['cholesky'] like vlgp/gp.py:97."""
+    if not config["Hstep"]:
+        return
+    with Session(trials, params, upload_factors=False) as s:
+        _hstep_dev(s, trials, params, config)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# constraints
+# ----------------------------------------------------------------------------------------------------------------------
+def _constrain_loading_dev(s: Session, params, config):
+    kind = config["constrain_loading"]
+    if not kind or kind == "none":
+        return
+    a = np.asarray(params["a"], dtype=float)
+    L = a.shape[0]
+    if kind == "svd":
+        _, _, vt = np.linalg.svd(a, full_matrices=False)
+        M = a @ vt.T
+        params["a"] = vt
+    elif kind == "fro":
+        sc = np.linalg.norm(a) + config["eps"]
+        params["a"] = a / sc
+        M = np.eye(L) * sc
+    else:
+        sc = np.linalg.norm(a, ord=kind, axis=1, keepdims=True) + config["eps"]
+        params["a"] = a / sc
+        M = np.diag(sc[:, 0])
+    s.eng.push_params(params, which=("a",))
+    s.ts.latent_affine(None, M)
+
+
+def _constrain_latent_dev(s: Session, params, config):
+    kind = config["constrain_latent"]
+    if not kind or kind == "none":
+        return
+    tot, sq, cnt = s.ts.latent_moments()
+    mean = tot / cnt
+    std = np.sqrt(np.maximum(sq / cnt - mean * mean, 0.0))
+    shift, M = None, None
+    if kind in ("location", "both"):
+        shift = mean
+        params["b"] = np.array(params["b"], dtype=float)
+        params["b"][0, :] += mean @ params["a"]
+    if kind in ("scale", "both"):
+        M = np.diag(1.0 / std)
+        params["a"] = np.asarray(params["a"], dtype=float) * std[:, None]
+    s.eng.push_params(params, which=("a", "b"))
+    s.ts.latent_affine(shift, M)
+
+
+def constrain_loading(trials, params, config):
+    """Normalise the loading matrix and rescale the latents accordingly."""
+    kind = config["constrain_loading"]
+    if not kind or kind == "none":
+        return
+    with Session(trials, params, upload_factors=False) as s:
+        _constrain_loading_dev(s, params, config)
+        s.pull(trials, ("mu",))
+
+
+def constrain_latent(trials, params, config):
+    """Centre / scale the posterior means and compensate in b / a."""
+    kind = config["constrain_latent"]
+    if not kind or kind == "none":
+        return
+    with Session(trials, params, upload_factors=False) as s:
+        _constrain_latent_dev(s, params, config)
+        s.pull(trials, ("mu",))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# outer loop
+# ----------------------------------------------------------------------------------------------------------------------
+def vem(trials, params, config, session: Session = None):
+    """Variational EM on (already cut) segments; fills config['runtime'] with the reference's keys."""
+    callbacks = config["callbacks"]
+    tol = config["tol"]
+    runtime = {"it": 0, "e_elapsed": [], "m_elapsed": [], "h_elapsed": [], "em_elapsed": []}
+    own = session is None
+    s = session or Session(trials, params)
+    try:
+        s.require_factors()
+        ts = s.ts
+        for it in range(config["max_iter"]):
+            runtime["it"] += 1
+            norm_mu = np.sqrt(ts.norms()[0])
+            norm_a = np.linalg.norm(params["a"])
+            norm_b = np.linalg.norm(params["b"])
+
+            t0 = time.perf_counter()
+            _constrain_loading_dev(s, params, config)
+            if config["Eniter"] >= 1:
+                nfail = ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+                if nfail:
+                    logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
+            t1 = time.perf_counter()
+            _constrain_latent_dev(s, params, config)
+            if config["Mniter"] >= 1:
+                _mstep_dev(s, params, config)
+            t2 = time.perf_counter()
+            if config["Hstep"]:
+                _hstep_dev(s, trials, params, config)
+            t3 = time.perf_counter()
+
+            runtime["e_elapsed"].append(t1 - t0)
+            runtime["m_elapsed"].append(t2 - t1)
+            runtime["h_elapsed"].append(t3 - t2)
+            runtime["em_elapsed"].append(t3 - t0)
+            config["runtime"] = runtime
+            _echo("Iteration {:4d}, E-step {:.2f}s, M-step {:.2f}s".format(runtime["it"], t1 - t0, t2 - t1))
+
+            if callbacks:
+                s.pull(trials)              # callbacks see coherent host dicts
+                for cb in callbacks:
+                    try:
+                        cb(trials, params, config)
+                    except RuntimeError:
+                        logger.error("Callback {} failed".format(cb))
+
+            norm_dmu = np.sqrt(ts.norms()[1])
+            converged = (norm_dmu < tol * norm_mu and np.linalg.norm(params["da"]) < tol * norm_a
+                         and np.linalg.norm(params["db"]) < tol * norm_b)
+            if converged and it + 1 >= config["min_iter"]:
+                break
+        s.pull(trials)
+    finally:
+        if own:
+            s.close()

@@ -1,0 +1,797 @@
+// C ABI of libvlgp_b200.so (include/vlgp_b200.h): context, model/trial-set buffers in HBM, entry points, and the
+// small elementwise / reduction kernels of the vem bookkeeping (vlgp/core.py:300-305,350-354,366-416).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <map>
+
+#include "common.cuh"
+#include "linalg.cuh"
+
+// kernels.cu files
+int vlgp_launch_ichol(vlgp_ctx *ctx, PriorFactor &pf, const double *d_omega, const double *d_sigma, double *d_work);
+int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter, double dmu_bound, int method_vb);
+int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled);
+int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
+                      double da_bound, double db_bound);
+int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts);
+int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, int l, double sigmasq, double omega, double eps,
+                                double out5[5], int *info);
+void vlgp_comm_destroy(vlgp_ctx *ctx);
+
+static std::string g_create_error;
+
+int vlgp_fail(vlgp_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+namespace {
+
+__global__ void latent_affine_kernel(int64_t nbin, int L, double *mu, const double *__restrict__ shiftM, int has_shift,
+                                     int has_M) {
+    // shiftM: [0,L) shift, [L, L+L*L) M row-major
+    const int64_t bin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bin >= nbin) return;
+    double x[VLGP_MAX_L], o[VLGP_MAX_L];
+    for (int l = 0; l < L; ++l) x[l] = mu[bin * L + l] - (has_shift ? shiftM[l] : 0.0);
+    if (has_M) {
+        for (int k = 0; k < L; ++k) {
+            double s = 0.0;
+            for (int l = 0; l < L; ++l) s = fma(x[l], shiftM[L + l * L + k], s);
+            o[k] = s;
+        }
+        for (int k = 0; k < L; ++k) mu[bin * L + k] = o[k];
+    } else {
+        for (int l = 0; l < L; ++l) mu[bin * L + l] = x[l];
+    }
+}
+
+// part[b][0..2L+2): per-latent sum mu, per-latent sum mu^2, sum dmu^2 total, (unused)
+__global__ void __launch_bounds__(256) moments_kernel(int64_t nbin, int L, const double *__restrict__ mu,
+                                                      const double *__restrict__ dmu, double *part) {
+    __shared__ double red[32];
+    double sm[VLGP_MAX_L], sq[VLGP_MAX_L];
+    for (int l = 0; l < L; ++l) sm[l] = sq[l] = 0.0;
+    double dd = 0.0;
+    for (int64_t bin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bin < nbin; bin += (int64_t)gridDim.x * blockDim.x)
+        for (int l = 0; l < L; ++l) {
+            const double m = mu[bin * L + l], d = dmu[bin * L + l];
+            sm[l] += m;
+            sq[l] = fma(m, m, sq[l]);
+            dd = fma(d, d, dd);
+        }
+    const int K = 2 * L + 1;
+    for (int l = 0; l < L; ++l) {
+        const double a = block_sum(sm[l], red);
+        const double b = block_sum(sq[l], red);
+        if (threadIdx.x == 0) {
+            part[(size_t)blockIdx.x * K + l] = a;
+            part[(size_t)blockIdx.x * K + L + l] = b;
+        }
+    }
+    dd = block_sum(dd, red);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.x * K + 2 * L] = dd;
+}
+
+__global__ void reduce_parts_kernel3(const double *__restrict__ part, int G, int K, double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double s = 0.0;
+    for (int g = 0; g < G; ++g) s += part[(size_t)g * K + k];
+    out[k] = s;
+}
+
+// ---- peak probes ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double *out) {
+    double a[16];
+    const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *out) {
+    double c[8][2];
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void copy_kernel(const double4 *__restrict__ src, double4 *__restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+__global__ void fill_kernel(double4 *dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+}
+
+void free_set(TrialSet &ts) {
+    auto F = [](auto *&p) {
+        if (p) cudaFree((void *)p);
+        p = nullptr;
+    };
+    F(ts.d_len); F(ts.d_start); F(ts.d_fidx); F(ts.d_Gptr); F(ts.d_ncolptr); F(ts.d_y);
+    F(ts.d_mu); F(ts.d_v); F(ts.d_w); F(ts.d_dmu); F(ts.d_ra); F(ts.d_u); F(ts.d_minv);
+    F(ts.d_M); F(ts.d_K); F(ts.d_hpart); F(ts.d_hout);
+    for (auto &pf : ts.factors) {
+        F(pf.d_G); F(pf.d_ncol); F(pf.d_piv);
+    }
+    ts = TrialSet();
+}
+
+}   // namespace
+
+extern "C" {
+
+int vlgp_create(int device, vlgp_ctx **out) {
+    vlgp_ctx *ctx = nullptr;
+    if (!out) return vlgp_fail(nullptr, VLGP_ERR_ARG, "vlgp_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return vlgp_fail(nullptr, VLGP_ERR_CUDA, "vlgp_create: no CUDA device (%s)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return vlgp_fail(nullptr, VLGP_ERR_ARG, "vlgp_create: bad device %d", device);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return vlgp_fail(nullptr, VLGP_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx = new vlgp_ctx();
+    ctx->device = device;
+    cudaGetDeviceProperties(&ctx->prop, device);
+    if (ctx->prop.major < 10) {
+        int rc = vlgp_fail(nullptr, VLGP_ERR_UNSUPPORTED, "vlgp_create: device %s is sm_%d%d; this library is sm_100a only",
+                           ctx->prop.name, ctx->prop.major, ctx->prop.minor);
+        delete ctx;
+        return rc;
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->pev0) == cudaSuccess && cudaEventCreate(&ctx->pev1) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_flags, 16 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_flags, 16 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_pin, 4096) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_small, 4096) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_flags, 0, 16 * sizeof(int)) == cudaSuccess;
+    if (!ok) {
+        int rc = vlgp_fail(nullptr, VLGP_ERR_CUDA, "vlgp_create: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return VLGP_OK;
+}
+
+int vlgp_destroy(vlgp_ctx *ctx) {
+    if (!ctx) return VLGP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    vlgp_comm_destroy(ctx);
+    for (auto &ts : ctx->sets)
+        if (ts.used) free_set(ts);
+    auto F = [](auto *&p) {
+        if (p) cudaFree((void *)p);
+        p = nullptr;
+    };
+    F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db);
+    F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_small); F(ctx->d_flush);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->pev0); cudaEventDestroy(ctx->pev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VLGP_OK;
+}
+
+const char *vlgp_last_error(const vlgp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int vlgp_device_info(vlgp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, uint64_t *total_mem, char name[128]) {
+    if (!ctx) return VLGP_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (total_mem) *total_mem = ctx->prop.totalGlobalMem;
+    if (name) {
+        strncpy(name, ctx->prop.name, 127);
+        name[127] = 0;
+    }
+    return VLGP_OK;
+}
+
+int vlgp_sync(vlgp_ctx *ctx) {
+    if (!ctx) return VLGP_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+int vlgp_timer_start(vlgp_ctx *ctx) {
+    if (!ctx) return VLGP_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return VLGP_OK;
+}
+
+int vlgp_timer_stop(vlgp_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return VLGP_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return VLGP_OK;
+}
+
+int vlgp_counters(vlgp_ctx *ctx, int64_t c[4]) {
+    if (!ctx || !c) return VLGP_ERR_ARG;
+    for (int i = 0; i < 4; ++i) c[i] = ctx->counters[i];
+    return VLGP_OK;
+}
+
+// ---- model ------------------------------------------------------------------------------------------------------------
+int vlgp_set_model(vlgp_ctx *ctx, int N, int L, int rank, const uint8_t *poisson_mask, double gp_noise, double dt) {
+    if (!ctx) return VLGP_ERR_ARG;
+    REQUIRE(N >= 1 && L >= 1 && L <= 12, "set_model: need 1 <= n_latents <= 12 and n_neurons >= 1 (got %d, %d)", L, N);
+    REQUIRE(rank >= 1 && rank <= VLGP_MAX_RANK, "set_model: rank %d outside [1, %d]", rank, VLGP_MAX_RANK);
+    REQUIRE(poisson_mask != nullptr, "set_model: poisson_mask is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &ts : ctx->sets)
+        if (ts.used) free_set(ts);
+    auto F = [](auto *&p) {
+        if (p) cudaFree((void *)p);
+        p = nullptr;
+    };
+    F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db); F(ctx->d_mstat);
+    F(ctx->d_mpart);
+    ctx->mpart_grid = 0;
+    ctx->N = N; ctx->L = L; ctx->rank = rank; ctx->gp_noise = gp_noise; ctx->dt = dt;
+    CK(cudaMalloc(&ctx->d_poisson, N));
+    CK(cudaMalloc(&ctx->d_a, (size_t)L * N * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_da, (size_t)L * N * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_b, (size_t)N * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_db, (size_t)N * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_noise, (size_t)N * sizeof(double)));
+    const int nstat = L + L * (L + 1) / 2 + 4;
+    CK(cudaMalloc(&ctx->d_mstat, ((size_t)nstat * N + 8) * sizeof(double)));
+    CK(cudaMemcpy(ctx->d_poisson, poisson_mask, N, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_a, 0, (size_t)L * N * sizeof(double)));
+    CK(cudaMemset(ctx->d_da, 0, (size_t)L * N * sizeof(double)));
+    CK(cudaMemset(ctx->d_b, 0, (size_t)N * sizeof(double)));
+    CK(cudaMemset(ctx->d_db, 0, (size_t)N * sizeof(double)));
+    std::vector<double> ones(N, 1.0);
+    CK(cudaMemcpy(ctx->d_noise, ones.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->any_gauss = false;
+    for (int n = 0; n < N; ++n)
+        if (!poisson_mask[n]) ctx->any_gauss = true;
+    ctx->h_sigma.assign(L, 1.0);
+    ctx->h_omega.assign(L, 1e-3);
+    return VLGP_OK;
+}
+
+int vlgp_set_params(vlgp_ctx *ctx, const double *a, const double *b, const double *noise, const double *sigma,
+                    const double *omega) {
+    if (!ctx) return VLGP_ERR_ARG;
+    REQUIRE(ctx->N > 0, "set_params before set_model");
+    const size_t N = ctx->N, L = ctx->L;
+    CK(cudaSetDevice(ctx->device));
+    if (a) CK(cudaMemcpyAsync(ctx->d_a, a, L * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(ctx->d_b, b, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (noise) CK(cudaMemcpyAsync(ctx->d_noise, noise, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (sigma) ctx->h_sigma.assign(sigma, sigma + L);
+    if (omega) ctx->h_omega.assign(omega, omega + L);
+    CK(cudaStreamSynchronize(ctx->stream));     // host buffers are borrowed only for the duration of the call
+    return VLGP_OK;
+}
+
+int vlgp_get_params(vlgp_ctx *ctx, double *a, double *b, double *noise, double *da, double *db, double *sigma,
+                    double *omega) {
+    if (!ctx) return VLGP_ERR_ARG;
+    REQUIRE(ctx->N > 0, "get_params before set_model");
+    const size_t N = ctx->N, L = ctx->L;
+    CK(cudaSetDevice(ctx->device));
+    if (a) CK(cudaMemcpyAsync(a, ctx->d_a, L * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (da) CK(cudaMemcpyAsync(da, ctx->d_da, L * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(b, ctx->d_b, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (db) CK(cudaMemcpyAsync(db, ctx->d_db, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (noise) CK(cudaMemcpyAsync(noise, ctx->d_noise, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (sigma) std::copy(ctx->h_sigma.begin(), ctx->h_sigma.end(), sigma);
+    if (omega) std::copy(ctx->h_omega.begin(), ctx->h_omega.end(), omega);
+    return VLGP_OK;
+}
+
+// ---- trial sets -------------------------------------------------------------------------------------------------------
+int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int *set_id) {
+    if (!ctx) return VLGP_ERR_ARG;
+    REQUIRE(ctx->N > 0, "trials_create before set_model");
+    REQUIRE(n_trials >= 1 && lengths && set_id, "trials_create: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    int id = -1;
+    for (size_t i = 0; i < ctx->sets.size(); ++i)
+        if (!ctx->sets[i].used) { id = (int)i; break; }
+    if (id < 0) {
+        ctx->sets.emplace_back();
+        id = (int)ctx->sets.size() - 1;
+    }
+    TrialSet &ts = ctx->sets[id];
+    ts = TrialSet();
+    ts.used = true;
+    ts.n_trials = n_trials;
+    ts.h_len.assign(lengths, lengths + n_trials);
+    ts.h_start.resize(n_trials);
+    std::map<int, int> uniq;
+    int64_t off = 0;
+    ts.max_len = 0;
+    ts.min_len = 1 << 30;
+    for (int i = 0; i < n_trials; ++i) {
+        if (lengths[i] < 1) {
+            ts.used = false;
+            return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_create: trial %d has length %d", i, lengths[i]);
+        }
+        ts.h_start[i] = off;
+        off += lengths[i];
+        ts.max_len = std::max(ts.max_len, (int)lengths[i]);
+        ts.min_len = std::min(ts.min_len, (int)lengths[i]);
+        uniq.emplace(lengths[i], 0);
+    }
+    ts.nbin = off;
+    int k = 0;
+    for (auto &kv : uniq) kv.second = k++;
+    ts.factors.resize(uniq.size());
+    for (auto &kv : uniq) ts.factors[kv.second].length = kv.first;
+    ts.h_fidx.resize(n_trials);
+    for (int i = 0; i < n_trials; ++i) ts.h_fidx[i] = uniq[lengths[i]];
+
+    const size_t L = ctx->L, N = ctx->N, R = ctx->rank;
+    CK(cudaMalloc(&ts.d_len, n_trials * sizeof(int)));
+    CK(cudaMalloc(&ts.d_start, n_trials * sizeof(int64_t)));
+    CK(cudaMalloc(&ts.d_fidx, n_trials * sizeof(int)));
+    CK(cudaMemcpy(ts.d_len, ts.h_len.data(), n_trials * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ts.d_start, ts.h_start.data(), n_trials * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ts.d_fidx, ts.h_fidx.data(), n_trials * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<double *> gp(ts.factors.size());
+    std::vector<int *> np_(ts.factors.size());
+    for (size_t f = 0; f < ts.factors.size(); ++f) {
+        PriorFactor &pf = ts.factors[f];
+        CK(cudaMalloc(&pf.d_G, L * pf.length * R * sizeof(double)));
+        CK(cudaMemset(pf.d_G, 0, L * pf.length * R * sizeof(double)));
+        CK(cudaMalloc(&pf.d_ncol, L * sizeof(int)));
+        CK(cudaMemset(pf.d_ncol, 0, L * sizeof(int)));
+        CK(cudaMalloc(&pf.d_piv, L * R * sizeof(int)));
+        CK(cudaMemset(pf.d_piv, 0xff, L * R * sizeof(int)));
+        pf.h_ncol.assign(L, 0);
+        gp[f] = pf.d_G;
+        np_[f] = pf.d_ncol;
+    }
+    CK(cudaMalloc(&ts.d_Gptr, gp.size() * sizeof(double *)));
+    CK(cudaMalloc(&ts.d_ncolptr, np_.size() * sizeof(int *)));
+    CK(cudaMemcpy(ts.d_Gptr, gp.data(), gp.size() * sizeof(double *), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ts.d_ncolptr, np_.data(), np_.size() * sizeof(int *), cudaMemcpyHostToDevice));
+    const size_t nb = (size_t)ts.nbin;
+    CK(cudaMalloc(&ts.d_mu, nb * L * sizeof(double)));
+    CK(cudaMalloc(&ts.d_v, nb * L * sizeof(double)));
+    CK(cudaMalloc(&ts.d_w, nb * L * sizeof(double)));
+    CK(cudaMalloc(&ts.d_dmu, nb * L * sizeof(double)));
+    CK(cudaMalloc(&ts.d_ra, nb * L * sizeof(double)));
+    CK(cudaMalloc(&ts.d_u, nb * sizeof(double)));
+    CK(cudaMemset(ts.d_mu, 0, nb * L * sizeof(double)));
+    CK(cudaMemset(ts.d_v, 0, nb * L * sizeof(double)));
+    CK(cudaMemset(ts.d_w, 0, nb * L * sizeof(double)));
+    CK(cudaMemset(ts.d_dmu, 0, nb * L * sizeof(double)));
+    (void)N;
+    *set_id = id;
+    return VLGP_OK;
+}
+
+int vlgp_trials_free(vlgp_ctx *ctx, int set_id) {
+    TrialSet *ts = get_set(ctx, set_id);
+    if (!ts) return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_free: bad set %d", set_id);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_set(*ts);
+    return VLGP_OK;
+}
+
+int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydtype) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && y, "trials_set_y: bad set %d or NULL y", set_id);
+    REQUIRE(ydtype == VLGP_Y_F64 || ydtype == VLGP_Y_U8, "trials_set_y: bad dtype %d", ydtype);
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ts->nbin * ctx->N * (ydtype == VLGP_Y_U8 ? 1 : sizeof(double));
+    if (ts->d_y && ts->ydtype != ydtype) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(ts->d_y));
+        ts->d_y = nullptr;
+    }
+    if (!ts->d_y) CK(cudaMalloc(&ts->d_y, bytes));
+    ts->ydtype = ydtype;
+    CK(cudaMemcpyAsync(ts->d_y, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "trials_set_state: bad set %d", set_id);
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ts->nbin * ctx->L * sizeof(double);
+    if (mu) CK(cudaMemcpyAsync(ts->d_mu, mu, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (v) CK(cudaMemcpyAsync(ts->d_v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (w) CK(cudaMemcpyAsync(ts->d_w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+int vlgp_trials_get_state(vlgp_ctx *ctx, int set_id, double *mu, double *v, double *w, double *dmu) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "trials_get_state: bad set %d", set_id);
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ts->nbin * ctx->L * sizeof(double);
+    if (mu) CK(cudaMemcpyAsync(mu, ts->d_mu, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (v) CK(cudaMemcpyAsync(v, ts->d_v, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w) CK(cudaMemcpyAsync(w, ts->d_w, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dmu) CK(cudaMemcpyAsync(dmu, ts->d_dmu, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+// ---- prior factor -----------------------------------------------------------------------------------------------------
+int vlgp_make_cholesky(vlgp_ctx *ctx, int set_id) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "make_cholesky: bad set %d", set_id);
+    CK(cudaSetDevice(ctx->device));
+    const int L = ctx->L, R = ctx->rank;
+    for (int l = 0; l < L; ++l) {
+        ctx->h_pin[l] = ctx->h_omega[l];
+        ctx->h_pin[VLGP_MAX_L + l] = ctx->h_sigma[l];
+    }
+    CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, 2 * VLGP_MAX_L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double *work = nullptr;
+    CK(cudaMalloc(&work, (size_t)L * R * ts->max_len * sizeof(double)));
+    int rc = VLGP_OK;
+    for (auto &pf : ts->factors) {
+        rc = vlgp_launch_ichol(ctx, pf, ctx->d_small, ctx->d_small + VLGP_MAX_L, work);
+        if (rc) break;
+    }
+    if (!rc) {
+        for (auto &pf : ts->factors) {
+            cudaError_t e = cudaMemcpyAsync(pf.h_ncol.data(), pf.d_ncol, L * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e != cudaSuccess) rc = vlgp_fail(ctx, VLGP_ERR_CUDA, "make_cholesky: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(work);
+    if (!rc && e != cudaSuccess) rc = vlgp_fail(ctx, VLGP_ERR_CUDA, "make_cholesky: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+static PriorFactor *find_factor(TrialSet *ts, int length) {
+    for (auto &pf : ts->factors)
+        if (pf.length == length) return &pf;
+    return nullptr;
+}
+
+int vlgp_get_cholesky(vlgp_ctx *ctx, int set_id, int length, double *G, int32_t *pivots, int32_t *ncol) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "get_cholesky: bad set %d", set_id);
+    PriorFactor *pf = find_factor(ts, length);
+    REQUIRE(pf, "get_cholesky: no trial of length %d in set %d", length, set_id);
+    CK(cudaSetDevice(ctx->device));
+    const size_t L = ctx->L, R = ctx->rank;
+    if (G) CK(cudaMemcpyAsync(G, pf->d_G, L * length * R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pivots) CK(cudaMemcpyAsync(pivots, pf->d_piv, L * R * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ncol) CK(cudaMemcpyAsync(ncol, pf->d_ncol, L * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+int vlgp_set_cholesky(vlgp_ctx *ctx, int set_id, int length, const double *G) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && G, "set_cholesky: bad set %d or NULL G", set_id);
+    PriorFactor *pf = find_factor(ts, length);
+    REQUIRE(pf, "set_cholesky: no trial of length %d in set %d", length, set_id);
+    CK(cudaSetDevice(ctx->device));
+    const size_t L = ctx->L, R = ctx->rank;
+    // number of leading non-zero columns (trailing columns of an early-stopped factor are exactly zero)
+    for (size_t l = 0; l < L; ++l) {
+        int nc = 0;
+        for (size_t t = 0; t < (size_t)length; ++t)
+            for (int m = (int)R - 1; m >= nc; --m)
+                if (G[(l * length + t) * R + m] != 0.0) { nc = m + 1; break; }
+        pf->h_ncol[l] = nc;
+    }
+    CK(cudaMemcpyAsync(pf->d_G, G, L * length * R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(pf->d_ncol, pf->h_ncol.data(), L * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+// ---- E-step ---------------------------------------------------------------------------------------------------------
+static int read_flag(vlgp_ctx *ctx, int idx, int *out) {
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out) *out = ctx->h_flags[idx];
+    return VLGP_OK;
+}
+
+static int check_ready(vlgp_ctx *ctx, TrialSet *ts, const char *who) {
+    REQUIRE(ts, "%s: bad trial set", who);
+    REQUIRE(ts->d_y, "%s: y not set", who);
+    return VLGP_OK;
+}
+
+int vlgp_estep(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, int *n_failed) {
+    TrialSet *ts = get_set(ctx, set_id);
+    int rc = check_ready(ctx, ts, "estep");
+    if (rc) return rc;
+    if (n_failed) *n_failed = 0;
+    if (n_iter < 1) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    {
+        ProfScope ps(ctx, 0);
+        bool handled = false;
+        rc = vlgp_launch_estep_segments(ctx, ts, n_iter, dmu_bound, method_vb, &handled);
+        if (rc) return rc;
+        if (!handled) rc = vlgp_launch_estep_generic(ctx, ts, 0, n_iter, dmu_bound, method_vb);
+        if (rc) return rc;
+    }
+    ctx->counters[1] += (int64_t)ts->n_trials * ctx->L * n_iter * 2;
+    return read_flag(ctx, 0, n_failed);
+}
+
+int vlgp_update_w(vlgp_ctx *ctx, int set_id) {
+    TrialSet *ts = get_set(ctx, set_id);
+    int rc = check_ready(ctx, ts, "update_w");
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    rc = vlgp_launch_estep_generic(ctx, ts, 1, 1, 0.0, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+int vlgp_update_v(vlgp_ctx *ctx, int set_id, int *n_failed) {
+    TrialSet *ts = get_set(ctx, set_id);
+    int rc = check_ready(ctx, ts, "update_v");
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    rc = vlgp_launch_estep_generic(ctx, ts, 2, 1, 0.0, 1);
+    if (rc) return rc;
+    ctx->counters[1] += (int64_t)ts->n_trials * ctx->L;
+    return read_flag(ctx, 0, n_failed);
+}
+
+// ---- M-step ---------------------------------------------------------------------------------------------------------
+int vlgp_mstep(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double eps, double lr, double da_bound,
+               double db_bound, int *n_fallback) {
+    TrialSet *ts = get_set(ctx, set_id);
+    int rc = check_ready(ctx, ts, "mstep");
+    if (rc) return rc;
+    if (n_fallback) *n_fallback = 0;
+    if (n_iter < 1) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream));
+    rc = vlgp_launch_mstep(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound);
+    if (rc) return rc;
+    return read_flag(ctx, 1, n_fallback);
+}
+
+// ---- H-step ---------------------------------------------------------------------------------------------------------
+int vlgp_hstep_prepare(vlgp_ctx *ctx, int set_id) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "hstep_prepare: bad set %d", set_id);
+    REQUIRE(ts->min_len == ts->max_len, "hstep_prepare: all segments must have the same length (vlgp/gp.py:77-80)");
+    REQUIRE(ts->max_len <= VLGP_MAX_W, "hstep_prepare: window %d > %d", ts->max_len, VLGP_MAX_W);
+    CK(cudaSetDevice(ctx->device));
+    return vlgp_launch_hstep_prepare(ctx, ts);
+}
+
+int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyper[3], double *ll, double *dll,
+                         int *info) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && ts->h_prepared, "hstep_objective: call hstep_prepare first");
+    REQUIRE(latent >= 0 && latent < ctx->L && hyper && ll && dll && info, "hstep_objective: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    double o[5];
+    int rc = vlgp_launch_hstep_objective(ctx, ts, latent, hyper[0], hyper[1], hyper[2], o, info);
+    if (rc) return rc;
+    // number of segments over all ranks
+    double nseg = (double)ts->n_trials;
+    if (ctx->n_ranks > 1) {
+        double tmp = nseg;
+        rc = vlgp_comm_allreduce(ctx, &tmp, 1, 0);
+        if (rc) return rc;
+        nseg = tmp;
+    }
+    *ll = -0.5 * o[0] - 0.5 * o[3] - nseg * o[1];
+    *dll = 0.5 * (o[2] - o[4]);
+    return VLGP_OK;
+}
+
+// ---- constraints / bookkeeping ---------------------------------------------------------------------------------------
+int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "latent_affine: bad set %d", set_id);
+    if (!shift && !M) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int L = ctx->L;
+    for (int l = 0; l < L; ++l) ctx->h_pin[l] = shift ? shift[l] : 0.0;
+    for (int i = 0; i < L * L; ++i) ctx->h_pin[L + i] = M ? M[i] : 0.0;
+    CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, (L + L * L) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int nt = 256;
+    latent_affine_kernel<<<(unsigned)((ts->nbin + nt - 1) / nt), nt, 0, ctx->stream>>>(ts->nbin, L, ts->d_mu, ctx->d_small,
+                                                                                     shift != nullptr, M != nullptr);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
+static int moments(vlgp_ctx *ctx, TrialSet *ts, std::vector<double> &out) {
+    const int L = ctx->L, K = 2 * L + 1;
+    int grid = 2 * ctx->prop.multiProcessorCount;
+    if ((int64_t)grid * 256 > ts->nbin) grid = (int)((ts->nbin + 255) / 256);
+    double *part = nullptr;
+    CK(cudaMalloc(&part, (size_t)(grid + 1) * K * sizeof(double)));
+    moments_kernel<<<grid, 256, 0, ctx->stream>>>(ts->nbin, L, ts->d_mu, ts->d_dmu, part);
+    CKL();
+    double *res = part + (size_t)grid * K;
+    reduce_parts_kernel3<<<1, 64, 0, ctx->stream>>>(part, grid, K, res);
+    CKL();
+    int rc = vlgp_allreduce_dev(ctx, res, K, 0);
+    if (rc) { cudaFree(part); return rc; }
+    CK(cudaMemcpyAsync(ctx->h_pin, res, K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out.assign(ctx->h_pin, ctx->h_pin + K);
+    CK(cudaFree(part));
+    return VLGP_OK;
+}
+
+int vlgp_norms(vlgp_ctx *ctx, int set_id, double out[2]) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && out, "norms: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> m;
+    int rc = moments(ctx, ts, m);
+    if (rc) return rc;
+    const int L = ctx->L;
+    double s = 0.0;
+    for (int l = 0; l < L; ++l) s += m[L + l];
+    out[0] = s;
+    out[1] = m[2 * L];
+    return VLGP_OK;
+}
+
+int vlgp_latent_moments(vlgp_ctx *ctx, int set_id, double *sum, double *sumsq, int64_t *count) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "latent_moments: bad set %d", set_id);
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> m;
+    int rc = moments(ctx, ts, m);
+    if (rc) return rc;
+    const int L = ctx->L;
+    for (int l = 0; l < L; ++l) {
+        if (sum) sum[l] = m[l];
+        if (sumsq) sumsq[l] = m[L + l];
+    }
+    if (count) {
+        double c = (double)ts->nbin;
+        if (ctx->n_ranks > 1) {
+            rc = vlgp_comm_allreduce(ctx, &c, 1, 0);
+            if (rc) return rc;
+        }
+        *count = (int64_t)(c + 0.5);
+    }
+    return VLGP_OK;
+}
+
+// ---- measurement helpers -------------------------------------------------------------------------------------------
+int vlgp_peak_fp64(vlgp_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
+    if (!ctx) return VLGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int grid = ctx->prop.multiProcessorCount * 8, nt = 256, iters = 4096;
+    float ms = 0.f;
+    for (int which = 0; which < 2; ++which) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            if (which == 0) dfma_peak_kernel<<<grid, nt, 0, ctx->stream>>>(iters, ctx->d_small);
+            else dmma_peak_kernel<<<grid, nt, 0, ctx->stream>>>(iters, ctx->d_small);
+            CKL();
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaEventSynchronize(ctx->ev1));
+            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            // DFMA: 16 FMA per thread per iteration; DMMA: 8 mma of 8x8x4 per warp per iteration = 8*256 FMA per warp
+            const double fma_count = which == 0 ? (double)grid * nt * iters * 16.0
+                                                : (double)grid * (nt / 32) * iters * 8.0 * 256.0;
+            const double tf = 2.0 * fma_count / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
+        if (which == 0 && dfma_tflops) *dfma_tflops = best;
+        if (which == 1 && dmma_tflops) *dmma_tflops = best;
+    }
+    return VLGP_OK;
+}
+
+int vlgp_peak_hbm(vlgp_ctx *ctx, uint64_t nbytes, double *gbs) {
+    if (!ctx || !gbs) return VLGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    nbytes = (nbytes / 32) * 32;
+    REQUIRE(nbytes >= 32, "peak_hbm: nbytes too small");
+    void *src = nullptr, *dst = nullptr;
+    CK(cudaMalloc(&src, nbytes));
+    CK(cudaMalloc(&dst, nbytes));
+    CK(cudaMemsetAsync(src, 1, nbytes, ctx->stream));
+    const int grid = ctx->prop.multiProcessorCount * 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        float ms = 0.f;
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        copy_kernel<<<grid, 512, 0, ctx->stream>>>((const double4 *)src, (double4 *)dst, nbytes / 32);
+        CKL();
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double g = 2.0 * (double)nbytes / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    CK(cudaFree(src));
+    CK(cudaFree(dst));
+    *gbs = best;
+    return VLGP_OK;
+}
+
+int vlgp_flush_l2(vlgp_ctx *ctx) {
+    if (!ctx) return VLGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_flush) {
+        ctx->flush_bytes = (size_t)256 << 20;     // 256 MiB > 126 MB L2
+        CK(cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+    }
+    fill_kernel<<<ctx->prop.multiProcessorCount * 8, 512, 0, ctx->stream>>>((double4 *)ctx->d_flush, ctx->flush_bytes / 32);
+    CKL();
+    ctx->counters[0]--;   // not one of the engine's kernels
+    return VLGP_OK;
+}
+
+int vlgp_profile_enable(vlgp_ctx *ctx, int on) {
+    if (!ctx) return VLGP_ERR_ARG;
+    ctx->profile = on != 0;
+    for (int i = 0; i < 4; ++i) {
+        ctx->prof_ms[i] = 0.0;
+        ctx->prof_n[i] = 0;
+    }
+    return VLGP_OK;
+}
+
+int vlgp_profile_get(vlgp_ctx *ctx, int which, double *total_ms, int64_t *n) {
+    if (!ctx || which < 0 || which > 3) return VLGP_ERR_ARG;
+    if (total_ms) *total_ms = ctx->prof_ms[which];
+    if (n) *n = ctx->prof_n[which];
+    return VLGP_OK;
+}
+
+}   // extern "C"

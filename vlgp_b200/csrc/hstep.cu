@@ -1,0 +1,250 @@
+// K7: H-step objective -- ELBO of one latent's GP hyperparameters and its derivative w.r.t. log(omega).
+//
+// Replaces gp.construct_posterior_cov (vlgp/gp.py:126-147), gp.elbo (:12-43) and gp.kernel (:46-62) for the closure
+// that scipy's L-BFGS-B evaluates (vlgp/gp.py:107-111).  The reference materialises S_i = (K^-1 + diag(w_i))^-1 for
+// every segment and contracts W x W x S tensors.  With d = sqrt(w_i) and B_i = I + diag(d) K diag(d) (SPD, eigenvalues
+// >= 1, so no inverse of the ill-conditioned K per segment):
+//     tr(K^-1 S_i)              = tr(B_i^-1)
+//     K^-1 S_i K^-1 - K^-1      = -diag(d) B_i^-1 diag(d)
+// so    ll  = -1/2 tr(K^-1 M) - 1/2 sum_i tr(B_i^-1) - S sum(log diag chol K),        M = sum_i mu_i mu_i'
+//       dll =  1/2 [ (K^-1 M K^-1) : dK  -  sum_i (diag(d) B_i^-1 diag(d)) : dK ],    dK = -omega D^2 o (K - eps I)
+// (checked against the reference to 1e-12, tests/test_reformulation.py).  M is built once per H-step; each evaluation
+// costs one W x W inverse per segment, done by an in-SMEM symmetric sweep.
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+// ---- second moments of mu over segments: Mpart[chunk][l][a][b] -------------------------------------------------------
+__global__ void __launch_bounds__(NT) hstep_moment_kernel(int nseg, int W, int L, const double *__restrict__ mu,
+                                                          double *__restrict__ part) {
+    __shared__ double tile[8][VLGP_MAX_W];
+    const int l = blockIdx.y;
+    const int per = (nseg + gridDim.x - 1) / gridDim.x;
+    const int s0 = blockIdx.x * per, s1 = min(nseg, s0 + per);
+    const int tid = threadIdx.x;
+    constexpr int MAXE = (VLGP_MAX_W * VLGP_MAX_W + NT - 1) / NT;   // 16 entries per thread at W = 64
+    double acc[MAXE];
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) acc[e] = 0.0;
+    const int WW = W * W;
+    for (int s = s0; s < s1; s += 8) {
+        const int ns = min(8, s1 - s);
+        __syncthreads();
+        for (int i = tid; i < ns * W; i += NT) {
+            const int q = i / W, t = i - q * W;
+            tile[q][t] = mu[((size_t)(s + q) * W + t) * L + l];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < MAXE; ++e) {
+            const int idx = tid + e * NT;
+            if (idx < WW) {
+                const int a = idx / W, b = idx - a * W;
+                double x = acc[e];
+                for (int q = 0; q < ns; ++q) x = fma(tile[q][a], tile[q][b], x);
+                acc[e] = x;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < MAXE; ++e) {
+        const int idx = tid + e * NT;
+        if (idx < WW) part[((size_t)blockIdx.x * L + l) * WW + idx] = acc[e];
+    }
+}
+
+__global__ void reduce_parts_kernel2(const double *__restrict__ part, int G, int K, double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double s = 0.0;
+    for (int g = 0; g < G; ++g) s += part[(size_t)g * K + k];
+    out[k] = s;
+}
+
+// ---- per evaluation, one CTA: K, dK, K^-1 terms -------------------------------------------------------------------
+// out[0] = tr(K^-1 M), out[1] = sum log diag chol(K), out[2] = (K^-1 M K^-1):dK ; info[2] = 1 if K is not PD.
+__global__ void __launch_bounds__(NT) hstep_global_kernel(int W, double dt, double sigmasq, double omega, double eps,
+                                                          const double *__restrict__ M, double *__restrict__ Kout,
+                                                          double *__restrict__ dKout, double *__restrict__ out,
+                                                          int *__restrict__ flags) {
+    extern __shared__ double sm[];
+    const int ld = W | 1;
+    double *Aw = sm;                   // W x ld : K -> -K^-1
+    double *Tm = Aw + W * ld;          // W x ld : K^-1 M
+    double *ck = Tm + W * ld;          // 64
+    double *red = ck + 64;             // 32
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    for (int i = ty; i < W; i += 16)
+        for (int j = tx; j < W; j += 16) {
+            const double dx = (double)(i - j) * dt;
+            const double d2 = dx * dx;
+            const double ks = sigmasq * exp(-omega * d2);
+            const double k = ks + (i == j ? eps : 0.0);
+            Aw[i * ld + j] = k;
+            Kout[i * W + j] = k;
+            dKout[i * W + j] = -ks * d2 * omega;
+        }
+    __syncthreads();
+    double logdet = 0.0;
+    const bool ok = block_sweep_spd(Aw, ld, W, ck, &logdet);
+    if (!ok) {
+        if (tid == 0) {
+            flags[2] = 1;
+            out[0] = out[1] = out[2] = 0.0;
+        }
+        return;
+    }
+    // Tm = K^-1 M  (Aw = -K^-1)
+    double t1 = 0.0;
+    for (int i = ty; i < W; i += 16)
+        for (int j = tx; j < W; j += 16) {
+            double s = 0.0;
+            for (int k = 0; k < W; ++k) s = fma(Aw[i * ld + k], M[k * W + j], s);
+            Tm[i * ld + j] = -s;
+            if (i == j) t1 -= s;
+        }
+    __syncthreads();
+    // Q = Tm K^-1 ;  grad = Q : dK
+    double gr = 0.0;
+    for (int i = ty; i < W; i += 16)
+        for (int j = tx; j < W; j += 16) {
+            double s = 0.0;
+            for (int k = 0; k < W; ++k) s = fma(Tm[i * ld + k], Aw[k * ld + j], s);
+            gr = fma(-s, dKout[i * W + j], gr);
+        }
+    t1 = block_sum(t1, red);
+    gr = block_sum(gr, red);
+    if (tid == 0) {
+        out[0] = t1;
+        out[1] = 0.5 * logdet;
+        out[2] = gr;
+    }
+}
+
+// ---- per evaluation, one CTA per segment: B_i^-1 by sweep ---------------------------------------------------------
+__global__ void __launch_bounds__(NT) hstep_segment_kernel(int nseg, int W, int L, int l, const double *__restrict__ w,
+                                                           const double *__restrict__ K, const double *__restrict__ dK,
+                                                           double *__restrict__ part, int *__restrict__ flags) {
+    extern __shared__ double sm[];
+    const int ld = W | 1;
+    double *Aw = sm;                   // W x ld
+    double *dv = Aw + W * ld;          // 64 sqrt(w)
+    double *ck = dv + 64;              // 64
+    double *red = ck + 64;             // 32
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        __syncthreads();
+        if (tid < W) dv[tid] = sqrt(fmax(w[((size_t)seg * W + tid) * L + l], 0.0));
+        __syncthreads();
+        for (int i = ty; i < W; i += 16)
+            for (int j = tx; j < W; j += 16)
+                Aw[i * ld + j] = dv[i] * K[i * W + j] * dv[j] + (i == j ? 1.0 : 0.0);
+        __syncthreads();
+        const bool ok = block_sweep_spd(Aw, ld, W, ck, nullptr);
+        double tr = 0.0, pd = 0.0;
+        if (ok) {
+            for (int i = ty; i < W; i += 16)
+                for (int j = tx; j < W; j += 16) {
+                    const double binv = -Aw[i * ld + j];
+                    if (i == j) tr += binv;
+                    pd = fma(binv * dv[i] * dv[j], dK[i * W + j], pd);
+                }
+        } else if (tid == 0) {
+            atomicAdd(flags + 3, 1);
+        }
+        tr = block_sum(tr, red);
+        pd = block_sum(pd, red);
+        if (tid == 0) {
+            part[seg] = tr;
+            part[nseg + seg] = pd;
+        }
+    }
+}
+
+// out[3] = sum_i tr(B_i^-1), out[4] = sum_i (d B_i^-1 d):dK   (deterministic, one CTA)
+__global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double *__restrict__ part,
+                                                         double *__restrict__ out) {
+    __shared__ double red[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nseg; i += NT) {
+        a += part[i];
+        b += part[nseg + i];
+    }
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) {
+        out[3] = a;
+        out[4] = b;
+    }
+}
+
+}   // namespace
+
+int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
+    const int W = ts->max_len, L = ctx->L, S = ts->n_trials;
+    const int WW = W * W;
+    int chunks = (S + 31) / 32;
+    const int maxc = 4 * ctx->prop.multiProcessorCount / (L > 0 ? L : 1) + 1;
+    if (chunks > maxc) chunks = maxc;
+    if (chunks < 1) chunks = 1;
+    double *part = nullptr;
+    CK(cudaMalloc(&part, (size_t)chunks * L * WW * sizeof(double)));
+    if (!ts->d_M) CK(cudaMalloc(&ts->d_M, (size_t)L * WW * sizeof(double)));
+    if (!ts->d_K) CK(cudaMalloc(&ts->d_K, (size_t)2 * WW * sizeof(double)));
+    if (!ts->d_hpart) CK(cudaMalloc(&ts->d_hpart, (size_t)2 * S * sizeof(double)));
+    if (!ts->d_hout) CK(cudaMalloc(&ts->d_hout, 8 * sizeof(double)));
+    hstep_moment_kernel<<<dim3(chunks, L), NT, 0, ctx->stream>>>(S, W, L, ts->d_mu, part);
+    CKL();
+    reduce_parts_kernel2<<<(L * WW + 127) / 128, 128, 0, ctx->stream>>>(part, chunks, L * WW, ts->d_M);
+    CKL();
+    int rc = vlgp_allreduce_dev(ctx, ts->d_M, (size_t)L * WW, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(part));
+    ts->h_prepared = true;
+    return VLGP_OK;
+}
+
+// Returns the five partial results in out5 (host): tr(K^-1 M), sum log diag chol K, (K^-1 M K^-1):dK,
+// sum_i tr(B_i^-1), sum_i (d B_i^-1 d):dK -- the last two summed over ranks.
+int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, int l, double sigmasq, double omega, double eps,
+                                double out5[5], int *info) {
+    const int W = ts->max_len, L = ctx->L, S = ts->n_trials;
+    const int ld = W | 1;
+    const size_t smem_g = ((size_t)2 * W * ld + 96) * sizeof(double);
+    const size_t smem_s = ((size_t)W * ld + 160) * sizeof(double);
+    if (smem_g > 48 * 1024)
+        CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    if (smem_s > 48 * 1024)
+        CK(cudaFuncSetAttribute(hstep_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    CK(cudaMemsetAsync(ctx->d_flags + 2, 0, 2 * sizeof(int), ctx->stream));
+    double *Kd = ts->d_K, *dKd = ts->d_K + (size_t)W * W;
+    hstep_global_kernel<<<1, NT, smem_g, ctx->stream>>>(W, ctx->dt, sigmasq, omega, eps, ts->d_M + (size_t)l * W * W,
+                                                        Kd, dKd, ts->d_hout, ctx->d_flags);
+    CKL();
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, smem_s));
+    if (per_sm < 1) per_sm = 1;
+    int grid = per_sm * ctx->prop.multiProcessorCount;
+    if (grid > S) grid = S;
+    {
+        ProfScope ps(ctx, 2);
+        hstep_segment_kernel<<<grid, NT, smem_s, ctx->stream>>>(S, W, L, l, ts->d_w, Kd, dKd, ts->d_hpart,
+                                                                ctx->d_flags);
+        CKL();
+    }
+    hstep_final_kernel<<<1, NT, 0, ctx->stream>>>(S, ts->d_hpart, ts->d_hout);
+    CKL();
+    int rc = vlgp_allreduce_dev(ctx, ts->d_hout + 3, 2, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_pin, ts->d_hout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 5; ++i) out5[i] = ctx->h_pin[i];
+    *info = ctx->h_flags[2] != 0 ? 1 : (ctx->h_flags[3] != 0 ? 2 : 0);
+    ctx->counters[2] += S;
+    return VLGP_OK;
+}

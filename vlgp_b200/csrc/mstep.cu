@@ -1,0 +1,403 @@
+// K5/K6: M-step -- per-neuron Newton / least-squares updates of the loading a and bias b.
+//
+// Replaces core.mstep (vlgp/core.py:129-249).  One Newton iteration =
+//   mstep_stats   : one streaming pass over all bins x neurons (HBM/L2 -> registers): rate, gradient, packed Hessian and
+//                   noise moments per neuron, accumulated in registers, reduced per CTA, written as per-CTA partials
+//   reduce_parts  : deterministic sum of the per-CTA partials -> nstat x N sufficient statistics
+//   (NCCL sum-allreduce of that one fused buffer when trials are sharded over GPUs)
+//   mstep_solve   : one thread per neuron: L x L Cholesky solve (gradient fallback when not PD), clip, update
+// The rate is computed once per iteration and every neuron is updated from it (vlgp/core.py:174-176).
+#include "common.cuh"
+
+namespace {
+
+__host__ __device__ constexpr int nstat_of(int L) { return L + L * (L + 1) / 2 + 4; }
+// per-neuron statistic slots: [0,L) grad_a (Gaussian: mu'y) ; [L, L+L(L+1)/2) packed lower Hessian ;
+// then gb (Gaussian: sum y), Hb, sum e, sum e^2 with e = y - eta.
+
+struct MstatArgs {
+    int64_t nbin;
+    int N, NC, J;                // neurons, neurons per chunk (blockDim = J*NC rounded up to 32)
+    const void *y;
+    int ydtype;
+    const double *mu, *v, *a, *b;
+    const uint8_t *poisson;
+    double *part;                // gridDim.x x nstat x N
+};
+
+template <int LT>
+__global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(MstatArgs p) {
+    constexpr int NS = nstat_of(LT);
+    extern __shared__ double red[];             // 2 x blockDim
+    const int tid = threadIdx.x;
+    const int j = tid / p.NC;                   // bin lane
+    const int n = blockIdx.y * p.NC + (tid - j * p.NC);
+    const bool active = j < p.J && n < p.N;
+    const int64_t per = (p.nbin + gridDim.x - 1) / gridDim.x;
+    const int64_t b0 = (int64_t)blockIdx.x * per;
+    const int64_t b1 = b0 + per < p.nbin ? b0 + per : p.nbin;
+
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+
+    if (active) {
+        double al[LT], a2[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            al[l] = p.a[l * p.N + n];
+            a2[l] = al[l] * al[l];
+        }
+        const double bn = p.b[n];
+        const bool pois = p.poisson[n] != 0;
+        for (int64_t bin = b0 + j; bin < b1; bin += p.J) {
+            double m[LT], vv[LT];
+            double eta = bn, h = 0.0;
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                m[l] = p.mu[bin * LT + l];
+                vv[l] = p.v[bin * LT + l];
+                eta = fma(m[l], al[l], eta);
+                h = fma(vv[l], a2[l], h);
+            }
+            const double yv = load_y(p.y, p.ydtype, bin * p.N + n);
+            const double e = yv - eta;
+            acc[NS - 2] += e;
+            acc[NS - 1] = fma(e, e, acc[NS - 1]);
+            if (pois) {
+                const double r = trunc_exp(eta + 0.5 * h);
+                acc[NS - 4] += yv - r;
+                acc[NS - 3] += r;
+                double s[LT];
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    s[l] = fma(vv[l], al[l], m[l]);
+                    acc[l] += m[l] * yv - s[l] * r;
+                }
+                int q = LT;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    const double rs = r * s[l];
+#pragma unroll
+                    for (int k = 0; k <= l; ++k) {
+                        acc[q] = fma(rs, s[k], acc[q]);
+                        ++q;
+                    }
+                    acc[q - 1] = fma(r, vv[l], acc[q - 1]);     // + diag(r' v)   (vlgp/core.py:189)
+                }
+            } else {
+                acc[NS - 4] += yv;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) acc[l] = fma(m[l], yv, acc[l]);
+            }
+        }
+    }
+    // reduce over the J bin lanes of this CTA, one statistic at a time (double-buffered: one barrier per statistic)
+    const int nc_local = tid - j * p.NC;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double *buf = red + (s & 1) * blockDim.x;
+        buf[tid] = active ? acc[s] : 0.0;
+        __syncthreads();
+        if (j == 0 && n < p.N) {
+            double r = 0.0;
+            for (int jj = 0; jj < p.J; ++jj) r += buf[jj * p.NC + nc_local];
+            p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = r;
+        }
+    }
+}
+
+// out[k] = sum_g part[g * K + k]    (deterministic; K = nstat x N)
+__global__ void reduce_parts_kernel(const double *__restrict__ part, int G, int K, double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int g = 0;
+    for (; g + 3 < G; g += 4) {
+        s0 += part[(size_t)g * K + k];
+        s1 += part[(size_t)(g + 1) * K + k];
+        s2 += part[(size_t)(g + 2) * K + k];
+        s3 += part[(size_t)(g + 3) * K + k];
+    }
+    for (; g < G; ++g) s0 += part[(size_t)g * K + k];
+    out[k] = (s0 + s1) + (s2 + s3);
+}
+
+// Shared moments of the Gaussian channels: mu'mu (L x L), sum v (L), sum mu (L)  (vlgp/core.py:224-232)
+template <int LT>
+__global__ void __launch_bounds__(256) gauss_moments_kernel(int64_t nbin, const double *__restrict__ mu,
+                                                            const double *__restrict__ v, double *part) {
+    constexpr int K = LT * LT + 2 * LT;
+    __shared__ double red[32];
+    double acc[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) acc[s] = 0.0;
+    for (int64_t bin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; bin < nbin; bin += (int64_t)gridDim.x * blockDim.x) {
+        double m[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) m[l] = mu[bin * LT + l];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+#pragma unroll
+            for (int k = 0; k < LT; ++k) acc[l * LT + k] = fma(m[l], m[k], acc[l * LT + k]);
+            acc[LT * LT + l] += v[bin * LT + l];
+            acc[LT * LT + LT + l] += m[l];
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        const double x = warp_sum(acc[s]);
+        __syncthreads();
+        if (lane == 0) red[wid] = x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+            part[(size_t)blockIdx.x * K + s] = r;
+        }
+    }
+}
+
+struct MsolveArgs {
+    int N;
+    double count;                // total number of bins (all ranks)
+    const double *stat;          // nstat x N
+    const double *gshared;       // L*L + 2L (Gaussian channels) or null
+    const uint8_t *poisson;
+    double *a, *b, *noise, *da, *db;
+    int use_hessian;
+    double eps, lr, da_bound, db_bound;
+    int *flags;                  // flags[1] += gradient fallbacks
+};
+
+// Solve H x = g for SPD H (L x L, full storage, destroyed).  Returns false if not positive definite
+// (same criterion as LAPACK posv behind scipy.linalg.solve(sym_pos=True), vlgp/core.py:193).
+template <int LT>
+__device__ __forceinline__ bool chol_solve_small(double (&H)[LT][LT], double (&g)[LT]) {
+#pragma unroll
+    for (int k = 0; k < LT; ++k) {
+        double d = H[k][k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) d = fma(-H[k][m], H[k][m], d);
+        if (!(d > 0.0)) return false;
+        const double lkk = sqrt(d);
+        H[k][k] = lkk;
+#pragma unroll
+        for (int i = k + 1; i < LT; ++i) {
+            double s = H[i][k];
+#pragma unroll
+            for (int m = 0; m < k; ++m) s = fma(-H[i][m], H[k][m], s);
+            H[i][k] = s / lkk;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LT; ++i) {          // forward
+        double s = g[i];
+#pragma unroll
+        for (int m = 0; m < i; ++m) s = fma(-H[i][m], g[m], s);
+        g[i] = s / H[i][i];
+    }
+#pragma unroll
+    for (int i = LT - 1; i >= 0; --i) {     // backward
+        double s = g[i];
+#pragma unroll
+        for (int m = i + 1; m < LT; ++m) s = fma(-H[m][i], g[m], s);
+        g[i] = s / H[i][i];
+    }
+    return true;
+}
+
+template <int LT>
+__global__ void mstep_solve_kernel(MsolveArgs p) {
+    constexpr int NS = nstat_of(LT);
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.N) return;
+    const int N = p.N;
+    auto S = [&](int s) { return p.stat[(size_t)s * N + n]; };
+    const double me = S(NS - 2) / p.count;
+    p.noise[n] = S(NS - 1) / p.count - me * me;       // np.var(y - eta, ddof=0), vlgp/core.py:177
+    if (p.poisson[n]) {
+        double g[LT], H[LT][LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) g[l] = S(l);
+        double step[LT];
+        bool newton = p.use_hessian != 0;
+        if (newton) {
+            int q = LT;
+#pragma unroll
+            for (int l = 0; l < LT; ++l)
+#pragma unroll
+                for (int k = 0; k <= l; ++k) {
+                    const double h = S(q++);
+                    H[l][k] = h;
+                    H[k][l] = h;
+                }
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                H[l][l] += p.eps;
+                step[l] = g[l];
+            }
+            if (!chol_solve_small<LT>(H, step)) {
+                newton = false;
+                atomicAdd(p.flags + 1, 1);
+            }
+        }
+        if (!newton) {
+#pragma unroll
+            for (int l = 0; l < LT; ++l) step[l] = p.lr * g[l];
+        }
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            const double d = clipd(step[l], p.da_bound);
+            p.da[l * N + n] = d;
+            p.a[l * N + n] += d;
+        }
+        const double gb = S(NS - 4);
+        double sb;
+        const double hb = S(NS - 3) + p.eps;
+        if (p.use_hessian && hb > 0.0) sb = gb / hb;
+        else {
+            sb = p.lr * gb;
+            if (p.use_hessian) atomicAdd(p.flags + 1, 1);
+        }
+        sb = clipd(sb, p.db_bound);
+        p.db[n] = sb;
+        p.b[n] += sb;
+    } else if (p.gshared != nullptr) {
+        // least squares for a Gaussian channel (vlgp/core.py:221-235); da/db are left untouched like the reference
+        double H[LT][LT], rhs[LT], smu[LT];
+        const double bn = p.b[n];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+#pragma unroll
+            for (int k = 0; k < LT; ++k) H[l][k] = p.gshared[l * LT + k];
+            H[l][l] += p.gshared[LT * LT + l];
+            smu[l] = p.gshared[LT * LT + LT + l];
+            rhs[l] = S(l) - smu[l] * bn;
+        }
+        if (chol_solve_small<LT>(H, rhs)) {
+            double dot = 0.0;
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                p.a[l * N + n] = rhs[l];
+                dot = fma(smu[l], rhs[l], dot);
+            }
+            p.b[n] = (S(NS - 4) - dot) / p.count;
+        } else {
+            atomicAdd(p.flags + 1, 1);
+        }
+    }
+}
+
+template <int LT>
+int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr, double da_bound,
+            double db_bound) {
+    constexpr int NS = nstat_of(LT);
+    constexpr int MAXT = (LT <= 5) ? 512 : 256;
+    const int N = ctx->N;
+    const int NC = N < MAXT ? N : MAXT;
+    const int nchunk = (N + NC - 1) / NC;
+    const int J = MAXT / NC;
+    int nt = ((J * NC + 31) / 32) * 32;
+    const size_t smem = 2 * (size_t)nt * sizeof(double);
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mstep_stats_kernel<LT>, nt, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t gx = (int64_t)per_sm * ctx->prop.multiProcessorCount / nchunk;
+    const int64_t min_bins = 4 * (int64_t)J;       // at least a few bins per bin lane
+    if (gx > (ts->nbin + min_bins - 1) / min_bins) gx = (ts->nbin + min_bins - 1) / min_bins;
+    if (gx < 1) gx = 1;
+    const int K = NS * N;
+    if (ctx->mpart_grid < gx * (NS * N + 1)) {
+        if (ctx->d_mpart) CK(cudaFree(ctx->d_mpart));
+        ctx->d_mpart = nullptr;
+        CK(cudaMalloc(&ctx->d_mpart, (size_t)gx * (K + 64) * sizeof(double)));
+        ctx->mpart_grid = (int)(gx * (NS * N + 1));
+    }
+    if (ctx->d_mstat) CK(cudaFree(ctx->d_mstat));
+    ctx->d_mstat = nullptr;
+    CK(cudaMalloc(&ctx->d_mstat, (size_t)(K + 1) * sizeof(double)));
+
+    // total bin count over all ranks (the divisor of np.var / the Gaussian bias)
+    double count = (double)ts->nbin;
+    if (ctx->n_ranks > 1) {
+        ctx->h_pin[0] = count;
+        CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = vlgp_allreduce_dev(ctx, ctx->d_small, 1, 0);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_small, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        count = ctx->h_pin[0];
+    }
+
+    double *gshared = nullptr;
+    if (ctx->any_gauss) {
+        constexpr int KG = LT * LT + 2 * LT;
+        const int gg = 2 * ctx->prop.multiProcessorCount;
+        double *gpart = nullptr;
+        CK(cudaMalloc(&gpart, (size_t)gg * KG * sizeof(double)));
+        if (!ctx->d_gshared) CK(cudaMalloc(&ctx->d_gshared, (VLGP_MAX_L * VLGP_MAX_L + 2 * VLGP_MAX_L) * sizeof(double)));
+        gauss_moments_kernel<LT><<<gg, 256, 0, ctx->stream>>>(ts->nbin, ts->d_mu, ts->d_v, gpart);
+        CKL();
+        reduce_parts_kernel<<<(KG + 127) / 128, 128, 0, ctx->stream>>>(gpart, gg, KG, ctx->d_gshared);
+        CKL();
+        int rc = vlgp_allreduce_dev(ctx, ctx->d_gshared, KG, 0);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(gpart));
+        gshared = ctx->d_gshared;
+    }
+
+    MstatArgs sa{};
+    sa.nbin = ts->nbin; sa.N = N; sa.NC = NC; sa.J = J;
+    sa.y = ts->d_y; sa.ydtype = ts->ydtype;
+    sa.mu = ts->d_mu; sa.v = ts->d_v; sa.a = ctx->d_a; sa.b = ctx->d_b; sa.poisson = ctx->d_poisson;
+    sa.part = ctx->d_mpart;
+    MsolveArgs so{};
+    so.N = N; so.count = count; so.stat = ctx->d_mstat; so.gshared = gshared; so.poisson = ctx->d_poisson;
+    so.a = ctx->d_a; so.b = ctx->d_b; so.noise = ctx->d_noise; so.da = ctx->d_da; so.db = ctx->d_db;
+    so.use_hessian = use_hessian; so.eps = eps; so.lr = lr; so.da_bound = da_bound; so.db_bound = db_bound;
+    so.flags = ctx->d_flags;
+
+    for (int it = 0; it < n_iter; ++it) {
+        {
+            ProfScope ps(ctx, 1);
+            mstep_stats_kernel<LT><<<dim3((unsigned)gx, nchunk), nt, smem, ctx->stream>>>(sa);
+            CKL();
+        }
+        reduce_parts_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_mpart, (int)gx, K, ctx->d_mstat);
+        CKL();
+        int rc = vlgp_allreduce_dev(ctx, ctx->d_mstat, K, 0);
+        if (rc) return rc;
+        mstep_solve_kernel<LT><<<(N + 63) / 64, 64, 0, ctx->stream>>>(so);
+        CKL();
+    }
+    return VLGP_OK;
+}
+
+}   // namespace
+
+#define DISPATCH_L(L, CALL)                                                            \
+    switch (L) {                                                                       \
+        case 1: { constexpr int LT = 1; CALL; } break;                                 \
+        case 2: { constexpr int LT = 2; CALL; } break;                                 \
+        case 3: { constexpr int LT = 3; CALL; } break;                                 \
+        case 4: { constexpr int LT = 4; CALL; } break;                                 \
+        case 5: { constexpr int LT = 5; CALL; } break;                                 \
+        case 6: { constexpr int LT = 6; CALL; } break;                                 \
+        case 7: { constexpr int LT = 7; CALL; } break;                                 \
+        case 8: { constexpr int LT = 8; CALL; } break;                                 \
+        case 9: { constexpr int LT = 9; CALL; } break;                                 \
+        case 10: { constexpr int LT = 10; CALL; } break;                               \
+        case 11: { constexpr int LT = 11; CALL; } break;                               \
+        case 12: { constexpr int LT = 12; CALL; } break;                               \
+        default: return vlgp_fail(ctx, VLGP_ERR_UNSUPPORTED, "n_latents %d > 12", L);  \
+    }
+
+int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
+                      double da_bound, double db_bound) {
+    int rc = VLGP_OK;
+    DISPATCH_L(ctx->L, rc = mstep_t<LT>(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound));
+    return rc;
+}

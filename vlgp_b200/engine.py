@@ -1,0 +1,333 @@
+"""Host-side handle on the native engine: one ``Engine`` per process/GPU, ``TrialSet`` = device copy of a list of trials.
+
+This is plumbing between the reference's dict surface (trial dicts / params / config, vlgp/api.py:18-76) and the flat
+buffers of the C ABI; it does no arithmetic of the hot path itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import VlgpNativeError, as_f64, dptr
+
+__all__ = ["Engine", "TrialSet", "get_engine", "reset_engine", "pack_y"]
+
+_ENGINE = None
+
+
+def get_engine() -> "Engine":
+    """Process-wide engine on ``cuda:$LOCAL_RANK`` (created on first use)."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(int(os.environ.get("VLGP_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    return _ENGINE
+
+
+def reset_engine():
+    global _ENGINE
+    if _ENGINE is not None:
+        _ENGINE.close()
+    _ENGINE = None
+
+
+def pack_y(ys):
+    """Concatenate per-trial observations; store as uint8 when every entry is an integer count in [0, 255] (spike
+    counts almost always are), else float64.  Returns (array, ydtype code)."""
+    y = ys[0] if len(ys) == 1 else np.concatenate(ys, axis=0)
+    if y.dtype == np.uint8:
+        return np.ascontiguousarray(y), 1
+    yf = np.ascontiguousarray(y, dtype=np.float64)
+    if yf.size and yf.min() >= 0 and yf.max() <= 255 and np.array_equal(yf, np.rint(yf)):
+        return yf.astype(np.uint8), 1
+    return yf, 0
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        ctx = C.c_void_p()
+        rc = self.lib.vlgp_create(int(device), C.byref(ctx))
+        if rc != 0:
+            msg = self.lib.vlgp_last_error(None)
+            raise VlgpNativeError("vlgp_create(device=%d) failed (%d): %s" % (device, rc, (msg or b"").decode()))
+        self.ctx = ctx
+        self.device = int(device)
+        self.model_key = None
+        self.N = self.L = self.rank = 0
+        self.world_size = 1
+        self.rank_id = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self.lib.vlgp_last_error(self.ctx)
+            raise VlgpNativeError("%s failed (%d): %s" % (what, rc, (msg or b"").decode()))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.vlgp_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        mem = C.c_uint64()
+        name = C.create_string_buffer(128)
+        self._ck(self.lib.vlgp_device_info(self.ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem), name),
+                 "device_info")
+        return {"name": name.value.decode(), "sm_count": sm.value, "cc": (ma.value, mi.value), "mem": mem.value}
+
+    def sync(self):
+        self._ck(self.lib.vlgp_sync(self.ctx), "sync")
+
+    def timer_start(self):
+        self._ck(self.lib.vlgp_timer_start(self.ctx), "timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.vlgp_timer_stop(self.ctx, C.byref(ms)), "timer_stop")
+        return float(ms.value)
+
+    def counters(self):
+        c = (C.c_int64 * 4)()
+        self._ck(self.lib.vlgp_counters(self.ctx, c), "counters")
+        return {"launches": c[0], "estep_solves": c[1], "hstep_factorisations": c[2], "collectives": c[3]}
+
+    # -- model -------------------------------------------------------------------------------------------------------
+    def ensure_model(self, params):
+        """Bind the model dimensions / likelihoods of ``params`` (re-created only when they change)."""
+        lik = np.asarray(params["likelihood"])
+        mask = np.ascontiguousarray((lik == "poisson").astype(np.uint8))
+        bad = ~np.isin(lik, ("poisson", "gaussian"))
+        if bad.any():
+            raise ValueError("unsupported likelihood(s): %s" % sorted(set(lik[bad].tolist())))
+        if int(params.get("xdim", 1)) != 1:
+            raise NotImplementedError("vlgp_b200 supports xdim == 1 (bias only, history=0); got xdim=%s" % params["xdim"])
+        key = (int(params["ydim"]), int(params["zdim"]), int(params["rank"]), mask.tobytes(),
+               float(params["gp_noise"]), float(params["dt"]))
+        if key != self.model_key:
+            self._ck(self.lib.vlgp_set_model(self.ctx, key[0], key[1], key[2], mask.ctypes.data_as(_lib.c_u8_p),
+                                             key[4], key[5]), "set_model")
+            self.model_key = key
+            self.N, self.L, self.rank = key[0], key[1], key[2]
+
+    def push_params(self, params, which=("a", "b", "noise", "sigma", "omega")):
+        L, N = self.L, self.N
+        a = as_f64(params["a"], (L, N)) if "a" in which else None
+        b = as_f64(np.asarray(params["b"]).reshape(-1), (N,)) if "b" in which else None
+        noise = as_f64(params["noise"], (N,)) if "noise" in which else None
+        sigma = as_f64(params["sigma"], (L,)) if "sigma" in which else None
+        omega = as_f64(params["omega"], (L,)) if "omega" in which else None
+        self._ck(self.lib.vlgp_set_params(self.ctx, dptr(a), dptr(b), dptr(noise), dptr(sigma), dptr(omega)),
+                 "set_params")
+
+    def pull_params(self, params, which=("a", "b", "noise", "da", "db")):
+        """Copy device parameters into the reference-shaped arrays of ``params`` (b/db are (1, N))."""
+        L, N = self.L, self.N
+        out = {k: np.empty((L, N)) for k in ("a", "da") if k in which}
+        out.update({k: np.empty((N,)) for k in ("b", "db", "noise") if k in which})
+        g = out.get
+        self._ck(self.lib.vlgp_get_params(self.ctx, dptr(g("a")), dptr(g("b")), dptr(g("noise")), dptr(g("da")),
+                                          dptr(g("db")), None, None), "get_params")
+        for k, val in out.items():
+            params[k] = val.reshape(1, N) if k in ("b", "db") else val
+        return params
+
+    def new_trials(self, lengths) -> "TrialSet":
+        return TrialSet(self, lengths)
+
+    # -- communicator ------------------------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.vlgp_comm_unique_id(self.ctx, _lib.nccl_path().encode(), buf), "comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, rank: int, world_size: int, unique_id: bytes):
+        if world_size > 1:
+            assert len(unique_id) == 128
+            self._ck(self.lib.vlgp_comm_init(self.ctx, _lib.nccl_path().encode(), int(rank), int(world_size),
+                                             C.create_string_buffer(unique_id, 128)), "comm_init")
+        self.world_size, self.rank_id = int(world_size), int(rank)
+
+    def allreduce(self, x, op="sum"):
+        """In-place allreduce of a small host array (<= 256 doubles per call; chunked here)."""
+        a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        if self.world_size > 1:
+            for i in range(0, a.size, 256):
+                chunk = np.ascontiguousarray(a[i:i + 256])
+                self._ck(self.lib.vlgp_comm_allreduce(self.ctx, dptr(chunk), chunk.size, 1 if op == "max" else 0),
+                         "comm_allreduce")
+                a[i:i + 256] = chunk
+        return a.reshape(np.shape(x))
+
+    # -- measurement -------------------------------------------------------------------------------------------------
+    def peak_fp64(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.vlgp_peak_fp64(self.ctx, C.byref(a), C.byref(b)), "peak_fp64")
+        return {"dfma_tflops": a.value, "dmma_tflops": b.value}
+
+    def peak_hbm(self, nbytes=1 << 30):
+        g = C.c_double()
+        self._ck(self.lib.vlgp_peak_hbm(self.ctx, int(nbytes), C.byref(g)), "peak_hbm")
+        return g.value
+
+    def flush_l2(self):
+        self._ck(self.lib.vlgp_flush_l2(self.ctx), "flush_l2")
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.vlgp_profile_enable(self.ctx, int(bool(on))), "profile_enable")
+
+    def profile_get(self, which):
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.lib.vlgp_profile_get(self.ctx, int(which), C.byref(ms), C.byref(n)), "profile_get")
+        return ms.value, n.value
+
+
+class TrialSet:
+    """Device-resident copy of a list of trials (or segments): y, mu, v, w, dmu and the prior factors per length."""
+
+    def __init__(self, eng: Engine, lengths):
+        self.eng = eng
+        self.lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        if self.lengths.ndim != 1 or self.lengths.size == 0:
+            raise ValueError("lengths must be a non-empty 1-D sequence")
+        self.nbin = int(self.lengths.sum())
+        self.starts = np.concatenate([[0], np.cumsum(self.lengths)[:-1]]).astype(np.int64)
+        sid = C.c_int()
+        eng._ck(eng.lib.vlgp_trials_create(eng.ctx, int(self.lengths.size), self.lengths.ctypes.data_as(_lib.c_i32_p),
+                                           C.byref(sid)), "trials_create")
+        self.id = sid.value
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def free(self):
+        if self.id is not None and self.eng.ctx:
+            self.eng._ck(self.eng.lib.vlgp_trials_free(self.eng.ctx, self.id), "trials_free")
+        self.id = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+        return False
+
+    def _lib(self):
+        return self.eng.lib, self.eng.ctx
+
+    # -- data ----------------------------------------------------------------------------------------------------------
+    def set_y(self, y, ydtype=None):
+        lib, ctx = self._lib()
+        if ydtype is None:
+            y, ydtype = pack_y([y])
+        y = np.ascontiguousarray(y)
+        if y.shape != (self.nbin, self.eng.N):
+            raise ValueError("y must be (%d, %d), got %s" % (self.nbin, self.eng.N, y.shape))
+        self.eng._ck(lib.vlgp_trials_set_y(ctx, self.id, y.ctypes.data_as(C.c_void_p), int(ydtype)), "trials_set_y")
+        self.h2d_bytes += y.nbytes
+
+    def set_state(self, mu=None, v=None, w=None):
+        lib, ctx = self._lib()
+        shp = (self.nbin, self.eng.L)
+        arrs = [None if x is None else as_f64(x, shp) for x in (mu, v, w)]
+        self.eng._ck(lib.vlgp_trials_set_state(ctx, self.id, *[dptr(x) for x in arrs]), "trials_set_state")
+        self.h2d_bytes += sum(x.nbytes for x in arrs if x is not None)
+
+    def get_state(self, which=("mu", "v", "w", "dmu")):
+        lib, ctx = self._lib()
+        shp = (self.nbin, self.eng.L)
+        out = {k: np.empty(shp) for k in which}
+        g = out.get
+        self.eng._ck(lib.vlgp_trials_get_state(ctx, self.id, dptr(g("mu")), dptr(g("v")), dptr(g("w")), dptr(g("dmu"))),
+                     "trials_get_state")
+        self.d2h_bytes += sum(x.nbytes for x in out.values())
+        return out
+
+    # -- prior factor -------------------------------------------------------------------------------------------------
+    def make_cholesky(self):
+        lib, ctx = self._lib()
+        self.eng._ck(lib.vlgp_make_cholesky(ctx, self.id), "make_cholesky")
+
+    def get_cholesky(self, length, with_pivots=False):
+        lib, ctx = self._lib()
+        L, r = self.eng.L, self.eng.rank
+        G = np.empty((L, int(length), r))
+        piv = np.empty((L, r), dtype=np.int32)
+        ncol = np.empty((L,), dtype=np.int32)
+        self.eng._ck(lib.vlgp_get_cholesky(ctx, self.id, int(length), dptr(G), piv.ctypes.data_as(_lib.c_i32_p),
+                                           ncol.ctypes.data_as(_lib.c_i32_p)), "get_cholesky")
+        return (G, piv, ncol) if with_pivots else G
+
+    def set_cholesky(self, length, G):
+        lib, ctx = self._lib()
+        G = as_f64(G, (self.eng.L, int(length), self.eng.rank))
+        self.eng._ck(lib.vlgp_set_cholesky(ctx, self.id, int(length), dptr(G)), "set_cholesky")
+        self.h2d_bytes += G.nbytes
+
+    # -- steps -----------------------------------------------------------------------------------------------------------
+    def estep(self, n_iter, dmu_bound=5.0, method="VB"):
+        lib, ctx = self._lib()
+        nf = C.c_int()
+        self.eng._ck(lib.vlgp_estep(ctx, self.id, int(n_iter), float(dmu_bound), int(method == "VB"), C.byref(nf)),
+                     "estep")
+        return nf.value
+
+    def update_w(self):
+        lib, ctx = self._lib()
+        self.eng._ck(lib.vlgp_update_w(ctx, self.id), "update_w")
+
+    def update_v(self):
+        lib, ctx = self._lib()
+        nf = C.c_int()
+        self.eng._ck(lib.vlgp_update_v(ctx, self.id, C.byref(nf)), "update_v")
+        return nf.value
+
+    def mstep(self, n_iter, use_hessian=True, eps=1e-8, learning_rate=1.0, da_bound=5.0, db_bound=5.0):
+        lib, ctx = self._lib()
+        nf = C.c_int()
+        self.eng._ck(lib.vlgp_mstep(ctx, self.id, int(n_iter), int(bool(use_hessian)), float(eps), float(learning_rate),
+                                    float(da_bound), float(db_bound), C.byref(nf)), "mstep")
+        return nf.value
+
+    def hstep_prepare(self):
+        lib, ctx = self._lib()
+        self.eng._ck(lib.vlgp_hstep_prepare(ctx, self.id), "hstep_prepare")
+
+    def hstep_objective(self, latent, hyper):
+        """(ll, dll/dlog omega, info) at hyper = (sigma^2, omega, eps)."""
+        lib, ctx = self._lib()
+        h = as_f64(hyper, (3,))
+        ll, dll, info = C.c_double(), C.c_double(), C.c_int()
+        self.eng._ck(lib.vlgp_hstep_objective(ctx, self.id, int(latent), dptr(h), C.byref(ll), C.byref(dll),
+                                              C.byref(info)), "hstep_objective")
+        return ll.value, dll.value, info.value
+
+    def latent_affine(self, shift=None, M=None):
+        lib, ctx = self._lib()
+        L = self.eng.L
+        s = None if shift is None else as_f64(np.asarray(shift).reshape(-1), (L,))
+        m = None if M is None else as_f64(M, (L, L))
+        self.eng._ck(lib.vlgp_latent_affine(ctx, self.id, dptr(s), dptr(m)), "latent_affine")
+
+    def norms(self):
+        """(sum mu^2, sum dmu^2) over all bins (all ranks)."""
+        lib, ctx = self._lib()
+        out = np.empty(2)
+        self.eng._ck(lib.vlgp_norms(ctx, self.id, dptr(out)), "norms")
+        return float(out[0]), float(out[1])
+
+    def latent_moments(self):
+        lib, ctx = self._lib()
+        L = self.eng.L
+        s, q = np.empty(L), np.empty(L)
+        n = C.c_int64()
+        self.eng._ck(lib.vlgp_latent_moments(ctx, self.id, dptr(s), dptr(q), C.byref(n)), "latent_moments")
+        return s, q, n.value

@@ -1,0 +1,111 @@
+"""Host-side set-up of the three dicts the reference passes around (trials / params / config).
+
+Mirrors the behaviour of vlgp/preprocess.py (get_config :84-112, get_params :49-81, initialize :4-46, fill_trials
+:115-120, fill_params :123-125) including its use of the *global* NumPy RNG (one ``np.random.choice`` per initialize),
+so that a seeded run draws the same numbers as the reference.  Nothing here is on the hot path: it stays NumPy/sklearn
+on the host, exactly like the reference (SURVEY.md section 8(f) item 1 lists a device initialiser as future work).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["get_config", "get_params", "initialize", "fill_trials", "fill_params"]
+
+_CONFIG_DEFAULTS = (
+    ("constrain_loading", "fro"),
+    ("constrain_latent", False),
+    ("use_hessian", True),
+    ("eps", 1e-8),
+    ("tol", 1e-8),
+    ("min_iter", 5),
+    ("method", "VB"),
+    ("learning_rate", 1.0),
+    ("max_iter", 20),
+    ("Eniter", 25),
+    ("Mniter", 25),
+    ("Hstep", True),
+    ("da_bound", 5.0),
+    ("db_bound", 5.0),
+    ("dmu_bound", 5.0),
+    ("omega_bound", (5e-4, 5e-2)),
+    ("window", 50),
+    ("saving_interval", 60 * 30),
+    ("callbacks", None),
+    ("parallel", False),
+)
+
+
+def get_config(**kwargs):
+    """Default configuration overridden by the recognised keyword arguments; unknown ones are dropped silently."""
+    config = {k: ([] if k == "callbacks" else v) for k, v in _CONFIG_DEFAULTS}
+    for k in list(config):
+        if k in kwargs:
+            config[k] = kwargs[k]
+    return config
+
+
+def get_params(trials, zdim, **kwargs):
+    """Initial parameter dict.  ``kwargs`` must carry ``omega_bound`` (fit passes config's)."""
+    ydim = trials[0]["y"].shape[-1]
+    lik = kwargs.get("lik", "poisson")
+    lik = np.asarray(lik if isinstance(lik, list) else [lik] * ydim)
+    return {
+        "ydim": ydim,
+        "zdim": zdim,
+        "xdim": max(kwargs.get("history", 0), 1),
+        "a": kwargs.get("a", None),
+        "b": kwargs.get("b", None),
+        "noise": kwargs.get("noise", np.ones(ydim)),
+        "sigma": kwargs.get("sigma", np.ones(zdim)),
+        "omega": kwargs.get("omega", np.full(zdim, kwargs["omega_bound"][1], dtype=float)),
+        "rank": 50,
+        "gp_noise": 1e-4,
+        "dt": 1,
+        "likelihood": lik,
+    }
+
+
+def initialize(trials, params, config):
+    """Factor-analysis initialisation of loading / bias / noise and of every trial's posterior mean."""
+    from sklearn.decomposition import FactorAnalysis
+
+    zdim, xdim = params["zdim"], params["xdim"]
+    y_all = np.concatenate([tr["y"] for tr in trials], axis=0)
+    nbin, ydim = y_all.shape
+    pick = np.random.choice(nbin, max(nbin // 10, 50))      # with replacement, like the reference
+
+    if params.get("transform") is None:
+        fa = FactorAnalysis(n_components=zdim, random_state=0)
+        z = fa.fit_transform(y_all[pick, :])
+        params["transform"] = fa.transform
+        if params.get("a") is None:
+            params["a"] = fa.components_
+        if params.get("b") is None:
+            params["b"] = np.log(np.maximum(y_all.mean(axis=0, keepdims=True), config["eps"]))
+        if params.get("noise") is None:
+            params["noise"] = np.var(y_all[pick, :] - z @ fa.components_, ddof=0, axis=0)
+
+    to_latent = params["transform"]
+    for tr in trials:
+        nt = tr["y"].shape[0]
+        if tr.get("mu") is None:
+            tr["mu"] = to_latent(tr["y"])
+        if tr.get("x") is None:
+            tr["x"] = np.ones((nt, xdim, ydim))
+        tr["w"] = np.zeros((nt, zdim))
+        tr["v"] = np.zeros((nt, zdim))
+
+
+def fill_trials(trials):
+    for i, tr in enumerate(trials):
+        tr["cut"] = i
+        for key in ("w", "v", "dmu"):
+            if key not in tr:
+                tr[key] = np.zeros_like(tr["mu"])
+
+
+def fill_params(params):
+    if "da" not in params:
+        params["da"] = np.zeros_like(params["a"])
+    if "db" not in params:
+        params["db"] = np.zeros_like(params["b"])

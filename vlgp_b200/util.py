@@ -1,0 +1,69 @@
+"""Host-side helpers kept from the reference's surface: window cutting (vlgp/util.py:457-499) and the in-place clip
+(:446-454).  Everything else in vlgp/util.py is post-hoc analysis and out of scope."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+__all__ = ["cut_trials", "cut_trial", "clip", "save", "load"]
+
+
+def clip(a, lbound, ubound=None):
+    """In-place clip; a single positive bound means [-bound, bound]."""
+    if ubound is None:
+        if not lbound > 0:
+            raise AssertionError("bound must be positive")
+        lbound, ubound = -lbound, lbound
+    elif not ubound > lbound:
+        raise AssertionError("ubound must exceed lbound")
+    np.clip(a, lbound, ubound, out=a)
+
+
+def window_starts(length: int, window: int):
+    """Start bins of the ceil(length/window) windows covering a trial.  When the length is not a multiple of the
+    window, the surplus is spread over the window boundaries by ONE draw of ``np.random.multinomial`` from the global
+    RNG (also drawn when the surplus is zero, so the RNG stream matches the reference's)."""
+    nseg = math.ceil(length / window)
+    surplus = nseg * window - length
+    grid = np.arange(nseg, dtype=int) * window
+    if nseg > 1:
+        spread = np.random.multinomial(surplus, np.full(nseg - 1, 1.0 / (nseg - 1)))
+    else:
+        # the reference divides by zero here (nseg - 1 == 0) and draws from an empty pvals vector; same draw, no warning
+        spread = np.random.multinomial(surplus, np.ones(0))
+    return grid - np.concatenate([[0], np.cumsum(spread)])
+
+
+def cut_trial(trial, window: int):
+    """Segments of exactly ``window`` bins whose arrays are VIEWS of the trial's arrays (so in-place updates of a
+    segment's mu/v show up in the trial, as in the reference)."""
+    segs = []
+    for s in window_starts(trial["y"].shape[0], window):
+        sl = slice(int(s), int(s) + window)
+        segs.append({k: trial[k][sl] for k in ("y", "x", "mu", "w", "v")})
+    return segs
+
+
+def cut_trials(trials, params, config):
+    window = config["window"]
+    if not window:
+        return trials
+    out = []
+    for tr in trials:
+        out.extend(cut_trial(tr, window))
+    arr = np.empty(len(out), dtype=object)      # the reference returns an object ndarray (np.concatenate of lists)
+    arr[:] = out
+    return arr
+
+
+def save(obj, fname, warnings=True):
+    """np.save of the (pickled) result dict, like vlgp/util.py:181-196; callables (params['transform']) are dropped."""
+    if isinstance(obj, dict) and isinstance(obj.get("params"), dict) and "transform" in obj["params"]:
+        obj = dict(obj, params={k: v for k, v in obj["params"].items() if k != "transform"})
+    np.save(fname, obj, allow_pickle=True)
+
+
+def load(fname):
+    out = np.load(fname, allow_pickle=True)
+    return out.item() if out.dtype == object and out.shape == () else out
