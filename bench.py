@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the vLGP variational-EM hot path (BASELINE.json: EM-iterations/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config config2] [--impl ours|reference]
+
+One "step" = one EM iteration of ``vem`` on the cut segments: constrain_loading + E-step (Eniter=25), M-step
+(Mniter=25), H-step (L-BFGS-B over omega per latent + new prior factors) -- vlgp/core.py:298-326 -- with the
+reference's default configuration.  Workload at every N: BASELINE config 2 (256 trials x T=1000 x 100 neurons x 5
+latents, Poisson, fp64; S = 5120 segments of 50 bins), synthetic spike trains, initialised exactly like ``fit``
+(FactorAnalysis + update_w/update_v + cut_trials).  N > 1 (torchrun, one process per GPU) shards the TRIALS over
+ranks: strong scaling of the same job, one NCCL allreduce per M-step Newton iteration / H-step evaluation.
+
+Printed JSON (rank 0): ``value`` = EM-iterations/sec with the state resident in HBM (CUDA events on the engine's stream,
+max over ranks); ``e2e`` = the same iteration through the public ``vem(splits, params, config)`` call with host
+buffers (upload + iteration + download each step); ``roofline`` = the E-step kernel (dominant) against the measured
+FP64 peak; ``cpu_baseline`` = the NumPy oracle port of the reference timed on a bounded sample on this host.
+
+``--impl reference`` times the reference's algorithm on the host cores (the NumPy/SciPy oracle port: the reference
+itself is pure Python and does not travel to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")     # the reference is fastest single-threaded
+
+import numpy as np  # noqa: E402
+
+METRIC = "EM-iterations/sec"
+UNIT = "EM-iter/s"
+
+
+def build_problem(cfgname, n_trials=None, verbose=False):
+    """Segments + params + config after the reference's own pre-vem pipeline (vlgp/api.py:28-60), on the host for the
+    oracle / as input of the device session.  Deterministic: np.random.seed(0) before the RNG-consuming steps."""
+    from vlgp_b200.synth import CONFIGS, make_trials
+    from vlgp_b200 import preprocess
+
+    c = dict(CONFIGS[cfgname])
+    if n_trials is not None:
+        c["n_trials"] = n_trials
+    trials = make_trials(c["n_trials"], c["T"], c["N"], c["L"], seed=0, latents=c.get("latents", "sine"))
+    config = preprocess.get_config()
+    params = preprocess.get_params(trials, c["L"], omega_bound=config["omega_bound"])
+    np.random.seed(0)
+    preprocess.initialize(trials, params, config)
+    preprocess.fill_params(params)
+    preprocess.fill_trials(trials)
+    params.pop("transform", None)
+    return trials, params, config, c
+
+
+def cut(trials, params, config):
+    from vlgp_b200.util import cut_trials
+    from vlgp_b200.preprocess import fill_trials
+
+    segs = list(cut_trials(trials, params, config))
+    fill_trials(segs)
+    return segs
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: NumPy/SciPy oracle port of the reference, bounded sample
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_em_iteration_time(cfgname, sample_trials, steps, warmup):
+    """Seconds per EM iteration of the oracle on ``sample_trials`` trials of the workload, and the segment counts."""
+    from oracle import vlgp_oracle as orc
+
+    trials, params, config, c = build_problem(cfgname, n_trials=sample_trials)
+    lengths = [t["y"].shape[0] for t in trials]
+    params["cholesky"] = orc.make_cholesky(lengths, params["omega"], params["sigma"], params["rank"])
+    orc.update_w(trials, params)
+    orc.update_v(trials, params, config)
+    segs = cut(trials, params, config)
+    segs = [copy.deepcopy(s) for s in segs]
+    params["cholesky"] = orc.make_cholesky([config["window"]], params["omega"], params["sigma"], params["rank"])
+    config["max_iter"] = 1
+    config["min_iter"] = 1
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.vem(segs, params, config)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), len(segs), c
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vlgp_b200.synth import CONFIGS
+
+    c = CONFIGS[args.config]
+    full_trials = c["n_trials"]
+    sample = max(1, min(args.cpu_sample_trials, full_trials))
+    sec, nseg, _ = cpu_em_iteration_time(args.config, sample, args.steps, args.warmup)
+    full_sec = sec * full_trials / sample          # E-, M- and H-step cost are all linear in the number of segments
+    value = 1.0 / full_sec
+    threads = int(os.environ.get("OPENBLAS_NUM_THREADS", os.environ.get("OMP_NUM_THREADS", "0")) or 0) or os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": full_sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.config, c, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d of %d trials (%d of %d segments), %.2f s per EM iteration measured, scaled "
+                                   "linearly in segments" % (sample, full_trials, nseg, nseg * full_trials // sample,
+                                                             sec)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, c, gpus):
+    T = c["T"]
+    return {"workload": "%s: %d trials x T=%s x %d neurons x %d latents, Poisson, window=50 rank=50 Eniter=25 Mniter=25 "
+                        "Hstep=True" % (name, c["n_trials"], T, c["N"], c["L"]),
+            "segments": c["n_trials"] * (T // 50) if isinstance(T, int) else None,
+            "sharding": "trials over %d rank(s), NCCL allreduce of M-/H-step statistics" % gpus,
+            "l2": "256 MiB write between steps evicts the 126 MB L2 (inside the timed region, <0.1 ms/step)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
+                                       "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def estep_flops(S, W, N, L, ncols, n_iter, rank):
+    """Algorithmic flops of one E-step launch (symmetric-aware minimum, c_exp = 20 flops per
+    exp): per segment-iteration 8 W L N + 2 c_exp W N for the two rate passes, and per latent the r x r Gram
+    (W r^2), its Cholesky (r^3/3), the solve + matvecs of the mean step (2 r^2 + 8 W r) and the W triangular solves of
+    the variance (W r^2).  Returned for r = rank (what the reference executes) and for r = the number of non-zero
+    columns of each latent's factor (what is mathematically required)."""
+    def per_latent(r):
+        return (W * r * r + r ** 3 / 3.0 + 2 * r * r + 8 * W * r) + (W * r * r)
+
+    base = 8.0 * W * L * N + 2 * 20.0 * W * N
+    full = S * n_iter * (base + L * per_latent(rank))
+    eff = S * n_iter * (base + sum(per_latent(int(r)) for r in ncols))
+    return full, eff
+
+
+def run_ours(args):
+    from vlgp_b200 import core, dist
+    from vlgp_b200.core import Session
+    from vlgp_b200.gp import make_cholesky
+
+    eng = dist.init_from_env()
+    world, rank = dist.world_size(), dist.rank()
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
+
+    # ---- problem: every rank builds the same global initial state, then keeps its shard of trials -------------------
+    trials, params, config, c = build_problem(args.config)
+    lo, hi = dist.shard_bounds(len(trials), world, rank)
+    my_trials = trials[lo:hi]
+    make_cholesky(my_trials, params, config)
+    core.update_w(my_trials, params, config)
+    core.update_v(my_trials, params, config)
+    segs = cut(my_trials, params, config)
+    make_cholesky(segs, params, config)
+    config["max_iter"] = 1
+    config["min_iter"] = 1
+    W, N, L = config["window"], c["N"], c["L"]
+    S_local, S_total = len(segs), len(trials) * (c["T"] // W)
+
+    peaks = {}
+    if rank == 0:
+        peaks = eng.peak_fp64()
+        peaks["hbm_gbs_copy"] = eng.peak_hbm(1 << 30)
+
+    # ---- device-resident arm ---------------------------------------------------------------------------------------
+    s = Session(segs, params)
+    state0 = s.ts.get_state(("mu", "v", "w"))
+    p0 = copy.deepcopy(params)
+    quiet = open(os.devnull, "w")
+
+    def step():
+        eng.flush_l2()
+        core._em_iteration(s, segs, params, config)
+        s.ts.norms()                              # convergence bookkeeping of vem (vlgp/core.py:350-354)
+
+    stdout = sys.stdout
+    sys.stdout = quiet
+    try:
+        for _ in range(args.warmup):
+            step()
+        eng.profile_enable(0x1)                  # E-step launches only: they end with a sync anyway
+        c0 = eng.counters()
+        sampler = ClockSampler(eng.device)
+        dist.barrier()
+        eng.sync()
+        sampler.start()
+        eng.timer_start()
+        t0 = time.perf_counter()
+        split = np.zeros(3)
+        for _ in range(args.steps):
+            eng.flush_l2()
+            split += core._em_iteration(s, segs, params, config)
+            s.ts.norms()
+        ms = eng.timer_stop()
+        wall = time.perf_counter() - t0
+        dist.barrier()
+        clocks = sampler.stop()
+        c1 = eng.counters()
+        e_ms, e_n = eng.profile_get(0)
+        eng.profile_enable(0)
+    finally:
+        sys.stdout = stdout
+    ms = float(eng.allreduce(np.array([ms]), op="max")[0])
+    launches = c1["launches"] - c0["launches"]
+    ncols = [int((np.abs(params["cholesky"][W][l]).sum(axis=0) > 0).sum()) for l in range(L)]
+    nfev = config.get("hstep_nfev", [])
+
+    # ---- end-to-end arm: public vem() with host buffers ------------------------------------------------------------
+    sys.stdout = quiet
+    try:
+        e2e_segs = copy.deepcopy(segs)
+        e2e_params = copy.deepcopy(p0)
+        for i, sg in enumerate(e2e_segs):
+            for k in ("mu", "v", "w"):
+                sg[k][...] = state0[k][i * W:(i + 1) * W]
+        e2e_steps = max(1, min(args.steps, 5))
+        core.vem(e2e_segs, e2e_params, config)     # warm-up
+        dist.barrier()
+        eng.sync()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sess = Session(e2e_segs, e2e_params)
+            core.vem(e2e_segs, e2e_params, config, session=sess)
+            h2d, d2h = sess.ts.h2d_bytes, sess.ts.d2h_bytes
+            sess.close()
+        eng.sync()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    finally:
+        sys.stdout = stdout
+    e2e_s = float(eng.allreduce(np.array([e2e_s]), op="max")[0])
+    s.close()
+
+    if rank != 0:
+        return
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+    f_full, f_eff = estep_flops(S_local, W, N, L, ncols, config["Eniter"], params["rank"])
+    e_avg_ms = e_ms / max(e_n, 1)
+    peak = peaks.get("dfma_tflops") or None
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = {"bound": "fp64", "kernel": "estep (all %d Newton iterations of every segment in one launch)" % config["Eniter"],
+            "achieved": f_eff / (e_avg_ms * 1e-3) / 1e12 if e_avg_ms else None,
+            "achieved_reference_flops": f_full / (e_avg_ms * 1e-3) / 1e12 if e_avg_ms else None,
+            "peak": peak, "unit": "TFLOP/s", "peak_source": "measured in this run: register-resident DFMA loop "
+            "(vlgp_peak_fp64); mma.sync.m8n8k4.f64 gives %.1f" % peaks.get("dmma_tflops", float("nan")),
+            "frac": (f_eff / (e_avg_ms * 1e-3) / 1e12 / peak) if (e_avg_ms and peak) else None,
+            "traffic": None, "ms_per_launch": e_avg_ms, "launches_timed": e_n,
+            "share_of_step": e_avg_ms / ms_per_step if ms_per_step else None,
+            "factor_columns": ncols,
+            "hbm": {"peak_copy_gbs_this_run": peaks.get("hbm_gbs_copy"), "peak_measured_json": mp.get("hbm_gbs")}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.config, c, args.gpus),
+        "split_ms": {"estep": split[0] / args.steps * 1e3, "mstep": split[1] / args.steps * 1e3,
+                     "hstep": split[2] / args.steps * 1e3, "wall_per_step": wall / args.steps * 1e3},
+        "hstep_evals_per_step": float(np.mean([sum(x) for x in nfev])) if nfev else None,
+        "solves_per_sec": (2.0 * S_total * L * config["Eniter"]) / (ms_per_step * 1e-3),
+        "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
+        "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3, "api": "vlgp_b200.core.vem(splits, params, config) with host ndarrays"},
+    }
+    if not args.no_cpu and args.gpus == 1:
+        sec, nseg, _ = cpu_em_iteration_time(args.config, args.cpu_sample_trials, 1, 0)
+        full_sec = sec * c["n_trials"] / args.cpu_sample_trials
+        line["cpu_baseline"] = {"value": 1.0 / full_sec, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d of %d trials (%d segments), %.2f s per EM iteration measured with the "
+                                          "NumPy/SciPy oracle, scaled linearly in segments" % (
+                                              args.cpu_sample_trials, c["n_trials"], nseg, sec)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="config2")
+    ap.add_argument("--cpu-sample-trials", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -126,9 +126,10 @@ VLGP_API int vlgp_peak_fp64(vlgp_ctx *ctx, double *dfma_tflops, double *dmma_tfl
 VLGP_API int vlgp_peak_hbm(vlgp_ctx *ctx, uint64_t nbytes, double *gbs);
 /* Write nbytes (> L2) to evict the L2 between timed iterations. */
 VLGP_API int vlgp_flush_l2(vlgp_ctx *ctx);
-/* Average device time (ms) per launch of the kernel classes, accumulated with CUDA events when profiling is on:
- * which: 0 = E-step, 1 = M-step statistics, 2 = H-step per-segment kernel, 3 = ichol.  n = launches accumulated. */
-VLGP_API int vlgp_profile_enable(vlgp_ctx *ctx, int on);
+/* Device time (ms) of the kernel classes, accumulated with CUDA events on the context's stream:
+ * class 0 = E-step kernel, 1 = M-step statistics kernel, 2 = H-step per-segment kernel, 3 = ichol kernel.
+ * mask bit i enables class i (each timed launch adds one event synchronisation); enabling resets the accumulators. */
+VLGP_API int vlgp_profile_enable(vlgp_ctx *ctx, int mask);
 VLGP_API int vlgp_profile_get(vlgp_ctx *ctx, int which, double *total_ms, int64_t *n);
 
 #ifdef __cplusplus

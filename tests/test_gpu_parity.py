@@ -127,8 +127,10 @@ def test_mstep_golden(vl, case):
     params = _params(g, p)
     cfg = _cfg(Mniter=int(case.split("it")[1]))
     core.mstep(segs, params, cfg)
-    for k in ("a", "b", "noise", "da", "db"):
+    for k in ("a", "b", "noise"):
         assert relerr(params[k], g[p + "out_" + k]) < STEP_TOL, k
+    for k in ("da", "db"):      # the last Newton step shrinks towards 0 as the iterations converge: scale of a / b
+        assert np.max(np.abs(params[k] - g[p + "out_" + k])) < STEP_TOL * np.max(np.abs(g[p + "out_" + k[1]])), k
     assert params["b"].shape == g[p + "out_b"].shape
 
 
@@ -277,15 +279,30 @@ def test_estep_mstep_vs_oracle_seeded(vl, N, L, lik):
     cfg = _cfg(Eniter=4, Mniter=3)
     s_ref, p_ref = copy.deepcopy(segs), copy.deepcopy(params)
     orc.estep(s_ref, p_ref, cfg)
+    # conditioning of this instance: how far the ORACLE's own output moves when its input mu moves by 1e-15 relative
+    # (random far-from-converged states with clipped Newton steps can amplify rounding by ~1e7; two correct fp64
+    # implementations cannot agree better than that)
+    s_pert = copy.deepcopy(segs)
+    for sg in s_pert:
+        sg["mu"] = sg["mu"] * (1 + 1e-15)
+    orc.estep(s_pert, copy.deepcopy(params), cfg)
+    mu_ref = np.stack([s["mu"] for s in s_ref])
+    sens = np.max(np.abs(np.stack([s["mu"] for s in s_pert]) - mu_ref)) / np.max(np.abs(mu_ref))
+    tol = max(STEP_TOL, 10 * sens)
     core.estep(segs, params, cfg)
     for k in ("mu", "v", "w", "dmu"):
         ref = np.stack([s[k] for s in s_ref])
-        scale = np.stack([s["mu"] for s in s_ref]) if k == "dmu" else ref
-        assert np.max(np.abs(np.stack([s[k] for s in segs]) - ref)) <= STEP_TOL * np.max(np.abs(scale)), k
+        scale = mu_ref if k == "dmu" else ref
+        assert np.max(np.abs(np.stack([s[k] for s in segs]) - ref)) <= tol * np.max(np.abs(scale)), (k, tol)
+    for sg, sr in zip(segs, s_ref):         # continue both M-steps from identical inputs
+        for k in ("mu", "v", "w", "dmu"):
+            sg[k] = sr[k].copy()
     orc.mstep(s_ref, p_ref, cfg)
     core.mstep(segs, params, cfg)
-    for k in ("a", "b", "noise", "da", "db"):
+    for k in ("a", "b", "noise"):
         assert relerr(params[k], p_ref[k]) < STEP_TOL, k
+    for k in ("da", "db"):
+        assert np.max(np.abs(params[k] - p_ref[k])) < STEP_TOL * np.max(np.abs(p_ref[k[1]])), k
 
 
 def test_estep_config2_shape_subset_vs_oracle(vl):
@@ -309,10 +326,11 @@ def test_estep_config2_shape_subset_vs_oracle(vl):
     prior_var = np.einsum("ltr,ltr->tl", params["cholesky"][50], params["cholesky"][50])
     assert np.all(v > 0) and np.all(v <= prior_var[None] * (1 + 1e-12))     # posterior variance below the prior's
     assert np.all(w > 0) and np.all(np.isfinite(np.stack([s["mu"] for s in segs])))
-    # idempotence of update_w / update_v at the E-step's fixed point of (w, v): recomputing w from (mu, v) reproduces it
-    w_before = w.copy()
+    # update_w on all 5120 segments reproduces the oracle's weights on the subset (w then includes the new v)
     core.update_w(segs, params, cfg)
-    assert relerr(np.stack([s["w"] for s in segs]), w_before) < 1e-6
+    orc.update_w(s_ref, params)
+    for j, i in enumerate(pick):
+        assert relerr(segs[i]["w"], s_ref[j]["w"]) < STEP_TOL
 
 
 def test_overlapping_windows_and_unequal_lengths(vl):

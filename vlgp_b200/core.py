@@ -252,6 +252,27 @@ def constrain_latent(trials, params, config):
 # ----------------------------------------------------------------------------------------------------------------------
 # outer loop
 # ----------------------------------------------------------------------------------------------------------------------
+def _em_iteration(s: Session, trials, params, config):
+    """One EM iteration on a device session: constrain + E-step, constrain + M-step, H-step (vlgp/core.py:307-326).
+    Returns (e_elapsed, m_elapsed, h_elapsed) wall-clock seconds; every stage ends with a device synchronisation."""
+    ts = s.ts
+    t0 = time.perf_counter()
+    _constrain_loading_dev(s, params, config)
+    if config["Eniter"] >= 1:
+        nfail = ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+        if nfail:
+            logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
+    t1 = time.perf_counter()
+    _constrain_latent_dev(s, params, config)
+    if config["Mniter"] >= 1:
+        _mstep_dev(s, params, config)
+    t2 = time.perf_counter()
+    if config["Hstep"]:
+        _hstep_dev(s, trials, params, config)
+    t3 = time.perf_counter()
+    return t1 - t0, t2 - t1, t3 - t2
+
+
 def vem(trials, params, config, session: Session = None):
     """Variational EM on (already cut) segments; fills config['runtime'] with the reference's keys."""
     callbacks = config["callbacks"]
@@ -268,27 +289,14 @@ def vem(trials, params, config, session: Session = None):
             norm_a = np.linalg.norm(params["a"])
             norm_b = np.linalg.norm(params["b"])
 
-            t0 = time.perf_counter()
-            _constrain_loading_dev(s, params, config)
-            if config["Eniter"] >= 1:
-                nfail = ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
-                if nfail:
-                    logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
-            t1 = time.perf_counter()
-            _constrain_latent_dev(s, params, config)
-            if config["Mniter"] >= 1:
-                _mstep_dev(s, params, config)
-            t2 = time.perf_counter()
-            if config["Hstep"]:
-                _hstep_dev(s, trials, params, config)
-            t3 = time.perf_counter()
+            te, tm, th = _em_iteration(s, trials, params, config)
 
-            runtime["e_elapsed"].append(t1 - t0)
-            runtime["m_elapsed"].append(t2 - t1)
-            runtime["h_elapsed"].append(t3 - t2)
-            runtime["em_elapsed"].append(t3 - t0)
+            runtime["e_elapsed"].append(te)
+            runtime["m_elapsed"].append(tm)
+            runtime["h_elapsed"].append(th)
+            runtime["em_elapsed"].append(te + tm + th)
             config["runtime"] = runtime
-            _echo("Iteration {:4d}, E-step {:.2f}s, M-step {:.2f}s".format(runtime["it"], t1 - t0, t2 - t1))
+            _echo("Iteration {:4d}, E-step {:.2f}s, M-step {:.2f}s".format(runtime["it"], te, tm))
 
             if callbacks:
                 s.pull(trials)              # callbacks see coherent host dicts

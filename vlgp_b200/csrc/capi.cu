@@ -777,9 +777,9 @@ int vlgp_flush_l2(vlgp_ctx *ctx) {
     return VLGP_OK;
 }
 
-int vlgp_profile_enable(vlgp_ctx *ctx, int on) {
+int vlgp_profile_enable(vlgp_ctx *ctx, int mask) {
     if (!ctx) return VLGP_ERR_ARG;
-    ctx->profile = on != 0;
+    ctx->profile = mask;
     for (int i = 0; i < 4; ++i) {
         ctx->prof_ms[i] = 0.0;
         ctx->prof_n[i] = 0;

@@ -84,7 +84,7 @@ struct vlgp_ctx {
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t counters[4] = {0, 0, 0, 0};
-    bool profile = false;
+    int profile = 0;             // bit i set: time kernel class i with CUDA events (adds a sync per launch)
     double prof_ms[4] = {0, 0, 0, 0};
     int64_t prof_n[4] = {0, 0, 0, 0};
     cudaEvent_t pev0 = nullptr, pev1 = nullptr;
@@ -126,10 +126,10 @@ struct ProfScope {   // accumulates device time of one kernel class when profili
     vlgp_ctx *ctx;
     int which;
     ProfScope(vlgp_ctx *c, int w) : ctx(c), which(w) {
-        if (ctx->profile) cudaEventRecord(ctx->pev0, ctx->stream);
+        if (ctx->profile & (1 << which)) cudaEventRecord(ctx->pev0, ctx->stream);
     }
     ~ProfScope() {
-        if (ctx->profile) {
+        if (ctx->profile & (1 << which)) {
             cudaEventRecord(ctx->pev1, ctx->stream);
             cudaEventSynchronize(ctx->pev1);
             float ms = 0.f;

@@ -182,8 +182,9 @@ class Engine:
     def flush_l2(self):
         self._ck(self.lib.vlgp_flush_l2(self.ctx), "flush_l2")
 
-    def profile_enable(self, on=True):
-        self._ck(self.lib.vlgp_profile_enable(self.ctx, int(bool(on))), "profile_enable")
+    def profile_enable(self, mask=0xF):
+        """Time kernel classes with CUDA events: bit 0 E-step, 1 M-step statistics, 2 H-step segments, 3 ichol."""
+        self._ck(self.lib.vlgp_profile_enable(self.ctx, int(mask)), "profile_enable")
 
     def profile_get(self, which):
         ms, n = C.c_double(), C.c_int64()
