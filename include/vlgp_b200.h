@@ -75,6 +75,11 @@ VLGP_API int vlgp_get_params(vlgp_ctx *ctx, double *a, double *b, double *noise,
 VLGP_API int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int *set_id);
 VLGP_API int vlgp_trials_free(vlgp_ctx *ctx, int set_id);
 VLGP_API int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydtype);
+/* Same from per-trial blocks (parts[i]: rows[i] x N, C-contiguous, dtype src_dtype) without a host-side concatenation:
+ * blocks are converted/copied into pinned staging by host threads and uploaded in a double-buffered pipeline.  float64
+ * blocks holding only integer counts in [0,255] are stored as uint8; *stored_dtype returns the choice. */
+VLGP_API int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *const *parts, const int64_t *rows,
+                            int src_dtype, int *stored_dtype);
 VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w);
 VLGP_API int vlgp_trials_get_state(vlgp_ctx *ctx, int set_id, double *mu, double *v, double *w, double *dmu);
 

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import logging
 import time
+import weakref
 
 import numpy as np
 
@@ -33,6 +34,37 @@ def _echo(msg):
         print(msg)
 
 
+_ONES_VERIFIED = {}      # id(array) -> weakref: regressor arrays already known to be all ones
+
+
+def _all_ones(x):
+    """True if the (bins, 1, neurons) regressor is the all-ones bias column.  Segments made by cut_trials are views of
+    their trial's x: the trial-level array is scanned once and remembered (weakly), not once per segment per call."""
+    base = x
+    while isinstance(base.base, np.ndarray):
+        base = base.base
+    ref = _ONES_VERIFIED.get(id(base))
+    if ref is not None and ref() is base:
+        return True
+    if base.min() != 1 or base.max() != 1:
+        return base is not x and x.min() == 1 and x.max() == 1
+    try:
+        key = id(base)
+        _ONES_VERIFIED[key] = weakref.ref(base, lambda _r, k=key: _ONES_VERIFIED.pop(k, None))
+    except TypeError:  # pragma: no cover
+        pass
+    return True
+
+
+def _check_regressors(trials):
+    for tr in trials:
+        x = tr.get("x")
+        if x is None:
+            continue
+        if x.ndim != 3 or x.shape[1] != 1 or not _all_ones(x):
+            raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
+
+
 class Session:
     """Device copy of a list of trials plus the current parameters."""
 
@@ -43,14 +75,10 @@ class Session:
         eng.push_params(params)
         self.n = len(trials)
         lengths = [tr["y"].shape[0] for tr in trials]
-        for tr in trials:
-            x = tr.get("x")
-            if x is not None and (x.ndim != 3 or x.shape[1] != 1 or x.min() != 1 or x.max() != 1):
-                raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
+        _check_regressors(trials)
         self.ts: TrialSet = eng.new_trials(lengths)
         try:
-            y, ydt = pack_y([tr["y"] for tr in trials])
-            self.ts.set_y(y, ydt)
+            self.ts.set_y_parts([tr["y"] for tr in trials])
             L = eng.L
 
             def cat(key):

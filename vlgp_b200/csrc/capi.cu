@@ -3,7 +3,9 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <thread>
 
 #include "common.cuh"
 #include "linalg.cuh"
@@ -202,6 +204,10 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_small); F(ctx->d_flush);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->pev0); cudaEventDestroy(ctx->pev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -430,6 +436,106 @@ int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydtype) {
     CK(cudaMemcpyAsync(ts->d_y, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VLGP_OK;
+}
+
+// Gather per-trial observation blocks (each rows[i] x N, C-contiguous) into the set's device buffer through two pinned
+// staging buffers: host threads convert/copy block k+1 while block k is in flight over PCIe.  float64 sources holding
+// only integer counts in [0, 255] are stored as uint8 (8x less HBM traffic in every pass over y); anything else stays
+// float64.  stored_dtype returns what was chosen.
+int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *const *parts, const int64_t *rows,
+                            int src_dtype, int *stored_dtype) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && parts && rows && n_parts >= 1, "trials_set_y_parts: bad arguments");
+    REQUIRE(src_dtype == VLGP_Y_F64 || src_dtype == VLGP_Y_U8, "trials_set_y_parts: bad dtype %d", src_dtype);
+    CK(cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    int64_t total = 0;
+    for (int i = 0; i < n_parts; ++i) total += rows[i];
+    REQUIRE(total == ts->nbin, "trials_set_y_parts: parts hold %lld rows, the set has %lld bins", (long long)total,
+            (long long)ts->nbin);
+    const size_t STAGE = (size_t)8 << 20;          // bytes per pinned staging buffer
+    if (!ctx->h_stage[0]) {
+        CK(cudaMallocHost(&ctx->h_stage[0], STAGE));
+        CK(cudaMallocHost(&ctx->h_stage[1], STAGE));
+        CK(cudaEventCreateWithFlags(&ctx->stage_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->stage_ev[1], cudaEventDisableTiming));
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+
+    // Flatten the parts into one virtual element range [0, total * N) so that chunks need not align with parts.
+    std::vector<int64_t> part_off(n_parts + 1, 0);
+    for (int i = 0; i < n_parts; ++i) part_off[i + 1] = part_off[i] + rows[i] * (int64_t)N;
+    const int64_t nelem = part_off[n_parts];
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // attempt 0: store uint8 (convert + verify when the source is float64); attempt 1: store float64 as is
+        const int dst_dtype = (attempt == 0) ? VLGP_Y_U8 : VLGP_Y_F64;
+        if (attempt == 1 && src_dtype == VLGP_Y_U8) break;
+        const size_t esz = dst_dtype == VLGP_Y_U8 ? 1 : sizeof(double);
+        if (ts->d_y && ts->ydtype != dst_dtype) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ts->d_y));
+            ts->d_y = nullptr;
+        }
+        if (!ts->d_y) CK(cudaMalloc(&ts->d_y, (size_t)nelem * esz));
+        ts->ydtype = dst_dtype;
+        const int64_t chunk = (int64_t)(STAGE / esz);
+        std::atomic<bool> exact(true);
+        int buf = 0;
+        int ip = 0;                                  // part containing the chunk start
+        for (int64_t e0 = 0; e0 < nelem && exact.load(); e0 += chunk, buf ^= 1) {
+            const int64_t e1 = std::min(nelem, e0 + chunk);
+            CK(cudaEventSynchronize(ctx->stage_ev[buf]));        // previous copy out of this buffer has finished
+            while (part_off[ip + 1] <= e0) ++ip;
+            // split [e0, e1) among the threads
+            auto work = [&](int t) {
+                const int64_t per = (e1 - e0 + nthreads - 1) / nthreads;
+                int64_t a = e0 + t * per, b = std::min(e1, a + per);
+                if (a >= b) return;
+                int p = ip;
+                while (part_off[p + 1] <= a) ++p;
+                while (a < b) {
+                    const int64_t stop = std::min(b, part_off[p + 1]);
+                    const int64_t loc = a - part_off[p];
+                    const int64_t cnt = stop - a;
+                    unsigned char *dst = (unsigned char *)ctx->h_stage[buf] + (size_t)(a - e0) * esz;
+                    if (dst_dtype == VLGP_Y_F64) {
+                        memcpy(dst, (const double *)parts[p] + loc, (size_t)cnt * sizeof(double));
+                    } else if (src_dtype == VLGP_Y_U8) {
+                        memcpy(dst, (const unsigned char *)parts[p] + loc, (size_t)cnt);
+                    } else {
+                        const double *src = (const double *)parts[p] + loc;
+                        bool ok = true;
+                        for (int64_t k = 0; k < cnt; ++k) {
+                            const double v = src[k];
+                            const bool in = (v >= 0.0) & (v <= 255.0);         // also false for NaN
+                            const unsigned char c = in ? (unsigned char)(int)v : (unsigned char)0;
+                            dst[k] = c;
+                            ok &= in & ((double)c == v);                       // exact only for integer counts
+                        }
+                        if (!ok) exact.store(false);
+                    }
+                    a = stop;
+                    ++p;
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+            if (!exact.load()) break;
+            CK(cudaMemcpyAsync((unsigned char *)ts->d_y + (size_t)e0 * esz, ctx->h_stage[buf], (size_t)(e1 - e0) * esz,
+                               cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaEventRecord(ctx->stage_ev[buf], ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (exact.load()) {
+            if (stored_dtype) *stored_dtype = dst_dtype;
+            return VLGP_OK;
+        }
+    }
+    return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_set_y_parts: uint8 source could not be stored");
 }
 
 int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w) {

@@ -77,6 +77,8 @@ struct vlgp_ctx {
     int *h_flags = nullptr;      // pinned
     double *h_pin = nullptr;     // pinned 4 KB staging for tiny D2H/H2D
     double *d_small = nullptr;   // 4 KB device staging
+    void *h_stage[2] = {nullptr, nullptr};        // pinned double buffer of the y upload pipeline
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     // comm
     NcclApi *nccl = nullptr;
     void *comm = nullptr;

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT) estep_generic_kernel(EstepArgs p) {
     const int ld = rank | 1;                 // odd leading dimension: conflict-free row-per-lane access
     double *Aw = sm;                         // rank x ld
     double *ck = Aw + rank * ld;             // 64
-    double *pv = ck + 64;                    // 64
+    double *pv = ck + 128;                   // 64   (ck: 2 x 64, double-buffered pivot column)
     double *cv = pv + 64;                    // 64
     double *mv = cv + 64;                    // 64
     double *part = mv + 64;                  // 4 x 64
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(NT) estep_generic_kernel(EstepArgs p) {
 template <int LT>
 int launch_estep_t(vlgp_ctx *ctx, TrialSet *ts, EstepArgs &p) {
     const int rank = p.rank;
-    const size_t smem = ((size_t)rank * (rank | 1) + 64 * 8) * sizeof(double);
+    const size_t smem = ((size_t)rank * (rank | 1) + 64 * 9) * sizeof(double);
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(estep_generic_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NT) hstep_global_kernel(int W, double dt, doub
     double *Aw = sm;                   // W x ld : K -> -K^-1
     double *Tm = Aw + W * ld;          // W x ld : K^-1 M
     double *ck = Tm + W * ld;          // 64
-    double *red = ck + 64;             // 32
+    double *red = ck + 128;            // 32   (ck: 2 x 64)
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     for (int i = ty; i < W; i += 16)
         for (int j = tx; j < W; j += 16) {
@@ -125,32 +125,51 @@ __global__ void __launch_bounds__(NT) hstep_global_kernel(int W, double dt, doub
 }
 
 // ---- per evaluation, one CTA per segment: B_i^-1 by sweep ---------------------------------------------------------
-__global__ void __launch_bounds__(NT) hstep_segment_kernel(int nseg, int W, int L, int l, const double *__restrict__ w,
+__global__ void __launch_bounds__(NT, 2) hstep_segment_kernel(int nseg, int W, int L, int l, const double *__restrict__ w,
                                                            const double *__restrict__ K, const double *__restrict__ dK,
                                                            double *__restrict__ part, int *__restrict__ flags) {
-    extern __shared__ double sm[];
-    const int ld = W | 1;
-    double *Aw = sm;                   // W x ld
-    double *dv = Aw + W * ld;          // 64 sqrt(w)
-    double *ck = dv + 64;              // 64
-    double *red = ck + 64;             // 32
+    // The W x W matrix lives in registers (16 x 16 thread grid, 4 x 4 cyclic elements per thread, see linalg.cuh);
+    // K is read once per CTA into registers in the same layout and reused for every segment of the CTA.
+    __shared__ double dv[64];          // sqrt(w)
+    __shared__ double ck[128];
+    __shared__ double red[32];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double kreg[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ty + 16 * p, j = tx + 16 * q;
+            kreg[p][q] = (i < W && j < W) ? K[i * W + j] : 0.0;
+        }
     for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
         __syncthreads();
-        if (tid < W) dv[tid] = sqrt(fmax(w[((size_t)seg * W + tid) * L + l], 0.0));
+        if (tid < 64) dv[tid] = tid < W ? sqrt(fmax(w[((size_t)seg * W + tid) * L + l], 0.0)) : 0.0;
         __syncthreads();
-        for (int i = ty; i < W; i += 16)
-            for (int j = tx; j < W; j += 16)
-                Aw[i * ld + j] = dv[i] * K[i * W + j] * dv[j] + (i == j ? 1.0 : 0.0);
-        __syncthreads();
-        const bool ok = block_sweep_spd(Aw, ld, W, ck, nullptr);
+        double di[4], dj[4], a[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            di[p] = dv[ty + 16 * p];
+            dj[p] = dv[tx + 16 * p];
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = ty + 16 * p, j = tx + 16 * q;
+                a[p][q] = di[p] * kreg[p][q] * dj[q] + ((i == j && i < W) ? 1.0 : 0.0);
+            }
+        const bool ok = block_sweep_regs(a, W, ck, nullptr);
         double tr = 0.0, pd = 0.0;
         if (ok) {
-            for (int i = ty; i < W; i += 16)
-                for (int j = tx; j < W; j += 16) {
-                    const double binv = -Aw[i * ld + j];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = ty + 16 * p, j = tx + 16 * q;
+                    const double binv = -a[p][q];
                     if (i == j) tr += binv;
-                    pd = fma(binv * dv[i] * dv[j], dK[i * W + j], pd);
+                    if (i < W && j < W) pd = fma(binv * di[p] * dj[q], __ldg(dK + i * W + j), pd);
                 }
         } else if (tid == 0) {
             atomicAdd(flags + 3, 1);
@@ -214,8 +233,8 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, int l, double sigma
                                 double out5[5], int *info) {
     const int W = ts->max_len, L = ctx->L, S = ts->n_trials;
     const int ld = W | 1;
-    const size_t smem_g = ((size_t)2 * W * ld + 96) * sizeof(double);
-    const size_t smem_s = ((size_t)W * ld + 160) * sizeof(double);
+    const size_t smem_g = ((size_t)2 * W * ld + 160) * sizeof(double);
+    const size_t smem_s = 0;
     if (smem_g > 48 * 1024)
         CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
     if (smem_s > 48 * 1024)

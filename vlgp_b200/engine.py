@@ -235,6 +235,30 @@ class TrialSet:
         self.eng._ck(lib.vlgp_trials_set_y(ctx, self.id, y.ctypes.data_as(C.c_void_p), int(ydtype)), "trials_set_y")
         self.h2d_bytes += y.nbytes
 
+    def set_y_parts(self, ys):
+        """Upload per-trial observation blocks without concatenating them on the host (native pinned pipeline).
+        Returns the stored dtype code (1 = uint8 counts, 0 = float64)."""
+        lib, ctx = self._lib()
+        N = self.eng.N
+        if len(ys) != self.lengths.size:
+            raise ValueError("expected %d observation blocks, got %d" % (self.lengths.size, len(ys)))
+        src_u8 = all(y.dtype == np.uint8 for y in ys)
+        want = np.uint8 if src_u8 else np.float64
+        keep = []
+        for y, n in zip(ys, self.lengths):
+            if y.shape != (int(n), N):
+                raise ValueError("observation block must be (%d, %d), got %s" % (n, N, y.shape))
+            if y.dtype != want or not y.flags.c_contiguous:
+                y = np.ascontiguousarray(y, dtype=want)
+            keep.append(y)
+        ptrs = (C.c_void_p * len(keep))(*[y.__array_interface__["data"][0] for y in keep])
+        rows = np.ascontiguousarray(self.lengths, dtype=np.int64)
+        stored = C.c_int()
+        self.eng._ck(lib.vlgp_trials_set_y_parts(ctx, self.id, len(keep), ptrs, rows.ctypes.data_as(_lib.c_i64_p),
+                                                 1 if src_u8 else 0, C.byref(stored)), "trials_set_y_parts")
+        self.h2d_bytes += self.nbin * N * (1 if stored.value == 1 else 8)
+        return stored.value
+
     def set_state(self, mu=None, v=None, w=None):
         lib, ctx = self._lib()
         shp = (self.nbin, self.eng.L)
