@@ -38,7 +38,7 @@ EXPORTS = {
     "vlgp_trials_create": (C.c_int, [ctx_p, C.c_int, c_i32_p, c_int_p]),
     "vlgp_trials_free": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_trials_set_y": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_int]),
-    "vlgp_trials_set_y_parts": (C.c_int, [ctx_p, C.c_int, C.POINTER(C.c_void_p), c_i64_p, C.c_int, c_int_p]),
+    "vlgp_trials_set_y_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_i64_p, C.c_int, c_int_p]),
     "vlgp_trials_set_state": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "vlgp_trials_get_state": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "vlgp_make_cholesky": (C.c_int, [ctx_p, C.c_int]),
