@@ -13,6 +13,9 @@
 #include "common.cuh"
 #include "linalg.cuh"
 
+int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double *dKd,
+                                    bool *handled);   // hstep_dmma.cu
+
 namespace {
 
 constexpr int NT = 256;
@@ -251,9 +254,14 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, int l, double sigma
     if (grid > S) grid = S;
     {
         ProfScope ps(ctx, 2);
-        hstep_segment_kernel<<<grid, NT, smem_s, ctx->stream>>>(S, W, L, l, ts->d_w, Kd, dKd, ts->d_hpart,
-                                                                ctx->d_flags);
-        CKL();
+        bool handled = false;
+        int rcd = vlgp_launch_hstep_segments_dmma(ctx, ts, l, Kd, dKd, &handled);
+        if (rcd) return rcd;
+        if (!handled) {
+            hstep_segment_kernel<<<grid, NT, smem_s, ctx->stream>>>(S, W, L, l, ts->d_w, Kd, dKd, ts->d_hpart,
+                                                                    ctx->d_flags);
+            CKL();
+        }
     }
     hstep_final_kernel<<<1, NT, 0, ctx->stream>>>(S, ts->d_hpart, ts->d_hout);
     CKL();

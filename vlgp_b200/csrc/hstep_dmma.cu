@@ -1,0 +1,258 @@
+// K7 (per-segment part) on the FP64 tensor path: one WARP per segment, the W x W matrix B_i = I + d K d (d = sqrt(w_i))
+// held entirely in registers as 8 x 8 tiles in the accumulator layout of mma.sync.m8n8k4.f64, inverted in place by a
+// BLOCKED symmetric sweep whose rank-8 updates are DMMA instructions.
+//
+// Block sweep on pivot block k (block generalisation of the scalar sweep in linalg.cuh; after all blocks the tiles hold
+// -B^-1):   P = A_kk^-1 ;  A_ik <- A_ik P ;  A_ij <- A_ij - A_ik P A_kj  (i, j != k) ;  A_kk <- -P
+// Only the lower block triangle is stored (NB (NB+1) / 2 tiles, 2 doubles per lane each).  Operand fragments are
+// produced from accumulator-layout tiles with intra-warp shuffles ("N-form": element [lane/4][4h + lane%4], "T-form":
+// element [4h + lane%4][lane/4]); the 8 x 8 pivot block is inverted by an 8-step scalar sweep done with shuffles.
+// No shared-memory traffic and no block barrier inside a segment; K and dK/dlog(omega) sit in shared memory in tile
+// order and are reused by every segment the CTA processes.  The lane-level algorithm was validated against
+// numpy.linalg.inv with a 32-lane emulation before it was written in CUDA (scripts/dmma_block_sweep_emulation.py).
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS = 4;
+
+struct Tile {
+    double x, y;      // [lane/4][2 (lane%4)], [lane/4][2 (lane%4) + 1]
+};
+
+__device__ __forceinline__ void dmma(Tile &c, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c.x), "+d"(c.y)
+                 : "d"(a), "d"(b));
+}
+
+// Tile[lane/4][4h + lane%4]
+__device__ __forceinline__ double nform(const Tile &t, int h, int lane) {
+    const int src = (lane & ~3) | (2 * h + ((lane & 3) >> 1));
+    const double a = __shfl_sync(FULL, t.x, src), b = __shfl_sync(FULL, t.y, src);
+    return (lane & 1) ? b : a;
+}
+
+// Tile[4h + lane%4][lane/4]
+__device__ __forceinline__ double tform(const Tile &t, int h, int lane) {
+    const int src = 4 * (4 * h + (lane & 3)) + (lane >> 3);
+    const double a = __shfl_sync(FULL, t.x, src), b = __shfl_sync(FULL, t.y, src);
+    return ((lane >> 2) & 1) ? b : a;
+}
+
+// In-place inverse of an SPD 8 x 8 tile (accumulator layout) by an 8-step scalar sweep.  Returns false (warp-uniform)
+// if a pivot is not positive, i.e. the matrix is not positive definite.
+__device__ __forceinline__ bool tile_spd_inverse(Tile &t, int lane) {
+    const int r = lane >> 2, c0 = 2 * (lane & 3);
+    bool ok = true;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const double comp = (p & 1) ? t.y : t.x;
+        const double d = __shfl_sync(FULL, comp, 4 * p + (p >> 1));            // a[p][p]
+        const double cr = __shfl_sync(FULL, comp, (lane & ~3) | (p >> 1));     // a[r][p]
+        const double pc0 = __shfl_sync(FULL, t.x, 4 * p + (lane & 3));         // a[p][c0]
+        const double pc1 = __shfl_sync(FULL, t.y, 4 * p + (lane & 3));         // a[p][c0 + 1]
+        ok = ok && (d > 0.0);
+        const double pinv = 1.0 / d;
+        const double crp = cr * pinv;
+        double nx = fma(-crp, pc0, t.x), ny = fma(-crp, pc1, t.y);
+        if (r == p) {
+            nx = pc0 * pinv;
+            ny = pc1 * pinv;
+        }
+        if (c0 == p) nx = (r == p) ? -pinv : crp;
+        if (c0 + 1 == p) ny = (r == p) ? -pinv : crp;
+        t.x = nx;
+        t.y = ny;
+    }
+    t.x = -t.x;
+    t.y = -t.y;
+    return ok;
+}
+
+__host__ __device__ constexpr int tix(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <int NB>
+__global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(int nseg, int W, int L, int l,
+                                                                        const double *__restrict__ w,
+                                                                        const double *__restrict__ K,
+                                                                        const double *__restrict__ dK,
+                                                                        double *__restrict__ part,
+                                                                        int *__restrict__ flags) {
+    constexpr int NT = NB * (NB + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *Ks = (double2 *)smem_raw;                 // NT x 32 : K in tile / lane order
+    double2 *dKs = Ks + NT * 32;                       // NT x 32 : dK/dlog(omega)
+    double *dsm = (double *)(dKs + NT * 32);           // WARPS x 64 : sqrt(w) of the warp's segment (0 beyond W)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r = lane >> 2, c0 = 2 * (lane & 3);
+
+    for (int t = wid; t < NT; t += WARPS) {
+        int i = 0;
+        while (tix(i + 1, 0) <= t) ++i;
+        const int j = t - tix(i, 0);
+        const int gi = 8 * i + r, gj = 8 * j + c0;
+        double2 kv, dv;
+        kv.x = (gi < W && gj < W) ? K[gi * W + gj] : 0.0;
+        kv.y = (gi < W && gj + 1 < W) ? K[gi * W + gj + 1] : 0.0;
+        dv.x = (gi < W && gj < W) ? dK[gi * W + gj] : 0.0;
+        dv.y = (gi < W && gj + 1 < W) ? dK[gi * W + gj + 1] : 0.0;
+        Ks[t * 32 + lane] = kv;
+        dKs[t * 32 + lane] = dv;
+    }
+    __syncthreads();
+
+    double *dw = dsm + wid * 64;
+    const int stride = gridDim.x * WARPS;
+    for (int seg = blockIdx.x * WARPS + wid; seg < nseg; seg += stride) {
+        __syncwarp();
+        for (int t = lane; t < 64; t += 32)
+            dw[t] = t < W ? sqrt(fmax(w[((size_t)seg * W + t) * L + l], 0.0)) : 0.0;
+        __syncwarp();
+        double di[NB], dj0[NB], dj1[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            di[b] = dw[8 * b + r];
+            dj0[b] = dw[8 * b + c0];
+            dj1[b] = dw[8 * b + c0 + 1];
+        }
+        // ---- B = I + d K d in tiles (identity on the padding) --------------------------------------------------
+        Tile A[NT];
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double2 kv = Ks[tix(i, j) * 32 + lane];
+                A[tix(i, j)].x = fma(di[i] * kv.x, dj0[j], (i == j && r == c0) ? 1.0 : 0.0);
+                A[tix(i, j)].y = fma(di[i] * kv.y, dj1[j], (i == j && r == c0 + 1) ? 1.0 : 0.0);
+            }
+        // ---- blocked symmetric sweep -> tiles hold -B^-1 ----------------------------------------------------------
+        bool ok = true;
+#pragma unroll
+        for (int kb = 0; kb < NB; ++kb) {
+            Tile P = A[tix(kb, kb)];
+            ok = tile_spd_inverse(P, lane) && ok;
+            const double Pt0 = tform(P, 0, lane), Pt1 = tform(P, 1, lane);
+            const double Pn0 = nform(P, 0, lane), Pn1 = nform(P, 1, lane);
+            double V0[NB], V1[NB];            // operand form of the OLD block column A_{m,kb} (rows = block m)
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (m == kb) continue;
+                if (m > kb) {
+                    V0[m] = nform(A[tix(m, kb)], 0, lane);
+                    V1[m] = nform(A[tix(m, kb)], 1, lane);
+                } else {
+                    V0[m] = tform(A[tix(kb, m)], 0, lane);
+                    V1[m] = tform(A[tix(kb, m)], 1, lane);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {    // new block column: A_{m,kb} P  (stored transposed for m < kb)
+                if (m == kb) continue;
+                Tile T{0.0, 0.0};
+                if (m > kb) {
+                    dmma(T, V0[m], Pt0);
+                    dmma(T, V1[m], Pt1);
+                    A[tix(m, kb)] = T;
+                } else {
+                    dmma(T, Pn0, V0[m]);
+                    dmma(T, Pn1, V1[m]);
+                    A[tix(kb, m)] = T;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {    // A_ij -= (A_ik P) A_kj
+                if (i == kb) continue;
+                double T0, T1;
+                if (i > kb) {
+                    T0 = -nform(A[tix(i, kb)], 0, lane);
+                    T1 = -nform(A[tix(i, kb)], 1, lane);
+                } else {
+                    T0 = -tform(A[tix(kb, i)], 0, lane);
+                    T1 = -tform(A[tix(kb, i)], 1, lane);
+                }
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    if (j == kb) continue;
+                    dmma(A[tix(i, j)], T0, V0[j]);
+                    dmma(A[tix(i, j)], T1, V1[j]);
+                }
+            }
+            A[tix(kb, kb)].x = -P.x;
+            A[tix(kb, kb)].y = -P.y;
+        }
+        // ---- tr(B^-1) and (d B^-1 d) : dK ---------------------------------------------------------------------------
+        double tr = 0.0, pd = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double2 dv = dKs[tix(i, j) * 32 + lane];
+                const double bx = -A[tix(i, j)].x, by = -A[tix(i, j)].y;
+                const double wgt = (i == j) ? 1.0 : 2.0;
+                pd = fma(wgt * bx * di[i] * dj0[j], dv.x, pd);
+                pd = fma(wgt * by * di[i] * dj1[j], dv.y, pd);
+                if (i == j) {
+                    const int gi = 8 * i + r;
+                    if (r == c0 && gi < W) tr += bx;
+                    if (r == c0 + 1 && gi < W) tr += by;
+                }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tr += __shfl_xor_sync(FULL, tr, o);
+            pd += __shfl_xor_sync(FULL, pd, o);
+        }
+        if (lane == 0) {
+            if (!ok) {
+                atomicAdd(flags + 3, 1);
+                tr = 0.0;
+                pd = 0.0;
+            }
+            part[seg] = tr;
+            part[nseg + seg] = pd;
+        }
+    }
+}
+
+template <int NB>
+int launch_t(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double *dKd) {
+    constexpr int NT = NB * (NB + 1) / 2;
+    const size_t smem = (size_t)2 * NT * 32 * sizeof(double2) + WARPS * 64 * sizeof(double);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(hstep_segment_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_dmma_kernel<NB>, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int S = ts->n_trials;
+    int grid = per_sm * ctx->prop.multiProcessorCount;
+    if (grid > (S + WARPS - 1) / WARPS) grid = (S + WARPS - 1) / WARPS;
+    hstep_segment_dmma_kernel<NB><<<grid, WARPS * 32, smem, ctx->stream>>>(S, ts->max_len, ctx->L, l, ts->d_w, Kd, dKd,
+                                                                          ts->d_hpart, ctx->d_flags);
+    CKL();
+    return VLGP_OK;
+}
+
+}   // namespace
+
+// Returns VLGP_OK and sets *handled when the window fits the register-resident tile layout (W <= 56).
+int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double *dKd,
+                                    bool *handled) {
+    *handled = false;
+    if (getenv("VLGP_FORCE_SWEEP_HSTEP")) return VLGP_OK;
+    const int NB = (ts->max_len + 7) / 8;
+    int rc = VLGP_OK;
+    switch (NB) {
+        case 1: rc = launch_t<1>(ctx, ts, l, Kd, dKd); break;
+        case 2: rc = launch_t<2>(ctx, ts, l, Kd, dKd); break;
+        case 3: rc = launch_t<3>(ctx, ts, l, Kd, dKd); break;
+        case 4: rc = launch_t<4>(ctx, ts, l, Kd, dKd); break;
+        case 5: rc = launch_t<5>(ctx, ts, l, Kd, dKd); break;
+        case 6: rc = launch_t<6>(ctx, ts, l, Kd, dKd); break;
+        case 7: rc = launch_t<7>(ctx, ts, l, Kd, dKd); break;
+        default: return VLGP_OK;          // W > 56: the CTA-wide sweep kernel in hstep.cu handles it
+    }
+    if (rc == VLGP_OK) *handled = true;
+    return rc;
+}
