@@ -237,17 +237,31 @@ def golden_fit(ref):
     print("fit_tutorial.npz", len(out))
 
 
+def golden_fit_fixed_omega(ref):
+    """fit() with Hstep=False: omega stays at its initial value, so the prior factors (and their pivot sets) are the
+    same on both sides and the whole chain initialise -> update_w/v -> cut -> vem -> infer can be compared tightly."""
+    out = {}
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    np.random.seed(0)
+    res = ref.fit(trials, 3, max_iter=3, min_iter=3, Hstep=False)
+    out["mu"] = np.stack([t["mu"] for t in res["trials"]])
+    out["v"] = np.stack([t["v"] for t in res["trials"]])
+    out["w"] = np.stack([t["w"] for t in res["trials"]])
+    for k in ("a", "b", "noise", "omega", "sigma"):
+        out[k] = np.array(res["params"][k])
+    np.savez_compressed(os.path.join(OUT, "fit_fixed_omega.npz"), **out)
+    print("fit_fixed_omega.npz", len(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
     import vlgp.preprocess, vlgp.core, vlgp.gp, vlgp.math, vlgp.util  # noqa: F401,E401
-    golden_ichol(ref)
-    golden_estep(ref)
-    golden_mstep(ref)
-    golden_hstep(ref)
-    golden_update_wv(ref)
-    golden_vem(ref)
-    golden_fit(ref)
+    only = sys.argv[1:]
+    for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
+               golden_fit_fixed_omega):
+        if not only or fn.__name__.replace("golden_", "") in only:
+            fn(ref)
 
 
 if __name__ == "__main__":

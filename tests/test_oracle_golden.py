@@ -154,3 +154,35 @@ def test_cut_trial_starts_matches_reference_rule():
     np.random.seed(3)
     s2 = orc.cut_trial_starts(200, 50)
     assert np.array_equal(s2, [0, 50, 100, 150])
+
+
+def test_fit_fixed_omega_pipeline():
+    """The whole fit() pipeline restated with the oracle (host set-up from vlgp_b200.preprocess/util, which mirror the
+    reference's RNG use) against the reference's fit(Hstep=False) golden: pins initialise + cut_trials + vem + infer."""
+    from vlgp_b200 import preprocess
+    from vlgp_b200.synth import make_trials
+    from vlgp_b200.util import cut_trials
+
+    g = load_golden("fit_fixed_omega")
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    config = preprocess.get_config(max_iter=3, min_iter=3, Hstep=False)
+    params = preprocess.get_params(trials, 3, omega_bound=config["omega_bound"])
+    np.random.seed(0)
+    preprocess.initialize(trials, params, config)
+    preprocess.fill_params(params)
+    preprocess.fill_trials(trials)
+    params["cholesky"] = orc.make_cholesky([200], params["omega"], params["sigma"], 50)
+    orc.update_w(trials, params)
+    orc.update_v(trials, params, config)
+    segs = list(cut_trials(trials, params, config))
+    preprocess.fill_trials(segs)
+    params["cholesky"] = orc.make_cholesky([50], params["omega"], params["sigma"], 50)
+    orc.vem(segs, params, config)
+    params["cholesky"] = orc.make_cholesky([200], params["omega"], params["sigma"], 50)
+    orc.update_w(trials, params)
+    orc.update_v(trials, params, config)
+    orc.estep(trials, params, config, n_iter=config["max_iter"])
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([t[k] for t in trials]), g[k]) < 1e-9, k
+    for k in ("a", "b", "noise"):
+        assert relerr(params[k], g[k]) < 1e-9, k
