@@ -110,6 +110,11 @@ VLGP_API int vlgp_hstep_prepare(vlgp_ctx *ctx, int set_id);
 VLGP_API int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyper[3], double *ll, double *dll,
                          int *info);
 
+/* n evaluations (latents[e], hypers[3e..3e+2]) in one pass over the segments: one set of launches, one allreduce and
+ * one synchronisation for the whole batch (the host runs the per-latent L-BFGS-B optimisers in lockstep). n <= 16. */
+VLGP_API int vlgp_hstep_objective_batch(vlgp_ctx *ctx, int set_id, int n, const int32_t *latents, const double *hypers,
+                               double *ll, double *dll, int32_t *info);
+
 /* ---- constraints and convergence bookkeeping (vlgp/core.py:300-305,350-354,366-416) ------------------------------ */
 /* mu <- (mu - shift) @ M for every bin; shift (L) and M (L x L, row-major) may be NULL (0 / identity). */
 VLGP_API int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M);

@@ -51,6 +51,8 @@ EXPORTS = {
                              c_int_p]),
     "vlgp_hstep_prepare": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_hstep_objective": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
+    "vlgp_hstep_objective_batch": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i32_p, c_double_p, c_double_p, c_double_p,
+                                             c_i32_p]),
     "vlgp_latent_affine": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p]),
     "vlgp_norms": (C.c_int, [ctx_p, C.c_int, c_double_p]),
     "vlgp_latent_moments": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_i64_p]),

@@ -17,8 +17,7 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
 int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
                       double da_bound, double db_bound);
 int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts);
-int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, int l, double sigmasq, double omega, double eps,
-                                double out5[5], int *info);
+int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, double *ll, double *dll, int *info);
 void vlgp_comm_destroy(vlgp_ctx *ctx);
 
 static std::string g_create_error;
@@ -716,26 +715,35 @@ int vlgp_hstep_prepare(vlgp_ctx *ctx, int set_id) {
     return vlgp_launch_hstep_prepare(ctx, ts);
 }
 
-int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyper[3], double *ll, double *dll,
-                         int *info) {
+int vlgp_hstep_objective_batch(vlgp_ctx *ctx, int set_id, int n, const int32_t *latents, const double *hypers,
+                               double *ll, double *dll, int32_t *info) {
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts && ts->h_prepared, "hstep_objective: call hstep_prepare first");
-    REQUIRE(latent >= 0 && latent < ctx->L && hyper && ll && dll && info, "hstep_objective: bad arguments");
-    CK(cudaSetDevice(ctx->device));
-    double o[5];
-    int rc = vlgp_launch_hstep_objective(ctx, ts, latent, hyper[0], hyper[1], hyper[2], o, info);
-    if (rc) return rc;
-    // number of segments over all ranks
-    double nseg = (double)ts->n_trials;
-    if (ctx->n_ranks > 1) {
-        double tmp = nseg;
-        rc = vlgp_comm_allreduce(ctx, &tmp, 1, 0);
-        if (rc) return rc;
-        nseg = tmp;
+    REQUIRE(n >= 1 && n <= VLGP_MAX_L && latents && hypers && ll && dll && info, "hstep_objective: bad arguments");
+    HEvalBatch eb{};
+    eb.n = n;
+    for (int e = 0; e < n; ++e) {
+        REQUIRE(latents[e] >= 0 && latents[e] < ctx->L, "hstep_objective: latent %d out of range", latents[e]);
+        eb.latent[e] = latents[e];
+        eb.sigmasq[e] = hypers[3 * e];
+        eb.omega[e] = hypers[3 * e + 1];
+        eb.eps[e] = hypers[3 * e + 2];
     }
-    *ll = -0.5 * o[0] - 0.5 * o[3] - nseg * o[1];
-    *dll = 0.5 * (o[2] - o[4]);
+    CK(cudaSetDevice(ctx->device));
+    int inf[VLGP_MAX_L];
+    int rc = vlgp_launch_hstep_objective(ctx, ts, eb, ll, dll, inf);
+    if (rc) return rc;
+    for (int e = 0; e < n; ++e) info[e] = inf[e];
     return VLGP_OK;
+}
+
+int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyper[3], double *ll, double *dll,
+                         int *info) {
+    REQUIRE(hyper && ll && dll && info, "hstep_objective: bad arguments");
+    int32_t l = latent, inf = 0;
+    int rc = vlgp_hstep_objective_batch(ctx, set_id, 1, &l, hyper, ll, dll, &inf);
+    *info = inf;
+    return rc;
 }
 
 // ---- constraints / bookkeeping ---------------------------------------------------------------------------------------

@@ -49,8 +49,17 @@ struct TrialSet {
     double *d_M = nullptr;             // L x W x W second moments of mu
     double *d_K = nullptr;             // 2 x W x W: K and dK/dlog(omega) of the current evaluation
     double *d_hpart = nullptr;         // per-segment partials (2 x n_trials)
-    double *d_hout = nullptr;          // 8 doubles
+    double *d_hout = nullptr;          // MAX_L x 8 per-evaluation outputs + MAX_L x 2 reducible sums
     bool h_prepared = false;
+    double h_nseg_total = 0.0;         // segments over all ranks
+    int h_seg_grid = 1;
+};
+
+// A batch of H-step objective evaluations (one per latent when the host optimisers run in lockstep), by value.
+struct HEvalBatch {
+    int n;
+    int latent[VLGP_MAX_L];
+    double sigmasq[VLGP_MAX_L], omega[VLGP_MAX_L], eps[VLGP_MAX_L];
 };
 
 struct NcclApi;   // dlopen'ed subset of NCCL (comm.cu)

@@ -13,6 +13,7 @@
 //   * only the nc leading non-zero columns of each latent's prior factor are kept (compact copy in shared memory,
 //     loaded once per CTA): nc = 6..29 for the reference's omega bounds at W = 50.
 #include "common.cuh"
+#include "linalg.cuh"
 
 namespace {
 
@@ -58,16 +59,17 @@ struct Smem {
         w = d; d += W * LT;
         ra = d; d += W * LT;
         dmu = d; d += W * LT;
-        part = d; d += p.tpb * W * LT;
-        vec = d; d += NWARP * 4 * 64;             // per warp: colk / pv / cv / uv
+        part = d;                                 // rate passes: tpb x W x LT partial sums ...
+        vec = d;                                  // ... aliased with the per-warp vectors of the latent phases
+        d += max(p.tpb * W * LT, NWARP * 4 * 64);
         pois = (uint8_t *)d;
         ys = pois + ((N + 15) / 16) * 16;
     }
 };
 
 __host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8) {
-    size_t d = (size_t)2 * LT * N + 2 * N + g_total + m_total + (size_t)5 * W * LT + (size_t)tpb * W * LT +
-               NWARP * 4 * 64;
+    const size_t un = (size_t)tpb * W * LT > (size_t)NWARP * 4 * 64 ? (size_t)tpb * W * LT : (size_t)NWARP * 4 * 64;
+    size_t d = (size_t)2 * LT * N + 2 * N + g_total + m_total + (size_t)5 * W * LT + un;
     size_t bytes = d * sizeof(double) + ((N + 15) / 16) * 16;
     if (y_u8) bytes += ((size_t)W * N + 15) / 16 * 16;
     return bytes;
@@ -88,6 +90,7 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
             acc[l] = 0.0;
         }
         const int n0 = k * p.chunk, n1 = min(N, n0 + p.chunk);
+#pragma unroll 2
         for (int n = n0; n < n1; ++n) {
             double al[LT], eta = s.b[n], h = 0.0;
 #pragma unroll
@@ -131,48 +134,48 @@ template <int LT>
 __device__ __forceinline__ bool warp_build_minv(const double *Gl, int ldg, int nc, int W, const double *wl, double *M,
                                                 int ldm, double *colk) {
     const int lane = threadIdx.x & 31;
-    // Gram matrix: lane computes its columns j, four rows i at a time
-    for (int j = lane; j < nc; j += 32) {
-        for (int i0 = 0; i0 < nc; i0 += 4) {
-            double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            const int i1 = min(i0 + 1, nc - 1), i2 = min(i0 + 2, nc - 1), i3 = min(i0 + 3, nc - 1);
-            for (int t = 0; t < W; ++t) {
-                const double *g = Gl + t * ldg;
-                const double gw = g[j] * wl[t * LT];
-                c0 = fma(g[i0], gw, c0);
-                c1 = fma(g[i1], gw, c1);
-                c2 = fma(g[i2], gw, c2);
-                c3 = fma(g[i3], gw, c3);
-            }
-            M[i0 * ldm + j] = c0 + (i0 == j ? 1.0 : 0.0);
-            if (i0 + 1 < nc) M[(i0 + 1) * ldm + j] = c1 + (i0 + 1 == j ? 1.0 : 0.0);
-            if (i0 + 2 < nc) M[(i0 + 2) * ldm + j] = c2 + (i0 + 2 == j ? 1.0 : 0.0);
-            if (i0 + 3 < nc) M[(i0 + 3) * ldm + j] = c3 + (i0 + 3 == j ? 1.0 : 0.0);
+    // Gram matrix: the nc (nc + 1) / 2 lower-triangle entries are spread over the 32 lanes, two per lane per pass
+    const int npair = nc * (nc + 1) / 2;
+    for (int e0 = lane; e0 < npair; e0 += 64) {
+        const bool has1 = e0 + 32 < npair;
+        int i0, j0, i1, j1;
+        tri_decode(e0, i0, j0);
+        tri_decode(has1 ? e0 + 32 : e0, i1, j1);
+        double c0 = 0.0, c1 = 0.0;
+        for (int t = 0; t < W; ++t) {
+            const double *g = Gl + t * ldg;
+            const double wt = wl[t * LT];
+            c0 = fma(g[i0] * wt, g[j0], c0);
+            c1 = fma(g[i1] * wt, g[j1], c1);
+        }
+        c0 += (i0 == j0) ? 1.0 : 0.0;
+        M[i0 * ldm + j0] = c0;
+        M[j0 * ldm + i0] = c0;
+        if (has1) {
+            c1 += (i1 == j1) ? 1.0 : 0.0;
+            M[i1 * ldm + j1] = c1;
+            M[j1 * ldm + i1] = c1;
         }
     }
     __syncwarp();
-    // symmetrise exactly (G'WG computed column-wise is symmetric only up to rounding): copy the upper triangle down
-    for (int j = lane; j < nc; j += 32)
-        for (int i = j + 1; i < nc; ++i) M[i * ldm + j] = M[j * ldm + i];
-    __syncwarp();
-    // symmetric sweep, one pivot per step
+    // symmetric sweep, one pivot per step; the nc x nc entries are spread over the lanes
+    const float inv_nc = 1.0f / (float)nc;
+    const int nn = nc * nc;
     for (int k = 0; k < nc; ++k) {
         for (int i = lane; i < nc; i += 32) colk[i] = M[i * ldm + k];
         __syncwarp();
         const double d = colk[k];
         if (!(d > 0.0)) return false;
         const double pinv = 1.0 / d;
-        for (int j = lane; j < nc; j += 32) {
-            const double cj = colk[j];
-            const double cjp = cj * pinv;
-            for (int i = 0; i < nc; ++i) {
-                const double ci = colk[i];
-                double val;
-                if (i == k) val = (j == k) ? -pinv : cjp;
-                else if (j == k) val = ci * pinv;
-                else val = fma(-ci, cjp, M[i * ldm + j]);
-                M[i * ldm + j] = val;
-            }
+        for (int e = lane; e < nn; e += 32) {
+            const int i = (int)(((float)e + 0.5f) * inv_nc);      // exact floor(e / nc) for e < 4096, nc <= 64
+            const int j = e - i * nc;
+            const double ci = colk[i], cj = colk[j];
+            double val;
+            if (i == k) val = (j == k) ? -pinv : cj * pinv;
+            else if (j == k) val = ci * pinv;
+            else val = fma(-ci * pinv, cj, M[i * ldm + j]);
+            M[i * ldm + j] = val;
         }
         __syncwarp();
     }

@@ -1,4 +1,5 @@
-// K7: H-step objective -- ELBO of one latent's GP hyperparameters and its derivative w.r.t. log(omega).
+// K7: H-step objective -- ELBO of a latent's GP hyperparameters and its derivative w.r.t. log(omega), batched over
+// the evaluations the host optimiser asks for at the same time (one per latent when the L-BFGS-B runs are in lockstep).
 //
 // Replaces gp.construct_posterior_cov (vlgp/gp.py:126-147), gp.elbo (:12-43) and gp.kernel (:46-62) for the closure
 // that scipy's L-BFGS-B evaluates (vlgp/gp.py:107-111).  The reference materialises S_i = (K^-1 + diag(w_i))^-1 for
@@ -8,13 +9,13 @@
 //     K^-1 S_i K^-1 - K^-1      = -diag(d) B_i^-1 diag(d)
 // so    ll  = -1/2 tr(K^-1 M) - 1/2 sum_i tr(B_i^-1) - S sum(log diag chol K),        M = sum_i mu_i mu_i'
 //       dll =  1/2 [ (K^-1 M K^-1) : dK  -  sum_i (diag(d) B_i^-1 diag(d)) : dK ],    dK = -omega D^2 o (K - eps I)
-// (checked against the reference to 1e-12, tests/test_reformulation.py).  M is built once per H-step; each evaluation
-// costs one W x W inverse per segment, done by an in-SMEM symmetric sweep.
+// (checked against the reference to 1e-12 with a NumPy prototype and by tests/test_gpu_parity.py on the golden
+// vectors).  M is built once per H-step; each evaluation costs one W x W inverse per segment: hstep_dmma.cu does it on
+// the FP64 tensor path with one warp per segment, the CTA-wide register sweep below is the fallback for W > 56.
 #include "common.cuh"
 #include "linalg.cuh"
 
-int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double *dKd,
-                                    bool *handled);   // hstep_dmma.cu
+int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, bool *handled);   // hstep_dmma.cu
 
 namespace {
 
@@ -67,18 +68,21 @@ __global__ void reduce_parts_kernel2(const double *__restrict__ part, int G, int
     out[k] = s;
 }
 
-// ---- per evaluation, one CTA: K, dK, K^-1 terms -------------------------------------------------------------------
-// out[0] = tr(K^-1 M), out[1] = sum log diag chol(K), out[2] = (K^-1 M K^-1):dK ; info[2] = 1 if K is not PD.
-__global__ void __launch_bounds__(NT) hstep_global_kernel(int W, double dt, double sigmasq, double omega, double eps,
-                                                          const double *__restrict__ M, double *__restrict__ Kout,
-                                                          double *__restrict__ dKout, double *__restrict__ out,
-                                                          int *__restrict__ flags) {
+// ---- per evaluation, one CTA (blockIdx.x = evaluation): K, dK, K^-1 terms -------------------------------------------
+// out[e][0] = tr(K^-1 M), [1] = sum log diag chol(K), [2] = (K^-1 M K^-1):dK, [5] = 1 if K is not PD.
+__global__ void __launch_bounds__(NT) hstep_global_kernel(HEvalBatch eb, int W, double dt, const double *__restrict__ Mall,
+                                                          double *__restrict__ Kall, double *__restrict__ outall) {
     extern __shared__ double sm[];
+    const int e = blockIdx.x;
+    const double sigmasq = eb.sigmasq[e], omega = eb.omega[e], eps = eb.eps[e];
+    const double *M = Mall + (size_t)eb.latent[e] * W * W;
+    double *Kout = Kall + (size_t)e * 2 * W * W, *dKout = Kout + (size_t)W * W;
+    double *out = outall + e * 8;
     const int ld = W | 1;
     double *Aw = sm;                   // W x ld : K -> -K^-1
     double *Tm = Aw + W * ld;          // W x ld : K^-1 M
-    double *ck = Tm + W * ld;          // 64
-    double *red = ck + 128;            // 32   (ck: 2 x 64)
+    double *ck = Tm + W * ld;          // 2 x 64
+    double *red = ck + 128;            // 32
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     for (int i = ty; i < W; i += 16)
         for (int j = tx; j < W; j += 16) {
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(NT) hstep_global_kernel(int W, double dt, doub
     const bool ok = block_sweep_spd(Aw, ld, W, ck, &logdet);
     if (!ok) {
         if (tid == 0) {
-            flags[2] = 1;
             out[0] = out[1] = out[2] = 0.0;
+            out[5] = 1.0;
         }
         return;
     }
@@ -124,18 +128,21 @@ __global__ void __launch_bounds__(NT) hstep_global_kernel(int W, double dt, doub
         out[0] = t1;
         out[1] = 0.5 * logdet;
         out[2] = gr;
+        out[5] = 0.0;
     }
 }
 
-// ---- per evaluation, one CTA per segment: B_i^-1 by sweep ---------------------------------------------------------
-__global__ void __launch_bounds__(NT, 2) hstep_segment_kernel(int nseg, int W, int L, int l, const double *__restrict__ w,
-                                                           const double *__restrict__ K, const double *__restrict__ dK,
-                                                           double *__restrict__ part, int *__restrict__ flags) {
-    // The W x W matrix lives in registers (16 x 16 thread grid, 4 x 4 cyclic elements per thread, see linalg.cuh);
-    // K is read once per CTA into registers in the same layout and reused for every segment of the CTA.
+// ---- fallback (W > 56): one CTA per segment, B_i^-1 by the CTA-wide register sweep; blockIdx.y = evaluation --------
+__global__ void __launch_bounds__(NT, 2) hstep_segment_kernel(HEvalBatch eb, int nseg, int W, int L,
+                                                              const double *__restrict__ w,
+                                                              const double *__restrict__ Kall,
+                                                              double *__restrict__ partall) {
     __shared__ double dv[64];          // sqrt(w)
     __shared__ double ck[128];
     __shared__ double red[32];
+    const int e = blockIdx.y, l = eb.latent[e];
+    const double *K = Kall + (size_t)e * 2 * W * W, *dK = K + (size_t)W * W;
+    double *part = partall + (size_t)e * 2 * nseg;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     double kreg[4][4];
 #pragma unroll
@@ -174,22 +181,22 @@ __global__ void __launch_bounds__(NT, 2) hstep_segment_kernel(int nseg, int W, i
                     if (i == j) tr += binv;
                     if (i < W && j < W) pd = fma(binv * di[p] * dj[q], __ldg(dK + i * W + j), pd);
                 }
-        } else if (tid == 0) {
-            atomicAdd(flags + 3, 1);
         }
         tr = block_sum(tr, red);
         pd = block_sum(pd, red);
         if (tid == 0) {
-            part[seg] = tr;
-            part[nseg + seg] = pd;
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            part[seg] = ok ? tr : nan;
+            part[nseg + seg] = ok ? pd : nan;
         }
     }
 }
 
-// out[3] = sum_i tr(B_i^-1), out[4] = sum_i (d B_i^-1 d):dK   (deterministic, one CTA)
-__global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double *__restrict__ part,
-                                                         double *__restrict__ out) {
+// red[e][0] = sum_i tr(B_i^-1), red[e][1] = sum_i (d B_i^-1 d):dK   (deterministic, one CTA per evaluation)
+__global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double *__restrict__ partall,
+                                                         double *__restrict__ redall) {
     __shared__ double red[32];
+    const double *part = partall + (size_t)blockIdx.x * 2 * nseg;
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < nseg; i += NT) {
         a += part[i];
@@ -198,8 +205,8 @@ __global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double 
     a = block_sum(a, red);
     b = block_sum(b, red);
     if (threadIdx.x == 0) {
-        out[3] = a;
-        out[4] = b;
+        redall[blockIdx.x * 2] = a;
+        redall[blockIdx.x * 2 + 1] = b;
     }
 }
 
@@ -215,63 +222,70 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     double *part = nullptr;
     CK(cudaMalloc(&part, (size_t)chunks * L * WW * sizeof(double)));
     if (!ts->d_M) CK(cudaMalloc(&ts->d_M, (size_t)L * WW * sizeof(double)));
-    if (!ts->d_K) CK(cudaMalloc(&ts->d_K, (size_t)2 * WW * sizeof(double)));
-    if (!ts->d_hpart) CK(cudaMalloc(&ts->d_hpart, (size_t)2 * S * sizeof(double)));
-    if (!ts->d_hout) CK(cudaMalloc(&ts->d_hout, 8 * sizeof(double)));
+    if (!ts->d_K) CK(cudaMalloc(&ts->d_K, (size_t)VLGP_MAX_L * 2 * WW * sizeof(double)));
+    if (!ts->d_hpart) CK(cudaMalloc(&ts->d_hpart, (size_t)VLGP_MAX_L * 2 * S * sizeof(double)));
+    if (!ts->d_hout) CK(cudaMalloc(&ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double)));
     hstep_moment_kernel<<<dim3(chunks, L), NT, 0, ctx->stream>>>(S, W, L, ts->d_mu, part);
     CKL();
     reduce_parts_kernel2<<<(L * WW + 127) / 128, 128, 0, ctx->stream>>>(part, chunks, L * WW, ts->d_M);
     CKL();
     int rc = vlgp_allreduce_dev(ctx, ts->d_M, (size_t)L * WW, 0);
     if (rc) return rc;
+    // number of segments over all ranks (the S of the log-determinant term)
+    ctx->h_pin[0] = (double)S;
+    if (ctx->n_ranks > 1) {
+        CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rc = vlgp_allreduce_dev(ctx, ctx->d_small, 1, 0);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_small, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    ts->h_nseg_total = ctx->h_pin[0];
     CK(cudaFree(part));
+    // launch geometry of the per-segment fallback kernel (the DMMA kernel sizes its own grid)
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, 0));
+    ts->h_seg_grid = (per_sm < 1 ? 1 : per_sm) * ctx->prop.multiProcessorCount;
+    if (ts->h_seg_grid > S) ts->h_seg_grid = S;
+    const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
+    if (smem_g > 48 * 1024)
+        CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
     ts->h_prepared = true;
     return VLGP_OK;
 }
 
-// Returns the five partial results in out5 (host): tr(K^-1 M), sum log diag chol K, (K^-1 M K^-1):dK,
-// sum_i tr(B_i^-1), sum_i (d B_i^-1 d):dK -- the last two summed over ranks.
-int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, int l, double sigmasq, double omega, double eps,
-                                double out5[5], int *info) {
-    const int W = ts->max_len, L = ctx->L, S = ts->n_trials;
-    const int ld = W | 1;
-    const size_t smem_g = ((size_t)2 * W * ld + 160) * sizeof(double);
-    const size_t smem_s = 0;
-    if (smem_g > 48 * 1024)
-        CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-    if (smem_s > 48 * 1024)
-        CK(cudaFuncSetAttribute(hstep_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    CK(cudaMemsetAsync(ctx->d_flags + 2, 0, 2 * sizeof(int), ctx->stream));
-    double *Kd = ts->d_K, *dKd = ts->d_K + (size_t)W * W;
-    hstep_global_kernel<<<1, NT, smem_g, ctx->stream>>>(W, ctx->dt, sigmasq, omega, eps, ts->d_M + (size_t)l * W * W,
-                                                        Kd, dKd, ts->d_hout, ctx->d_flags);
+// Evaluates eb.n (latent, hyper) pairs in one pass: 3 launches, one allreduce, one D2H copy, one synchronisation.
+int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, double *ll, double *dll, int *info) {
+    const int W = ts->max_len, S = ts->n_trials, n = eb.n;
+    const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
+    double *red = ts->d_hout + VLGP_MAX_L * 8;
+    hstep_global_kernel<<<n, NT, smem_g, ctx->stream>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout);
     CKL();
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, smem_s));
-    if (per_sm < 1) per_sm = 1;
-    int grid = per_sm * ctx->prop.multiProcessorCount;
-    if (grid > S) grid = S;
     {
         ProfScope ps(ctx, 2);
         bool handled = false;
-        int rcd = vlgp_launch_hstep_segments_dmma(ctx, ts, l, Kd, dKd, &handled);
+        int rcd = vlgp_launch_hstep_segments_dmma(ctx, ts, eb, &handled);
         if (rcd) return rcd;
         if (!handled) {
-            hstep_segment_kernel<<<grid, NT, smem_s, ctx->stream>>>(S, W, L, l, ts->d_w, Kd, dKd, ts->d_hpart,
-                                                                    ctx->d_flags);
+            hstep_segment_kernel<<<dim3(ts->h_seg_grid, n), NT, 0, ctx->stream>>>(eb, S, W, ctx->L, ts->d_w, ts->d_K,
+                                                                                 ts->d_hpart);
             CKL();
         }
     }
-    hstep_final_kernel<<<1, NT, 0, ctx->stream>>>(S, ts->d_hpart, ts->d_hout);
+    hstep_final_kernel<<<n, NT, 0, ctx->stream>>>(S, ts->d_hpart, red);
     CKL();
-    int rc = vlgp_allreduce_dev(ctx, ts->d_hout + 3, 2, 0);
+    int rc = vlgp_allreduce_dev(ctx, red, 2 * n, 0);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_pin, ts->d_hout, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < 5; ++i) out5[i] = ctx->h_pin[i];
-    *info = ctx->h_flags[2] != 0 ? 1 : (ctx->h_flags[3] != 0 ? 2 : 0);
-    ctx->counters[2] += S;
+    const double *o = ctx->h_pin, *r = ctx->h_pin + VLGP_MAX_L * 8;
+    for (int e = 0; e < n; ++e) {
+        const double *oe = o + e * 8;
+        ll[e] = -0.5 * oe[0] - 0.5 * r[2 * e] - ts->h_nseg_total * oe[1];
+        dll[e] = 0.5 * (oe[2] - r[2 * e + 1]);
+        info[e] = oe[5] != 0.0 ? 1 : ((r[2 * e] != r[2 * e]) ? 2 : 0);      // 1: K not PD; 2: some B_i not PD (NaN)
+    }
+    ctx->counters[2] += (int64_t)S * n;
     return VLGP_OK;
 }

@@ -74,12 +74,13 @@ __device__ __forceinline__ bool tile_spd_inverse(Tile &t, int lane) {
 __host__ __device__ constexpr int tix(int i, int j) { return i * (i + 1) / 2 + j; }
 
 template <int NB>
-__global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(int nseg, int W, int L, int l,
+__global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBatch eb, int nseg, int W, int L,
                                                                         const double *__restrict__ w,
-                                                                        const double *__restrict__ K,
-                                                                        const double *__restrict__ dK,
-                                                                        double *__restrict__ part,
-                                                                        int *__restrict__ flags) {
+                                                                        const double *__restrict__ Kall,
+                                                                        double *__restrict__ partall) {
+    const int ev = blockIdx.y, l = eb.latent[ev];          // blockIdx.y = evaluation of the batch
+    const double *K = Kall + (size_t)ev * 2 * W * W, *dK = K + (size_t)W * W;
+    double *part = partall + (size_t)ev * 2 * nseg;
     constexpr int NT = NB * (NB + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *Ks = (double2 *)smem_raw;                 // NT x 32 : K in tile / lane order
@@ -205,11 +206,7 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(int nseg
             pd += __shfl_xor_sync(FULL, pd, o);
         }
         if (lane == 0) {
-            if (!ok) {
-                atomicAdd(flags + 3, 1);
-                tr = 0.0;
-                pd = 0.0;
-            }
+            if (!ok) tr = pd = __longlong_as_double(0x7ff8000000000000LL);     // NaN marks a non-PD B_i for the host
             part[seg] = tr;
             part[nseg + seg] = pd;
         }
@@ -217,7 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(int nseg
 }
 
 template <int NB>
-int launch_t(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double *dKd) {
+int launch_t(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
     constexpr int NT = NB * (NB + 1) / 2;
     const size_t smem = (size_t)2 * NT * 32 * sizeof(double2) + WARPS * 64 * sizeof(double);
     if (smem > 48 * 1024)
@@ -228,8 +225,8 @@ int launch_t(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double 
     const int S = ts->n_trials;
     int grid = per_sm * ctx->prop.multiProcessorCount;
     if (grid > (S + WARPS - 1) / WARPS) grid = (S + WARPS - 1) / WARPS;
-    hstep_segment_dmma_kernel<NB><<<grid, WARPS * 32, smem, ctx->stream>>>(S, ts->max_len, ctx->L, l, ts->d_w, Kd, dKd,
-                                                                          ts->d_hpart, ctx->d_flags);
+    hstep_segment_dmma_kernel<NB><<<dim3(grid, eb.n), WARPS * 32, smem, ctx->stream>>>(eb, S, ts->max_len, ctx->L, ts->d_w,
+                                                                                      ts->d_K, ts->d_hpart);
     CKL();
     return VLGP_OK;
 }
@@ -237,20 +234,19 @@ int launch_t(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double 
 }   // namespace
 
 // Returns VLGP_OK and sets *handled when the window fits the register-resident tile layout (W <= 56).
-int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, int l, const double *Kd, const double *dKd,
-                                    bool *handled) {
+int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, bool *handled) {
     *handled = false;
     if (getenv("VLGP_FORCE_SWEEP_HSTEP")) return VLGP_OK;
     const int NB = (ts->max_len + 7) / 8;
     int rc = VLGP_OK;
     switch (NB) {
-        case 1: rc = launch_t<1>(ctx, ts, l, Kd, dKd); break;
-        case 2: rc = launch_t<2>(ctx, ts, l, Kd, dKd); break;
-        case 3: rc = launch_t<3>(ctx, ts, l, Kd, dKd); break;
-        case 4: rc = launch_t<4>(ctx, ts, l, Kd, dKd); break;
-        case 5: rc = launch_t<5>(ctx, ts, l, Kd, dKd); break;
-        case 6: rc = launch_t<6>(ctx, ts, l, Kd, dKd); break;
-        case 7: rc = launch_t<7>(ctx, ts, l, Kd, dKd); break;
+        case 1: rc = launch_t<1>(ctx, ts, eb); break;
+        case 2: rc = launch_t<2>(ctx, ts, eb); break;
+        case 3: rc = launch_t<3>(ctx, ts, eb); break;
+        case 4: rc = launch_t<4>(ctx, ts, eb); break;
+        case 5: rc = launch_t<5>(ctx, ts, eb); break;
+        case 6: rc = launch_t<6>(ctx, ts, eb); break;
+        case 7: rc = launch_t<7>(ctx, ts, eb); break;
         default: return VLGP_OK;          // W > 56: the CTA-wide sweep kernel in hstep.cu handles it
     }
     if (rc == VLGP_OK) *handled = true;

@@ -335,6 +335,18 @@ class TrialSet:
                                               C.byref(info)), "hstep_objective")
         return ll.value, dll.value, info.value
 
+    def hstep_objective_batch(self, latents, hypers):
+        """Evaluate several (latent, hyper) pairs in one device pass; returns (ll[n], dll[n], info[n])."""
+        lib, ctx = self._lib()
+        lat = np.ascontiguousarray(latents, dtype=np.int32)
+        h = as_f64(hypers, (lat.size, 3))
+        ll, dll = np.empty(lat.size), np.empty(lat.size)
+        info = np.empty(lat.size, dtype=np.int32)
+        self.eng._ck(lib.vlgp_hstep_objective_batch(ctx, self.id, int(lat.size), lat.ctypes.data_as(_lib.c_i32_p),
+                                                    dptr(h), dptr(ll), dptr(dll), info.ctypes.data_as(_lib.c_i32_p)),
+                     "hstep_objective_batch")
+        return ll, dll, info
+
     def latent_affine(self, shift=None, M=None):
         lib, ctx = self._lib()
         L = self.eng.L
