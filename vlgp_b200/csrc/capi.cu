@@ -140,7 +140,7 @@ void free_set(TrialSet &ts) {
     };
     F(ts.d_len); F(ts.d_start); F(ts.d_fidx); F(ts.d_Gptr); F(ts.d_ncolptr); F(ts.d_y);
     F(ts.d_mu); F(ts.d_v); F(ts.d_w); F(ts.d_dmu); F(ts.d_ra); F(ts.d_u); F(ts.d_minv);
-    F(ts.d_M); F(ts.d_K); F(ts.d_hpart); F(ts.d_hout);
+    F(ts.d_M); F(ts.d_K); F(ts.d_hpart); F(ts.d_hout); F(ts.d_mompart);
     for (auto &pf : ts.factors) {
         F(pf.d_G); F(pf.d_ncol); F(pf.d_piv);
     }

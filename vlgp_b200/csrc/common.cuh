@@ -53,6 +53,9 @@ struct TrialSet {
     bool h_prepared = false;
     double h_nseg_total = 0.0;         // segments over all ranks
     int h_seg_grid = 1;
+    bool h_geometry = false;
+    int dmma_grid = 0;                 // cached launch geometry of the DMMA segment kernel
+    double *d_mompart = nullptr;       // per-chunk partial second moments
 };
 
 // A batch of H-step objective evaluations (one per latent when the host optimisers run in lockstep), by value.

@@ -219,8 +219,8 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     const int maxc = 4 * ctx->prop.multiProcessorCount / (L > 0 ? L : 1) + 1;
     if (chunks > maxc) chunks = maxc;
     if (chunks < 1) chunks = 1;
-    double *part = nullptr;
-    CK(cudaMalloc(&part, (size_t)chunks * L * WW * sizeof(double)));
+    if (!ts->d_mompart) CK(cudaMalloc(&ts->d_mompart, (size_t)maxc * L * WW * sizeof(double)));
+    double *part = ts->d_mompart;
     if (!ts->d_M) CK(cudaMalloc(&ts->d_M, (size_t)L * WW * sizeof(double)));
     if (!ts->d_K) CK(cudaMalloc(&ts->d_K, (size_t)VLGP_MAX_L * 2 * WW * sizeof(double)));
     if (!ts->d_hpart) CK(cudaMalloc(&ts->d_hpart, (size_t)VLGP_MAX_L * 2 * S * sizeof(double)));
@@ -241,15 +241,17 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ts->h_nseg_total = ctx->h_pin[0];
-    CK(cudaFree(part));
-    // launch geometry of the per-segment fallback kernel (the DMMA kernel sizes its own grid)
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, 0));
-    ts->h_seg_grid = (per_sm < 1 ? 1 : per_sm) * ctx->prop.multiProcessorCount;
-    if (ts->h_seg_grid > S) ts->h_seg_grid = S;
-    const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
-    if (smem_g > 48 * 1024)
-        CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    if (!ts->h_geometry) {
+        // launch geometry of the per-segment fallback kernel (the DMMA kernel sizes its own grid), once per set
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, 0));
+        ts->h_seg_grid = (per_sm < 1 ? 1 : per_sm) * ctx->prop.multiProcessorCount;
+        if (ts->h_seg_grid > S) ts->h_seg_grid = S;
+        const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
+        if (smem_g > 48 * 1024)
+            CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        ts->h_geometry = true;
+    }
     ts->h_prepared = true;
     return VLGP_OK;
 }

@@ -217,14 +217,18 @@ template <int NB>
 int launch_t(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
     constexpr int NT = NB * (NB + 1) / 2;
     const size_t smem = (size_t)2 * NT * 32 * sizeof(double2) + WARPS * 64 * sizeof(double);
-    if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(hstep_segment_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_dmma_kernel<NB>, WARPS * 32, smem));
-    if (per_sm < 1) per_sm = 1;
     const int S = ts->n_trials;
-    int grid = per_sm * ctx->prop.multiProcessorCount;
-    if (grid > (S + WARPS - 1) / WARPS) grid = (S + WARPS - 1) / WARPS;
+    if (ts->dmma_grid == 0) {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(hstep_segment_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_dmma_kernel<NB>, WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        ts->dmma_grid = per_sm * ctx->prop.multiProcessorCount;
+        if (ts->dmma_grid > (S + WARPS - 1) / WARPS) ts->dmma_grid = (S + WARPS - 1) / WARPS;
+    }
+    const int grid = ts->dmma_grid;
     hstep_segment_dmma_kernel<NB><<<dim3(grid, eb.n), WARPS * 32, smem, ctx->stream>>>(eb, S, ts->max_len, ctx->L, ts->d_w,
                                                                                       ts->d_K, ts->d_hpart);
     CKL();
