@@ -83,6 +83,7 @@ struct vlgp_ctx {
     // M-step scratch
     double *d_mpart = nullptr;   // grid x nstat x N
     double *d_mstat = nullptr;   // nstat x N (+ tail)
+    double *d_ymom = nullptr;    // (L+1) x N : mu'y, sum y (constant during one M-step)
     int mpart_grid = 0;
     double *d_gshared = nullptr; // Gaussian-channel shared moments: L*L + 2L + 1
     int *d_flags = nullptr;      // device counters (failures etc.), 16 ints

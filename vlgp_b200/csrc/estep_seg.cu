@@ -48,8 +48,8 @@ struct Smem {
     __device__ Smem(unsigned char *base, const SegArgs &p) {
         double *d = (double *)base;
         const int N = p.N, W = p.W;
-        a = d; d += LT * N;
-        a2 = d; d += LT * N;
+        a = d; d += 2 * LT * N;                  // interleaved (a, a^2) pairs: one 128-bit load per (latent, neuron)
+        a2 = a;
         b = d; d += N;
         inv_noise = d; d += N;
         Gs = d; d += p.g_total;
@@ -90,18 +90,16 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
             acc[l] = 0.0;
         }
         const int n0 = k * p.chunk, n1 = min(N, n0 + p.chunk);
+        const double2 *aa = (const double2 *)s.a;
 #pragma unroll 2
         for (int n = n0; n < n1; ++n) {
             double al[LT], eta = s.b[n], h = 0.0;
 #pragma unroll
             for (int l = 0; l < LT; ++l) {
-                al[l] = s.a[l * N + n];
-                eta = fma(mu_t[l], al[l], eta);
-            }
-#pragma unroll
-            for (int l = 0; l < LT; ++l) {
-                al[l] = (STAGE == 1) ? al[l] : s.a2[l * N + n];
-                h = fma(v_t[l], s.a2[l * N + n], h);
+                const double2 p2 = aa[l * N + n];         // (a, a^2)
+                eta = fma(mu_t[l], p2.x, eta);
+                h = fma(v_t[l], p2.y, h);
+                al[l] = (STAGE == 1) ? p2.x : p2.y;
             }
             const bool pois = s.pois[n] != 0;
             double coef;
@@ -250,8 +248,8 @@ __global__ void __launch_bounds__(NT) estep_seg_kernel(SegArgs p) {
     // ---- once per CTA: parameters and the compact prior factors ------------------------------------------------------
     for (int i = tid; i < LT * N; i += NT) {
         const double x = p.a[i];
-        s.a[i] = x;
-        s.a2[i] = x * x;
+        s.a[2 * i] = x;
+        s.a[2 * i + 1] = x * x;
     }
     for (int n = tid; n < N; n += NT) {
         s.b[n] = p.b[n];

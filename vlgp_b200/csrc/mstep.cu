@@ -11,9 +11,12 @@
 
 namespace {
 
-__host__ __device__ constexpr int nstat_of(int L) { return L + L * (L + 1) / 2 + 4; }
-// per-neuron statistic slots: [0,L) grad_a (Gaussian: mu'y) ; [L, L+L(L+1)/2) packed lower Hessian ;
-// then gb (Gaussian: sum y), Hb, sum e, sum e^2 with e = y - eta.
+// Per-iteration statistic slots per neuron (Poisson): [0,L) sum_t s_l r (s = mu + v o a_n) ; [L, L+L(L+1)/2) packed lower
+// Hessian ; then sum_t r, sum e, sum e^2 (e = y - eta; only accumulated in the LAST iteration -- the reference keeps
+// the noise of the last iteration, vlgp/core.py:177,242).  The y-moments mu'y (L) and sum y do not depend on (a, b):
+// they are computed once per M-step (FIRST) into their own buffer instead of 25 times.
+__host__ __device__ constexpr int nstat_of(int L) { return L + L * (L + 1) / 2 + 3; }
+__host__ __device__ constexpr int nymom_of(int L) { return L + 1; }
 
 struct MstatArgs {
     int64_t nbin;
@@ -23,86 +26,130 @@ struct MstatArgs {
     const double *mu, *v, *a, *b;
     const uint8_t *poisson;
     double *part;                // gridDim.x x nstat x N
+    double *ypart;               // gridDim.x x (L+1) x N   (FIRST only)
+    int last;                    // accumulate the noise moments
 };
 
-template <int LT>
+constexpr int MS_U = 4;          // bins per thread per tile: MS_U independent exp chains in flight
+constexpr int MS_TB_MAX = 128;   // bins per SMEM tile (= MS_U * J <= 128)
+
+template <int LT, bool FIRST>
 __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(MstatArgs p) {
     constexpr int NS = nstat_of(LT);
-    extern __shared__ double red[];             // 2 x blockDim
+    extern __shared__ double sm[];
+    double *muv = sm;                              // MS_TB_MAX x 2 LT : (mu, v) of the tile's bins
+    double *red = sm + MS_TB_MAX * 2 * LT;          // 2 x blockDim
     const int tid = threadIdx.x;
-    const int j = tid / p.NC;                   // bin lane
-    const int n = blockIdx.y * p.NC + (tid - j * p.NC);
+    const int j = tid / p.NC;                      // bin lane
+    const int nloc = tid - j * p.NC;
+    const int n = blockIdx.y * p.NC + nloc;
     const bool active = j < p.J && n < p.N;
     const int64_t per = (p.nbin + gridDim.x - 1) / gridDim.x;
     const int64_t b0 = (int64_t)blockIdx.x * per;
     const int64_t b1 = b0 + per < p.nbin ? b0 + per : p.nbin;
+    const int TB = MS_U * p.J;
 
-    double acc[NS];
+    double acc[NS], yacc[FIRST ? LT + 1 : 1];
 #pragma unroll
     for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < (FIRST ? LT + 1 : 1); ++s) yacc[s] = 0.0;
 
+    double al[LT], a2[LT];
+    double bn = 0.0;
+    bool pois = false;
     if (active) {
-        double al[LT], a2[LT];
 #pragma unroll
         for (int l = 0; l < LT; ++l) {
             al[l] = p.a[l * p.N + n];
             a2[l] = al[l] * al[l];
         }
-        const double bn = p.b[n];
-        const bool pois = p.poisson[n] != 0;
-        for (int64_t bin = b0 + j; bin < b1; bin += p.J) {
-            double m[LT], vv[LT];
-            double eta = bn, h = 0.0;
+        bn = p.b[n];
+        pois = p.poisson[n] != 0;
+    }
+    for (int64_t t0 = b0; t0 < b1; t0 += TB) {
+        const int nb = (int)((b1 - t0 < TB) ? (b1 - t0) : TB);
+        __syncthreads();
+        for (int i = tid; i < nb * LT; i += blockDim.x) {          // coalesced: the tile's mu and v are contiguous
+            const int t = i / LT, l = i - t * LT;
+            muv[t * 2 * LT + l] = p.mu[t0 * LT + i];
+            muv[t * 2 * LT + LT + l] = p.v[t0 * LT + i];
+        }
+        __syncthreads();
+        if (!active) continue;
+        // phase A: MS_U independent rate evaluations
+        double r[MS_U], yv[MS_U], eta[MS_U];
 #pragma unroll
-            for (int l = 0; l < LT; ++l) {
-                m[l] = p.mu[bin * LT + l];
-                vv[l] = p.v[bin * LT + l];
-                eta = fma(m[l], al[l], eta);
-                h = fma(vv[l], a2[l], h);
+        for (int u = 0; u < MS_U; ++u) {
+            const int t = j + u * p.J;
+            r[u] = 0.0;
+            yv[u] = 0.0;
+            eta[u] = 0.0;
+            if (t < nb) {
+                const double *mv = muv + t * 2 * LT;
+                double e = bn, h = 0.0;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    e = fma(mv[l], al[l], e);
+                    h = fma(mv[LT + l], a2[l], h);
+                }
+                eta[u] = e;
+                yv[u] = load_y(p.y, p.ydtype, (t0 + t) * p.N + n);
+                if (pois) r[u] = trunc_exp(e + 0.5 * h);
             }
-            const double yv = load_y(p.y, p.ydtype, bin * p.N + n);
-            const double e = yv - eta;
-            acc[NS - 2] += e;
-            acc[NS - 1] = fma(e, e, acc[NS - 1]);
+        }
+        // phase B: accumulate
+#pragma unroll
+        for (int u = 0; u < MS_U; ++u) {
+            const int t = j + u * p.J;
+            if (t >= nb) continue;
+            const double *mv = muv + t * 2 * LT;
+            if (FIRST) {
+#pragma unroll
+                for (int l = 0; l < LT; ++l) yacc[l] = fma(mv[l], yv[u], yacc[l]);
+                yacc[LT] += yv[u];
+            }
+            if (p.last) {
+                const double e = yv[u] - eta[u];
+                acc[NS - 2] += e;
+                acc[NS - 1] = fma(e, e, acc[NS - 1]);
+            }
             if (pois) {
-                const double r = trunc_exp(eta + 0.5 * h);
-                acc[NS - 4] += yv - r;
-                acc[NS - 3] += r;
+                const double rr = r[u];
+                acc[NS - 3] += rr;
                 double s[LT];
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
-                    s[l] = fma(vv[l], al[l], m[l]);
-                    acc[l] += m[l] * yv - s[l] * r;
+                    s[l] = fma(mv[LT + l], al[l], mv[l]);
+                    acc[l] = fma(s[l], rr, acc[l]);
                 }
                 int q = LT;
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
-                    const double rs = r * s[l];
+                    const double rs = rr * s[l];
 #pragma unroll
                     for (int k = 0; k <= l; ++k) {
                         acc[q] = fma(rs, s[k], acc[q]);
                         ++q;
                     }
-                    acc[q - 1] = fma(r, vv[l], acc[q - 1]);     // + diag(r' v)   (vlgp/core.py:189)
+                    acc[q - 1] = fma(rr, mv[LT + l], acc[q - 1]);     // + diag(r' v)   (vlgp/core.py:189)
                 }
-            } else {
-                acc[NS - 4] += yv;
-#pragma unroll
-                for (int l = 0; l < LT; ++l) acc[l] = fma(m[l], yv, acc[l]);
             }
         }
     }
     // reduce over the J bin lanes of this CTA, one statistic at a time (double-buffered: one barrier per statistic)
-    const int nc_local = tid - j * p.NC;
+    __syncthreads();
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NS + (FIRST ? LT + 1 : 0); ++s) {
         double *buf = red + (s & 1) * blockDim.x;
-        buf[tid] = active ? acc[s] : 0.0;
+        const double val = s < NS ? acc[s < NS ? s : 0] : yacc[FIRST ? (s >= NS ? s - NS : 0) : 0];
+        buf[tid] = active ? val : 0.0;
         __syncthreads();
         if (j == 0 && n < p.N) {
-            double r = 0.0;
-            for (int jj = 0; jj < p.J; ++jj) r += buf[jj * p.NC + nc_local];
-            p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = r;
+            double x = 0.0;
+            for (int jj = 0; jj < p.J; ++jj) x += buf[jj * p.NC + nloc];
+            if (s < NS) p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = x;
+            else p.ypart[((size_t)blockIdx.x * (LT + 1) + (s - NS)) * p.N + n] = x;
         }
     }
 }
@@ -163,10 +210,11 @@ struct MsolveArgs {
     int N;
     double count;                // total number of bins (all ranks)
     const double *stat;          // nstat x N
+    const double *ymom;          // (L+1) x N : mu'y per latent, sum y
     const double *gshared;       // L*L + 2L (Gaussian channels) or null
     const uint8_t *poisson;
     double *a, *b, *noise, *da, *db;
-    int use_hessian;
+    int use_hessian, last;
     double eps, lr, da_bound, db_bound;
     int *flags;                  // flags[1] += gradient fallbacks
 };
@@ -215,12 +263,15 @@ __global__ void mstep_solve_kernel(MsolveArgs p) {
     if (n >= p.N) return;
     const int N = p.N;
     auto S = [&](int s) { return p.stat[(size_t)s * N + n]; };
-    const double me = S(NS - 2) / p.count;
-    p.noise[n] = S(NS - 1) / p.count - me * me;       // np.var(y - eta, ddof=0), vlgp/core.py:177
+    auto Y = [&](int s) { return p.ymom[(size_t)s * N + n]; };
+    if (p.last) {
+        const double me = S(NS - 2) / p.count;
+        p.noise[n] = S(NS - 1) / p.count - me * me;   // np.var(y - eta, ddof=0), vlgp/core.py:177
+    }
     if (p.poisson[n]) {
         double g[LT], H[LT][LT];
 #pragma unroll
-        for (int l = 0; l < LT; ++l) g[l] = S(l);
+        for (int l = 0; l < LT; ++l) g[l] = Y(l) - S(l);      // mu'y - (mu + v o a)' r
         double step[LT];
         bool newton = p.use_hessian != 0;
         if (newton) {
@@ -253,7 +304,7 @@ __global__ void mstep_solve_kernel(MsolveArgs p) {
             p.da[l * N + n] = d;
             p.a[l * N + n] += d;
         }
-        const double gb = S(NS - 4);
+        const double gb = Y(LT) - S(NS - 3);                   // sum (y - r)
         double sb;
         const double hb = S(NS - 3) + p.eps;
         if (p.use_hessian && hb > 0.0) sb = gb / hb;
@@ -274,7 +325,7 @@ __global__ void mstep_solve_kernel(MsolveArgs p) {
             for (int k = 0; k < LT; ++k) H[l][k] = p.gshared[l * LT + k];
             H[l][l] += p.gshared[LT * LT + l];
             smu[l] = p.gshared[LT * LT + LT + l];
-            rhs[l] = S(l) - smu[l] * bn;
+            rhs[l] = Y(l) - smu[l] * bn;
         }
         if (chol_solve_small<LT>(H, rhs)) {
             double dot = 0.0;
@@ -283,7 +334,7 @@ __global__ void mstep_solve_kernel(MsolveArgs p) {
                 p.a[l * N + n] = rhs[l];
                 dot = fma(smu[l], rhs[l], dot);
             }
-            p.b[n] = (S(NS - 4) - dot) / p.count;
+            p.b[n] = (Y(LT) - dot) / p.count;
         } else {
             atomicAdd(p.flags + 1, 1);
         }
@@ -298,26 +349,26 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
     const int N = ctx->N;
     const int NC = N < MAXT ? N : MAXT;
     const int nchunk = (N + NC - 1) / NC;
-    const int J = MAXT / NC;
+    const int J = (MAXT / NC) < (MS_TB_MAX / MS_U) ? (MAXT / NC) : (MS_TB_MAX / MS_U);
     int nt = ((J * NC + 31) / 32) * 32;
-    const size_t smem = 2 * (size_t)nt * sizeof(double);
+    const size_t smem = ((size_t)MS_TB_MAX * 2 * LT + 2 * (size_t)nt) * sizeof(double);
     int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mstep_stats_kernel<LT>, nt, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mstep_stats_kernel<LT, false>, nt, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t gx = (int64_t)per_sm * ctx->prop.multiProcessorCount / nchunk;
-    const int64_t min_bins = 4 * (int64_t)J;       // at least a few bins per bin lane
+    const int64_t min_bins = (int64_t)MS_U * J;    // at least one full tile per CTA
     if (gx > (ts->nbin + min_bins - 1) / min_bins) gx = (ts->nbin + min_bins - 1) / min_bins;
     if (gx < 1) gx = 1;
     const int K = NS * N;
-    if (ctx->mpart_grid < gx * (NS * N + 1)) {
+    const int KY = (LT + 1) * N;
+    if (ctx->mpart_grid < gx * (K + KY + 1)) {
         if (ctx->d_mpart) CK(cudaFree(ctx->d_mpart));
         ctx->d_mpart = nullptr;
-        CK(cudaMalloc(&ctx->d_mpart, (size_t)gx * (K + 64) * sizeof(double)));
-        ctx->mpart_grid = (int)(gx * (NS * N + 1));
+        CK(cudaMalloc(&ctx->d_mpart, (size_t)gx * (K + KY + 64) * sizeof(double)));
+        ctx->mpart_grid = (int)(gx * (K + KY + 1));
     }
-    if (ctx->d_mstat) CK(cudaFree(ctx->d_mstat));
-    ctx->d_mstat = nullptr;
-    CK(cudaMalloc(&ctx->d_mstat, (size_t)(K + 1) * sizeof(double)));
+    if (!ctx->d_ymom) CK(cudaMalloc(&ctx->d_ymom, (size_t)(VLGP_MAX_L + 1) * N * sizeof(double)));
+    double *ypart = ctx->d_mpart + (size_t)gx * K;
 
     // total bin count over all ranks (the divisor of np.var / the Gaussian bias)
     double count = (double)ts->nbin;
@@ -354,21 +405,33 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
     sa.y = ts->d_y; sa.ydtype = ts->ydtype;
     sa.mu = ts->d_mu; sa.v = ts->d_v; sa.a = ctx->d_a; sa.b = ctx->d_b; sa.poisson = ctx->d_poisson;
     sa.part = ctx->d_mpart;
+    sa.ypart = ypart;
     MsolveArgs so{};
-    so.N = N; so.count = count; so.stat = ctx->d_mstat; so.gshared = gshared; so.poisson = ctx->d_poisson;
+    so.N = N; so.count = count; so.stat = ctx->d_mstat; so.ymom = ctx->d_ymom; so.gshared = gshared; so.poisson = ctx->d_poisson;
     so.a = ctx->d_a; so.b = ctx->d_b; so.noise = ctx->d_noise; so.da = ctx->d_da; so.db = ctx->d_db;
     so.use_hessian = use_hessian; so.eps = eps; so.lr = lr; so.da_bound = da_bound; so.db_bound = db_bound;
     so.flags = ctx->d_flags;
 
     for (int it = 0; it < n_iter; ++it) {
+        sa.last = so.last = (it == n_iter - 1);
         {
             ProfScope ps(ctx, 1);
-            mstep_stats_kernel<LT><<<dim3((unsigned)gx, nchunk), nt, smem, ctx->stream>>>(sa);
+            if (it == 0)
+                mstep_stats_kernel<LT, true><<<dim3((unsigned)gx, nchunk), nt, smem, ctx->stream>>>(sa);
+            else
+                mstep_stats_kernel<LT, false><<<dim3((unsigned)gx, nchunk), nt, smem, ctx->stream>>>(sa);
             CKL();
+        }
+        int rc;
+        if (it == 0) {      // y-moments mu'y, sum y: once per M-step
+            reduce_parts_kernel<<<(KY + 127) / 128, 128, 0, ctx->stream>>>(ypart, (int)gx, KY, ctx->d_ymom);
+            CKL();
+            rc = vlgp_allreduce_dev(ctx, ctx->d_ymom, KY, 0);
+            if (rc) return rc;
         }
         reduce_parts_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_mpart, (int)gx, K, ctx->d_mstat);
         CKL();
-        int rc = vlgp_allreduce_dev(ctx, ctx->d_mstat, K, 0);
+        rc = vlgp_allreduce_dev(ctx, ctx->d_mstat, K, 0);
         if (rc) return rc;
         mstep_solve_kernel<LT><<<(N + 63) / 64, 64, 0, ctx->stream>>>(so);
         CKL();
