@@ -200,7 +200,7 @@ int vlgp_destroy(vlgp_ctx *ctx) {
         p = nullptr;
     };
     F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db);
-    F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_ymom); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_small); F(ctx->d_flush);
+    F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_ymom); F(ctx->d_ppack); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_small); F(ctx->d_flush);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int i = 0; i < 2; ++i) {
@@ -269,7 +269,7 @@ int vlgp_set_model(vlgp_ctx *ctx, int N, int L, int rank, const uint8_t *poisson
         p = nullptr;
     };
     F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db); F(ctx->d_mstat);
-    F(ctx->d_mpart); F(ctx->d_ymom);
+    F(ctx->d_mpart); F(ctx->d_ymom); F(ctx->d_ppack);
     ctx->mpart_grid = 0;
     ctx->N = N; ctx->L = L; ctx->rank = rank; ctx->gp_noise = gp_noise; ctx->dt = dt;
     CK(cudaMalloc(&ctx->d_poisson, N));

@@ -27,16 +27,22 @@ struct SegArgs {
     int goff[VLGP_MAX_L];         // offsets (doubles) of the compact factor / Minv of latent l inside their regions
     int moff[VLGP_MAX_L];
     int g_total, m_total;         // region sizes (doubles)
+    int pairoff[VLGP_MAX_L + 1];  // prefix sums of nc (nc + 1) / 2 : (latent, Gram entry) items
+    int coloff[VLGP_MAX_L + 1];   // prefix sums of nc : (latent, column) items
+    int pair_total, col_total;
     const void *y;
     int ydtype;
     double *mu, *v, *w, *dmu;
     const double *a, *b, *noise;
     const uint8_t *poisson;
+    const double2 *pa;            // L x N (a, a^2) pairs and N (b, 1/noise) pairs, packed by pack_params_kernel
+    const double2 *pb;
     int n_iter;
     double dmu_bound;
     int method_vb;
     int *flags;
     int tpb, chunk;               // threads per bin and neurons per thread in the rate passes
+    int skip;                     // debug/timing only (VLGP_DEBUG_SKIP): 1 rate passes, 2 mean step, 4 factor, 8 variance
 };
 
 __device__ __forceinline__ int ldodd(int n) { return n | 1; }
@@ -50,8 +56,8 @@ struct Smem {
         const int N = p.N, W = p.W;
         a = d; d += 2 * LT * N;                  // interleaved (a, a^2) pairs: one 128-bit load per (latent, neuron)
         a2 = a;
-        b = d; d += N;
-        inv_noise = d; d += N;
+        b = d; d += 2 * N;                       // interleaved (bias, 1 / noise) pairs
+        inv_noise = b;
         Gs = d; d += p.g_total;
         Mi = d; d += p.m_total;
         mu = d; d += W * LT;
@@ -60,15 +66,15 @@ struct Smem {
         ra = d; d += W * LT;
         dmu = d; d += W * LT;
         part = d;                                 // rate passes: tpb x W x LT partial sums ...
-        vec = d;                                  // ... aliased with the per-warp vectors of the latent phases
-        d += max(p.tpb * W * LT, NWARP * 4 * 64);
+        vec = d;                                  // ... aliased with the per-latent vectors (3 x 64) of the r x r phases
+        d += max(p.tpb * W * LT, LT * 192);
         pois = (uint8_t *)d;
         ys = pois + ((N + 15) / 16) * 16;
     }
 };
 
 __host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8) {
-    const size_t un = (size_t)tpb * W * LT > (size_t)NWARP * 4 * 64 ? (size_t)tpb * W * LT : (size_t)NWARP * 4 * 64;
+    const size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
     size_t d = (size_t)2 * LT * N + 2 * N + g_total + m_total + (size_t)5 * W * LT + un;
     size_t bytes = d * sizeof(double) + ((N + 15) / 16) * 16;
     if (y_u8) bytes += ((size_t)W * N + 15) / 16 * 16;
@@ -89,14 +95,17 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
             v_t[l] = s.v[t * LT + l];
             acc[l] = 0.0;
         }
-        const int n0 = k * p.chunk, n1 = min(N, n0 + p.chunk);
         const double2 *aa = (const double2 *)s.a;
+        const double2 *bb = (const double2 *)s.b;
+        // neurons are interleaved over the tpb threads of a bin (n = k, k + tpb, ...): at every step the threads of a
+        // warp touch tpb CONSECUTIVE neurons, so the (a, a^2), bias and count loads are bank-conflict-free broadcasts
 #pragma unroll 2
-        for (int n = n0; n < n1; ++n) {
-            double al[LT], eta = s.b[n], h = 0.0;
+        for (int n = k; n < N; n += p.tpb) {
+            const double2 bn = bb[n];                       // (bias, 1 / noise)
+            double al[LT], eta = bn.x, h = 0.0;
 #pragma unroll
             for (int l = 0; l < LT; ++l) {
-                const double2 p2 = aa[l * N + n];         // (a, a^2)
+                const double2 p2 = aa[l * N + n];          // (a, a^2)
                 eta = fma(mu_t[l], p2.x, eta);
                 h = fma(v_t[l], p2.y, h);
                 al[l] = (STAGE == 1) ? p2.x : p2.y;
@@ -106,9 +115,9 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
             if (STAGE == 1) {
                 const double yv = p.ydtype == VLGP_Y_U8 ? (double)s.ys[t * N + n]
                                                        : ((const double *)p.y)[(bin0 + t) * N + n];
-                coef = pois ? yv - trunc_exp(eta + 0.5 * h) : (yv - eta) * s.inv_noise[n];
+                coef = pois ? yv - trunc_exp(eta + 0.5 * h) : (yv - eta) * bn.y;
             } else {
-                coef = pois ? trunc_exp(eta + 0.5 * h) : s.inv_noise[n];
+                coef = pois ? trunc_exp(eta + 0.5 * h) : bn.y;
             }
 #pragma unroll
             for (int l = 0; l < LT; ++l) acc[l] = fma(coef, al[l], acc[l]);
@@ -126,37 +135,44 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
     __syncthreads();
 }
 
-// ---- warp-level routines of one latent (lane owns columns lane, lane+32 and bins lane, lane+32) ---------------------
-// M (ld odd) <- -(I + G' diag(w_l) G)^-1.  Returns false (warp-uniform) if not positive definite.
+// ---- per-latent r x r work.  Gram, variance and the mean-step mat-vecs are flattened over ALL threads of the CTA as
+// (latent, entry) items so no warp idles; only the short symmetric sweep runs one warp per latent. --------------------
+
+// idx -> (latent, lower-triangle entry (i, j)) of the per-latent Gram matrices; pairoff[l] = first item of latent l
+__device__ __forceinline__ void decode_pair(const SegArgs &p, int LT, int idx, int &l, int &i, int &j) {
+    l = 0;
+    while (l + 1 < LT && idx >= p.pairoff[l + 1]) ++l;
+    tri_decode(idx - p.pairoff[l], i, j);
+}
+
+// M_l <- I + G_l' diag(w_l) G_l for every latent (both triangles written)
 template <int LT>
-__device__ __forceinline__ bool warp_build_minv(const double *Gl, int ldg, int nc, int W, const double *wl, double *M,
-                                                int ldm, double *colk) {
-    const int lane = threadIdx.x & 31;
-    // Gram matrix: the nc (nc + 1) / 2 lower-triangle entries are spread over the 32 lanes, two per lane per pass
-    const int npair = nc * (nc + 1) / 2;
-    for (int e0 = lane; e0 < npair; e0 += 64) {
-        const bool has1 = e0 + 32 < npair;
-        int i0, j0, i1, j1;
-        tri_decode(e0, i0, j0);
-        tri_decode(has1 ? e0 + 32 : e0, i1, j1);
+__device__ __forceinline__ void gram_all(const SegArgs &p, const Smem<LT> &s) {
+    const int W = p.W;
+    for (int idx = threadIdx.x; idx < p.pair_total; idx += NT) {
+        int l, i, j;
+        decode_pair(p, LT, idx, l, i, j);
+        const int ldg = ldodd(p.nc[l]);
+        const double *g = s.Gs + p.goff[l];
+        const double *wl = s.w + l;
         double c0 = 0.0, c1 = 0.0;
-        for (int t = 0; t < W; ++t) {
-            const double *g = Gl + t * ldg;
-            const double wt = wl[t * LT];
-            c0 = fma(g[i0] * wt, g[j0], c0);
-            c1 = fma(g[i1] * wt, g[j1], c1);
+        int t = 0;
+        for (; t + 1 < W; t += 2) {
+            c0 = fma(g[t * ldg + i] * wl[t * LT], g[t * ldg + j], c0);
+            c1 = fma(g[(t + 1) * ldg + i] * wl[(t + 1) * LT], g[(t + 1) * ldg + j], c1);
         }
-        c0 += (i0 == j0) ? 1.0 : 0.0;
-        M[i0 * ldm + j0] = c0;
-        M[j0 * ldm + i0] = c0;
-        if (has1) {
-            c1 += (i1 == j1) ? 1.0 : 0.0;
-            M[i1 * ldm + j1] = c1;
-            M[j1 * ldm + i1] = c1;
-        }
+        if (t < W) c0 = fma(g[t * ldg + i] * wl[t * LT], g[t * ldg + j], c0);
+        const double c = c0 + c1 + ((i == j) ? 1.0 : 0.0);
+        double *M = s.Mi + p.moff[l];
+        M[i * ldg + j] = c;
+        M[j * ldg + i] = c;
     }
-    __syncwarp();
-    // symmetric sweep, one pivot per step; the nc x nc entries are spread over the lanes
+}
+
+// In-place symmetric sweep of one latent's matrix by one warp: M <- -M^-1.  Returns false (warp-uniform) if a pivot is
+// not positive (the matrix is not positive definite).
+__device__ __forceinline__ bool warp_sweep(double *M, int ldm, int nc, double *colk) {
+    const int lane = threadIdx.x & 31;
     const float inv_nc = 1.0f / (float)nc;
     const int nn = nc * nc;
     for (int k = 0; k < nc; ++k) {
@@ -164,7 +180,7 @@ __device__ __forceinline__ bool warp_build_minv(const double *Gl, int ldg, int n
         __syncwarp();
         const double d = colk[k];
         if (!(d > 0.0)) return false;
-        const double pinv = 1.0 / d;
+        const double pinv = fast_rcp(d);
         for (int e = lane; e < nn; e += 32) {
             const int i = (int)(((float)e + 0.5f) * inv_nc);      // exact floor(e / nc) for e < 4096, nc <= 64
             const int j = e - i * nc;
@@ -180,61 +196,112 @@ __device__ __forceinline__ bool warp_build_minv(const double *Gl, int ldg, int n
     return true;
 }
 
+// Gram + sweep for every latent: on return M_l = -(I + G_l' W_l G_l)^-1 and bad[l] says whether that failed.
 template <int LT>
-__device__ __forceinline__ void warp_variance(const double *Gl, int ldg, int nc, int W, const double *M, int ldm,
-                                              double *vl) {
-    const int lane = threadIdx.x & 31;
-    for (int t = lane; t < W; t += 32) {
-        const double *g = Gl + t * ldg;
-        double s = 0.0;
+__device__ __forceinline__ void factor_all(const SegArgs &p, const Smem<LT> &s, int *bad) {
+    gram_all<LT>(p, s);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int l = wid; l < LT; l += NWARP) {
+        const bool ok = warp_sweep(s.Mi + p.moff[l], ldodd(p.nc[l]), p.nc[l], s.vec + (size_t)l * 192);
+        if (lane == 0) {
+            bad[l] = ok ? 0 : 1;
+            if (!ok) atomicAdd(p.flags, 1);
+        }
+    }
+    __syncthreads();
+}
+
+// v_t = G_t Minv G_t' for every (latent, bin)   (M holds -Minv)
+template <int LT>
+__device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s, const int *bad) {
+    const int W = p.W;
+    const float inv_w = 1.0f / (float)W;
+    for (int idx = threadIdx.x; idx < LT * W; idx += NT) {
+        const int l = (int)(((float)idx + 0.5f) * inv_w);
+        const int t = idx - l * W;
+        if (bad[l]) continue;                                      // failed solve: v keeps its value (core.py:112)
+        const int nc = p.nc[l], ld = ldodd(nc);
+        const double *g = s.Gs + p.goff[l] + t * ld;
+        const double *M = s.Mi + p.moff[l];
+        double acc = 0.0;
         for (int i = 0; i < nc; ++i) {
             double inner = 0.0;
-            for (int j = 0; j < nc; ++j) inner = fma(M[i * ldm + j], g[j], inner);
-            s = fma(g[i], inner, s);
+            for (int j = 0; j < nc; ++j) inner = fma(M[i * ld + j], g[j], inner);
+            acc = fma(g[i], inner, acc);
         }
-        vl[t * LT] = -s;          // M holds -Minv
+        s.v[t * LT + l] = -acc;
     }
 }
 
-// Newton step of the posterior mean of one latent (vlgp/core.py:81-97); vec: 4 x 64 doubles of per-warp SMEM.
+// Newton step of the posterior mean of every latent (vlgp/core.py:81-97), Jacobi over latents.
+// vec: per latent 3 x 64 doubles (pv / cv / uv).
 template <int LT>
-__device__ __forceinline__ void warp_mean_step(const double *Gl, int ldg, int nc, int W, const double *M, int ldm,
-                                               const double *ral, const double *wl, double *mul, double *dmul,
-                                               double *vec, double bound) {
-    const int lane = threadIdx.x & 31;
-    double *pv = vec + 64, *cv = vec + 128, *uv = vec + 192;
-    for (int j = lane; j < nc; j += 32) {                       // p = G' (resid a_l)
-        double s = 0.0;
-        for (int t = 0; t < W; ++t) s = fma(Gl[t * ldg + j], ral[t * LT], s);
-        pv[j] = s;
+__device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &s, const int *bad) {
+    const int W = p.W, tid = threadIdx.x;
+    const float inv_w = 1.0f / (float)W;
+    // p = G' (resid a_l)
+    for (int idx = tid; idx < p.col_total; idx += NT) {
+        int l = 0;
+        while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+        const int j = idx - p.coloff[l], ld = ldodd(p.nc[l]);
+        const double *g = s.Gs + p.goff[l];
+        double acc = 0.0;
+        for (int t = 0; t < W; ++t) acc = fma(g[t * ld + j], s.ra[t * LT + l], acc);
+        s.vec[l * 192 + j] = acc;
     }
-    __syncwarp();
-    for (int t = lane; t < W; t += 32) {                        // u = G p - mu_l
-        double s = 0.0;
-        for (int j = 0; j < nc; ++j) s = fma(Gl[t * ldg + j], pv[j], s);
-        uv[t] = s - mul[t * LT];
+    __syncthreads();
+    // u = G p - mu_l
+    for (int idx = tid; idx < LT * W; idx += NT) {
+        const int l = (int)(((float)idx + 0.5f) * inv_w), t = idx - l * W;
+        const int nc = p.nc[l], ld = ldodd(nc);
+        const double *g = s.Gs + p.goff[l] + t * ld;
+        const double *pv = s.vec + l * 192;
+        double acc = 0.0;
+        for (int j = 0; j < nc; ++j) acc = fma(g[j], pv[j], acc);
+        s.vec[l * 192 + 128 + t] = acc - s.mu[t * LT + l];
     }
-    __syncwarp();
-    for (int j = lane; j < nc; j += 32) {                       // c = G' (w_l o u)
-        double s = 0.0;
-        for (int t = 0; t < W; ++t) s = fma(Gl[t * ldg + j], wl[t * LT] * uv[t], s);
-        cv[j] = s;
+    __syncthreads();
+    // c = G' (w_l o u)
+    for (int idx = tid; idx < p.col_total; idx += NT) {
+        int l = 0;
+        while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+        const int j = idx - p.coloff[l], ld = ldodd(p.nc[l]);
+        const double *g = s.Gs + p.goff[l];
+        const double *uv = s.vec + l * 192 + 128;
+        double acc = 0.0;
+        for (int t = 0; t < W; ++t) acc = fma(g[t * ld + j], s.w[t * LT + l] * uv[t], acc);
+        s.vec[l * 192 + 64 + j] = acc;
     }
-    __syncwarp();
-    for (int i = lane; i < nc; i += 32) {                       // m = Minv c   (M = -Minv, symmetric)
-        double s = 0.0;
-        for (int j = 0; j < nc; ++j) s = fma(M[j * ldm + i], cv[j], s);
-        pv[i] = -s;
+    __syncthreads();
+    // m = Minv c   (M = -Minv, symmetric)
+    for (int idx = tid; idx < p.col_total; idx += NT) {
+        int l = 0;
+        while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+        const int i = idx - p.coloff[l], nc = p.nc[l], ld = ldodd(nc);
+        const double *M = s.Mi + p.moff[l];
+        const double *cv = s.vec + l * 192 + 64;
+        double acc = 0.0;
+        for (int j = 0; j < nc; ++j) acc = fma(M[j * ld + i], cv[j], acc);
+        s.vec[l * 192 + i] = -acc;
     }
-    __syncwarp();
-    for (int t = lane; t < W; t += 32) {                        // delta = clip(u - G m)
-        double s = 0.0;
-        for (int j = 0; j < nc; ++j) s = fma(Gl[t * ldg + j], pv[j], s);
-        const double d = clipd(uv[t] - s, bound);
-        dmul[t * LT] = d;
-        mul[t * LT] += d;
+    __syncthreads();
+    // delta = clip(u - G m); a failed factorisation zeroes the step (vlgp/core.py:92-94)
+    for (int idx = tid; idx < LT * W; idx += NT) {
+        const int l = (int)(((float)idx + 0.5f) * inv_w), t = idx - l * W;
+        double d = 0.0;
+        if (!bad[l]) {
+            const int nc = p.nc[l], ld = ldodd(nc);
+            const double *g = s.Gs + p.goff[l] + t * ld;
+            const double *mv = s.vec + l * 192;
+            double acc = 0.0;
+            for (int j = 0; j < nc; ++j) acc = fma(g[j], mv[j], acc);
+            d = clipd(s.vec[l * 192 + 128 + t] - acc, p.dmu_bound);
+        }
+        s.dmu[t * LT + l] = d;
+        s.mu[t * LT + l] += d;
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 template <int LT>
@@ -242,18 +309,13 @@ __global__ void __launch_bounds__(NT) estep_seg_kernel(SegArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<LT> s(smem_raw, p);
     __shared__ int bad[VLGP_MAX_L];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const int W = p.W, N = p.N;
 
     // ---- once per CTA: parameters and the compact prior factors ------------------------------------------------------
-    for (int i = tid; i < LT * N; i += NT) {
-        const double x = p.a[i];
-        s.a[2 * i] = x;
-        s.a[2 * i + 1] = x * x;
-    }
+    for (int i = tid; i < LT * N; i += NT) ((double2 *)s.a)[i] = p.pa[i];
     for (int n = tid; n < N; n += NT) {
-        s.b[n] = p.b[n];
-        s.inv_noise[n] = 1.0 / p.noise[n];
+        ((double2 *)s.b)[n] = p.pb[n];
         s.pois[n] = p.poisson[n];
     }
     for (int l = 0; l < LT; ++l) {
@@ -283,44 +345,15 @@ __global__ void __launch_bounds__(NT) estep_seg_kernel(SegArgs p) {
         __syncthreads();
 
         for (int it = 0; it < p.n_iter; ++it) {
-            rate_pass<LT, 1>(p, s, bin0);
-            for (int l = wid; l < LT; l += NWARP) {
-                const int nc = p.nc[l], ldg = ldodd(nc), ldm = ldodd(nc);
-                const double *Gl = s.Gs + p.goff[l];
-                double *M = s.Mi + p.moff[l];
-                double *vec = s.vec + wid * 256;
-                if (it == 0) {
-                    const bool ok = warp_build_minv<LT>(Gl, ldg, nc, W, s.w + l, M, ldm, vec);
-                    if (lane == 0) {
-                        bad[l] = ok ? 0 : 1;
-                        if (!ok) atomicAdd(p.flags, 1);
-                    }
-                    __syncwarp();
-                }
-                if (bad[l]) {
-                    for (int t = lane; t < W; t += 32) s.dmu[t * LT + l] = 0.0;
-                } else {
-                    warp_mean_step<LT>(Gl, ldg, nc, W, M, ldm, s.ra + l, s.w + l, s.mu + l, s.dmu + l, vec,
-                                       p.dmu_bound);
-                }
-            }
-            __syncthreads();
-            rate_pass<LT, 2>(p, s, bin0);
+            if (!(p.skip & 1)) rate_pass<LT, 1>(p, s, bin0);    // ends with a barrier; part (aliases vec) is free again
+            if (it == 0) factor_all<LT>(p, s, bad);             // the first mean step uses the incoming w
+            if (!(p.skip & 2)) mean_step_all<LT>(p, s, bad);
+            if (!(p.skip & 1)) rate_pass<LT, 2>(p, s, bin0);
             if (p.method_vb || it + 1 < p.n_iter) {
-                for (int l = wid; l < LT; l += NWARP) {
-                    const int nc = p.nc[l], ldg = ldodd(nc), ldm = ldodd(nc);
-                    const double *Gl = s.Gs + p.goff[l];
-                    double *M = s.Mi + p.moff[l];
-                    double *vec = s.vec + wid * 256;
-                    const bool ok = warp_build_minv<LT>(Gl, ldg, nc, W, s.w + l, M, ldm, vec);
-                    if (lane == 0) {
-                        bad[l] = ok ? 0 : 1;
-                        if (!ok) atomicAdd(p.flags, 1);
-                    }
-                    if (ok && p.method_vb) warp_variance<LT>(Gl, ldg, nc, W, M, ldm, s.v + l);
-                }
+                if (!(p.skip & 4)) factor_all<LT>(p, s, bad);
+                if (p.method_vb && !(p.skip & 8)) variance_all<LT>(p, s, bad);
+                __syncthreads();
             }
-            __syncthreads();
         }
         for (int i = tid; i < W * LT; i += NT) {
             p.mu[bin0 * LT + i] = s.mu[i];
@@ -332,8 +365,25 @@ __global__ void __launch_bounds__(NT) estep_seg_kernel(SegArgs p) {
     }
 }
 
+__global__ void pack_params_kernel(int LN, int N, const double *__restrict__ a, const double *__restrict__ b,
+                                   const double *__restrict__ noise, double2 *__restrict__ pa, double2 *__restrict__ pb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < LN) {
+        const double x = a[i];
+        pa[i] = make_double2(x, x * x);
+    }
+    if (i < N) pb[i] = make_double2(b[i], 1.0 / noise[i]);
+}
+
 template <int LT>
 int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *handled) {
+    const int LN = LT * p.N;
+    if (!ctx->d_ppack) CK(cudaMalloc(&ctx->d_ppack, (size_t)(VLGP_MAX_L + 1) * p.N * sizeof(double2)));
+    p.pa = (const double2 *)ctx->d_ppack;
+    p.pb = p.pa + LN;
+    pack_params_kernel<<<(LN + 255) / 256, 256, 0, ctx->stream>>>(LN, p.N, p.a, p.b, p.noise, (double2 *)p.pa,
+                                                                  (double2 *)p.pb);
+    CKL();
     CK(cudaFuncSetAttribute(estep_seg_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_seg_kernel<LT>, NT, smem));
@@ -373,20 +423,28 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     SegArgs p{};
     p.n_seg = ts->n_trials; p.W = W; p.N = N; p.rank = ctx->rank;
     p.G = ts->factors[0].d_G;
-    int goff = 0, moff = 0;
+    int goff = 0, moff = 0, po = 0, co = 0;
     for (int l = 0; l < L; ++l) {
         const int nc = ts->factors[0].h_ncol[l];
+        if (nc < 1) return VLGP_OK;          // degenerate factor: let the general kernel handle it
         p.nc[l] = nc;
         p.goff[l] = goff;
         p.moff[l] = moff;
+        p.pairoff[l] = po;
+        p.coloff[l] = co;
         goff += W * (nc | 1);
-        moff += (nc > 0 ? nc : 1) * (nc | 1);
+        moff += nc * (nc | 1);
+        po += nc * (nc + 1) / 2;
+        co += nc;
     }
+    p.pairoff[L] = po; p.coloff[L] = co;
+    p.pair_total = po; p.col_total = co;
     p.g_total = goff; p.m_total = moff;
     p.y = ts->d_y; p.ydtype = ts->ydtype;
     p.mu = ts->d_mu; p.v = ts->d_v; p.w = ts->d_w; p.dmu = ts->d_dmu;
     p.a = ctx->d_a; p.b = ctx->d_b; p.noise = ctx->d_noise; p.poisson = ctx->d_poisson;
     p.n_iter = n_iter; p.dmu_bound = dmu_bound; p.method_vb = method_vb; p.flags = ctx->d_flags;
+    p.skip = getenv("VLGP_DEBUG_SKIP") ? atoi(getenv("VLGP_DEBUG_SKIP")) : 0;
     p.tpb = NT / W;
     if (p.tpb < 1) return VLGP_OK;
     if (p.tpb > N) p.tpb = N;

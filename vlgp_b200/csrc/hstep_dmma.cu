@@ -54,7 +54,7 @@ __device__ __forceinline__ bool tile_spd_inverse(Tile &t, int lane) {
         const double pc0 = __shfl_sync(FULL, t.x, 4 * p + (lane & 3));         // a[p][c0]
         const double pc1 = __shfl_sync(FULL, t.y, 4 * p + (lane & 3));         // a[p][c0 + 1]
         ok = ok && (d > 0.0);
-        const double pinv = 1.0 / d;
+        const double pinv = fast_rcp(d);
         const double crp = cr * pinv;
         double nx = fma(-crp, pc0, t.x), ny = fma(-crp, pc1, t.y);
         if (r == p) {

@@ -29,7 +29,7 @@ __device__ __forceinline__ bool block_sweep_regs(double (&a)[4][4], int n, doubl
         const double d = buf[k];
         if (!(d > 0.0)) { ok = false; break; }      // uniform: every thread reads the same value
         if (logdet) lsum += log(d);
-        const double pinv = 1.0 / d;
+        const double pinv = fast_rcp(d);
         double ci[4], cj[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
