@@ -81,6 +81,12 @@ VLGP_API int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydt
 VLGP_API int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *const *parts, const int64_t *rows,
                             int src_dtype, int *stored_dtype);
 VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w);
+/* Per-trial-block variants (which: 0 mu, 1 v, 2 w, 3 dmu [get only]; parts[i]: rows[i] x L float64, C-contiguous):
+ * gather / scatter through the pinned double-buffered pipeline, so segment views are read and written in place. */
+VLGP_API int vlgp_trials_set_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, const double *const *parts,
+                                const int64_t *rows);
+VLGP_API int vlgp_trials_get_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, double *const *parts,
+                                const int64_t *rows);
 VLGP_API int vlgp_trials_get_state(vlgp_ctx *ctx, int set_id, double *mu, double *v, double *w, double *dmu);
 
 /* ---- prior factor: gp.make_cholesky (vlgp/gp.py:150-162) over math.ichol_gauss (vlgp/math.py:76-126) ------------- */

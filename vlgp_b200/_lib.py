@@ -38,8 +38,11 @@ EXPORTS = {
     "vlgp_trials_create": (C.c_int, [ctx_p, C.c_int, c_i32_p, c_int_p]),
     "vlgp_trials_free": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_trials_set_y": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_int]),
-    "vlgp_trials_set_y_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_i64_p, C.c_int, c_int_p]),
+    # the two pointer/row tables are passed as packed byte strings (uint64 / int64), see _fastpack.pointers
+    "vlgp_trials_set_y_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, c_int_p]),
     "vlgp_trials_set_state": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p]),
+    "vlgp_trials_set_state_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
+    "vlgp_trials_get_state_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "vlgp_trials_get_state": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "vlgp_make_cholesky": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_get_cholesky": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p, c_i32_p, c_i32_p]),

@@ -63,7 +63,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(log)
     if jobs or not os.path.exists(LIB):
         run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"])
+    build_fastpack(force)
     return LIB
+
+
+def build_fastpack(force: bool = False):
+    """Optional CPython helper (host pointer tables); skipped silently when Python.h or gcc is missing."""
+    import sysconfig
+
+    src = os.path.join(CSRC, "fastpack.c")
+    out = os.path.join(HERE, "_fastpack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+    inc = sysconfig.get_paths()["include"]
+    if not os.path.exists(os.path.join(inc, "Python.h")) or not shutil.which("gcc"):
+        return None
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        r = subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I" + inc, "-o", out, src], capture_output=True, text=True)
+        if r.returncode != 0:
+            return None
+    return out
 
 
 if __name__ == "__main__":

@@ -81,11 +81,10 @@ class Session:
             self.ts.set_y_parts([tr["y"] for tr in trials])
             L = eng.L
 
-            def cat(key):
-                parts = [tr[key] if tr.get(key) is not None else np.zeros((n, L)) for tr, n in zip(trials, lengths)]
-                return np.concatenate(parts, axis=0) if len(parts) > 1 else parts[0]
+            def blocks(key):
+                return [tr[key] if tr.get(key) is not None else np.zeros((n, L)) for tr, n in zip(trials, lengths)]
 
-            self.ts.set_state(cat("mu"), cat("v"), cat("w"))
+            self.ts.set_state_parts(mu=blocks("mu"), v=blocks("v"), w=blocks("w"))
             chol = params.get("cholesky") if upload_factors else None
             self.have_factors = False
             if chol:
@@ -111,17 +110,30 @@ class Session:
         self.have_factors = True
 
     def pull(self, trials, which=("mu", "v", "w", "dmu")):
-        st = self.ts.get_state(which)
-        for i, tr in enumerate(trials):
-            s0 = int(self.ts.starts[i])
-            s1 = s0 + int(self.ts.lengths[i])
-            for k in which:
-                val = st[k][s0:s1]
-                if k in ("mu", "v") and isinstance(tr.get(k), np.ndarray) and tr[k].shape == val.shape \
-                        and tr[k].dtype == np.float64:
-                    tr[k][...] = val            # in place: segment arrays are views of the parent trial
-                else:
-                    tr[k] = val.copy()
+        """Device state -> trial dicts with the reference's aliasing: mu and v are written IN PLACE (segment arrays are
+        views of their trial), w and dmu are rebound to fresh arrays (views of one new block per key)."""
+        L = self.eng.L
+        inplace, fresh = {}, {}
+        for k in which:
+            ok = k in ("mu", "v") and all(
+                isinstance(tr.get(k), np.ndarray) and tr[k].dtype == np.float64 and tr[k].flags.c_contiguous
+                and tr[k].flags.writeable and tr[k].shape == (int(n), L) for tr, n in zip(trials, self.ts.lengths))
+            if ok:
+                inplace[k] = [tr[k] for tr in trials]
+            else:
+                fresh[k] = np.empty((self.ts.nbin, L))
+        if inplace:
+            self.ts.get_state_parts(**inplace)
+        if fresh:
+            self.ts.get_state_parts(**{k: [a] for k, a in fresh.items()})
+            for i, tr in enumerate(trials):
+                s0 = int(self.ts.starts[i])
+                s1 = s0 + int(self.ts.lengths[i])
+                for k, a in fresh.items():
+                    if k in ("mu", "v") and isinstance(tr.get(k), np.ndarray) and tr[k].shape == (s1 - s0, L):
+                        tr[k][...] = a[s0:s1]
+                    else:
+                        tr[k] = a[s0:s1]
 
     def close(self):
         self.ts.free()

@@ -537,6 +537,130 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
     return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_set_y_parts: uint8 source could not be stored");
 }
 
+// Gather (to_device) or scatter (from device) a device array of nelem elements of esz bytes from/to host blocks whose
+// element offsets are part_off[0..n_parts], through the two pinned staging buffers, with host threads doing the
+// block copies while the previous chunk is in flight over PCIe.
+static int pipeline_copy(vlgp_ctx *ctx, void *dev, size_t esz, int n_parts, void *const *parts,
+                         const std::vector<int64_t> &part_off, bool to_device) {
+    const size_t STAGE = (size_t)8 << 20;
+    if (!ctx->h_stage[0]) {
+        CK(cudaMallocHost(&ctx->h_stage[0], STAGE));
+        CK(cudaMallocHost(&ctx->h_stage[1], STAGE));
+        CK(cudaEventCreateWithFlags(&ctx->stage_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->stage_ev[1], cudaEventDisableTiming));
+    }
+    const int64_t nelem = part_off[n_parts];
+    const int64_t chunk = (int64_t)(STAGE / esz);
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+    auto copy_chunk = [&](int buf, int64_t e0, int64_t e1) {
+        int ip = 0;
+        {   // binary search of the part containing e0
+            int lo = 0, hi = n_parts - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) / 2;
+                if (part_off[mid] <= e0) lo = mid; else hi = mid - 1;
+            }
+            ip = lo;
+        }
+        auto work = [&](int t) {
+            const int64_t per = (e1 - e0 + nthreads - 1) / nthreads;
+            int64_t a = e0 + t * per;
+            const int64_t b = std::min(e1, a + per);
+            if (a >= b) return;
+            int p = ip;
+            while (part_off[p + 1] <= a) ++p;
+            while (a < b) {
+                const int64_t stop = std::min(b, part_off[p + 1]);
+                unsigned char *st = (unsigned char *)ctx->h_stage[buf] + (size_t)(a - e0) * esz;
+                unsigned char *hp = (unsigned char *)parts[p] + (size_t)(a - part_off[p]) * esz;
+                if (to_device) memcpy(st, hp, (size_t)(stop - a) * esz);
+                else memcpy(hp, st, (size_t)(stop - a) * esz);
+                a = stop;
+                ++p;
+            }
+        };
+        if (e1 - e0 < (int64_t)(1 << 16)) {
+            for (int t = 0; t < nthreads; ++t) work(t);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+        }
+    };
+    if (to_device) {
+        int buf = 0;
+        for (int64_t e0 = 0; e0 < nelem; e0 += chunk, buf ^= 1) {
+            const int64_t e1 = std::min(nelem, e0 + chunk);
+            CK(cudaEventSynchronize(ctx->stage_ev[buf]));
+            copy_chunk(buf, e0, e1);
+            CK(cudaMemcpyAsync((unsigned char *)dev + (size_t)e0 * esz, ctx->h_stage[buf], (size_t)(e1 - e0) * esz,
+                               cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaEventRecord(ctx->stage_ev[buf], ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        // issue chunk k+1's D2H before scattering chunk k
+        int buf = 0;
+        int64_t e0 = 0;
+        if (nelem > 0) {
+            const int64_t e1 = std::min(nelem, chunk);
+            CK(cudaMemcpyAsync(ctx->h_stage[0], dev, (size_t)e1 * esz, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
+        }
+        while (e0 < nelem) {
+            const int64_t e1 = std::min(nelem, e0 + chunk);
+            if (e1 < nelem) {
+                const int64_t f1 = std::min(nelem, e1 + chunk);
+                CK(cudaMemcpyAsync(ctx->h_stage[buf ^ 1], (const unsigned char *)dev + (size_t)e1 * esz,
+                                   (size_t)(f1 - e1) * esz, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaEventRecord(ctx->stage_ev[buf ^ 1], ctx->stream));
+            }
+            CK(cudaEventSynchronize(ctx->stage_ev[buf]));
+            copy_chunk(buf, e0, e1);
+            e0 = e1;
+            buf ^= 1;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return VLGP_OK;
+}
+
+static double *state_array(TrialSet *ts, int which) {
+    switch (which) {
+        case 0: return ts->d_mu;
+        case 1: return ts->d_v;
+        case 2: return ts->d_w;
+        case 3: return ts->d_dmu;
+        default: return nullptr;
+    }
+}
+
+static int state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, void *const *parts, const int64_t *rows,
+                       bool to_device) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && parts && rows && n_parts >= 1, "trials_state_parts: bad arguments");
+    double *dev = state_array(ts, which);
+    REQUIRE(dev != nullptr && (which != 3 || !to_device), "trials_state_parts: bad array selector %d", which);
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int64_t> off(n_parts + 1, 0);
+    for (int i = 0; i < n_parts; ++i) off[i + 1] = off[i] + rows[i] * (int64_t)ctx->L;
+    REQUIRE(off[n_parts] == ts->nbin * (int64_t)ctx->L, "trials_state_parts: blocks hold %lld rows, the set has %lld bins",
+            (long long)(off[n_parts] / ctx->L), (long long)ts->nbin);
+    return pipeline_copy(ctx, dev, sizeof(double), n_parts, parts, off, to_device);
+}
+
+int vlgp_trials_set_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, const double *const *parts,
+                                const int64_t *rows) {
+    return state_parts(ctx, set_id, which, n_parts, (void *const *)parts, rows, true);
+}
+
+int vlgp_trials_get_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, double *const *parts,
+                                const int64_t *rows) {
+    return state_parts(ctx, set_id, which, n_parts, (void *const *)parts, rows, false);
+}
+
 int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w) {
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts, "trials_set_state: bad set %d", set_id);

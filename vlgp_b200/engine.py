@@ -13,6 +13,11 @@ import numpy as np
 from . import _lib
 from ._lib import VlgpNativeError, as_f64, dptr
 
+try:  # optional C helper for the pointer tables (host plumbing only); pure-Python fallback below
+    from . import _fastpack
+except ImportError:  # pragma: no cover
+    _fastpack = None
+
 __all__ = ["Engine", "TrialSet", "get_engine", "reset_engine", "pack_y"]
 
 _ENGINE = None
@@ -43,6 +48,35 @@ def pack_y(ys):
     if yf.size and yf.min() >= 0 and yf.max() <= 255 and np.array_equal(yf, np.rint(yf)):
         return yf.astype(np.uint8), 1
     return yf, 0
+
+
+def _pointer_table(arrs, dtype, ncols, writable=False):
+    """(arrays kept alive, packed uint64 pointers, packed int64 row counts) of a sequence of 2-D blocks.  Blocks that
+    are not C-contiguous arrays of ``dtype`` are converted (copied) first -- except when ``writable``."""
+    itemsize = np.dtype(dtype).itemsize
+    keep = list(arrs)
+    if _fastpack is not None and all(isinstance(a, np.ndarray) and a.dtype == dtype for a in keep):
+        try:
+            ptrs, rows = _fastpack.pointers(keep, itemsize, ncols, writable)
+            return keep, ptrs, rows
+        except (TypeError, ValueError, BufferError):
+            pass
+    fixed = []
+    for a in keep:
+        a = np.asarray(a)
+        if a.dtype != dtype or not a.flags.c_contiguous:
+            if writable:
+                raise ValueError("expected writable C-contiguous %s blocks" % np.dtype(dtype).name)
+            a = np.ascontiguousarray(a, dtype=dtype)
+        if a.ndim != 2 or a.shape[1] != ncols:
+            raise ValueError("expected blocks of shape (rows, %d), got %s" % (ncols, a.shape))
+        fixed.append(a)
+    if _fastpack is not None:
+        ptrs, rows = _fastpack.pointers(fixed, itemsize, ncols, writable)
+    else:
+        ptrs = np.array([a.ctypes.data for a in fixed], dtype=np.uint64).tobytes()
+        rows = np.array([a.shape[0] for a in fixed], dtype=np.int64).tobytes()
+    return fixed, ptrs, rows
 
 
 class Engine:
@@ -242,22 +276,42 @@ class TrialSet:
         N = self.eng.N
         if len(ys) != self.lengths.size:
             raise ValueError("expected %d observation blocks, got %d" % (self.lengths.size, len(ys)))
-        src_u8 = all(y.dtype == np.uint8 for y in ys)
+        src_u8 = all(isinstance(y, np.ndarray) and y.dtype == np.uint8 for y in ys)
         want = np.uint8 if src_u8 else np.float64
-        keep = []
-        for y, n in zip(ys, self.lengths):
-            if y.shape != (int(n), N):
-                raise ValueError("observation block must be (%d, %d), got %s" % (n, N, y.shape))
-            if y.dtype != want or not y.flags.c_contiguous:
-                y = np.ascontiguousarray(y, dtype=want)
-            keep.append(y)
-        ptrs = (C.c_void_p * len(keep))(*[y.__array_interface__["data"][0] for y in keep])
-        rows = np.ascontiguousarray(self.lengths, dtype=np.int64)
+        keep, ptrs, rows = _pointer_table(ys, want, N)
+        if not np.array_equal(np.frombuffer(rows, dtype=np.int64), self.lengths):
+            raise ValueError("observation blocks do not match the trial lengths")
         stored = C.c_int()
-        self.eng._ck(lib.vlgp_trials_set_y_parts(ctx, self.id, len(keep), ptrs, rows.ctypes.data_as(_lib.c_i64_p),
-                                                 1 if src_u8 else 0, C.byref(stored)), "trials_set_y_parts")
+        self.eng._ck(lib.vlgp_trials_set_y_parts(ctx, self.id, len(keep), ptrs, rows, 1 if src_u8 else 0,
+                                                 C.byref(stored)), "trials_set_y_parts")
         self.h2d_bytes += self.nbin * N * (1 if stored.value == 1 else 8)
         return stored.value
+
+    _WHICH = {"mu": 0, "v": 1, "w": 2, "dmu": 3}
+
+    def set_state_parts(self, **blocks):
+        """Upload mu / v / w given as one (rows_i, L) float64 block per trial, gathered natively (no host concat)."""
+        lib, ctx = self._lib()
+        for key, arrs in blocks.items():
+            if arrs is None:
+                continue
+            keep, ptrs, rows = _pointer_table(arrs, np.float64, self.eng.L)
+            self.eng._ck(lib.vlgp_trials_set_state_parts(ctx, self.id, self._WHICH[key], len(keep), ptrs, rows),
+                         "trials_set_state_parts")
+            self.h2d_bytes += self.nbin * self.eng.L * 8
+
+    def get_state_parts(self, **blocks):
+        """Download mu / v / w / dmu straight INTO the given per-trial float64 blocks (in place)."""
+        lib, ctx = self._lib()
+        for key, arrs in blocks.items():
+            if arrs is None:
+                continue
+            keep, ptrs, rows = _pointer_table(arrs, np.float64, self.eng.L, writable=True)
+            if any(k is not a for k, a in zip(keep, arrs)):
+                raise ValueError("get_state_parts needs writable C-contiguous float64 blocks")
+            self.eng._ck(lib.vlgp_trials_get_state_parts(ctx, self.id, self._WHICH[key], len(keep), ptrs, rows),
+                         "trials_get_state_parts")
+            self.d2h_bytes += self.nbin * self.eng.L * 8
 
     def set_state(self, mu=None, v=None, w=None):
         lib, ctx = self._lib()
