@@ -111,23 +111,18 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
         for (int t = lane; t < 64; t += 32)
             dw[t] = t < W ? sqrt(fmax(w[((size_t)seg * W + t) * L + l], 0.0)) : 0.0;
         __syncwarp();
-        double di[NB], dj0[NB], dj1[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            di[b] = dw[8 * b + r];
-            dj0[b] = dw[8 * b + c0];
-            dj1[b] = dw[8 * b + c0 + 1];
-        }
         // ---- B = I + d K d in tiles (identity on the padding) --------------------------------------------------
         Tile A[NT];
 #pragma unroll
-        for (int i = 0; i < NB; ++i)
+        for (int i = 0; i < NB; ++i) {
+            const double di = dw[8 * i + r];
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
                 const double2 kv = Ks[tix(i, j) * 32 + lane];
-                A[tix(i, j)].x = fma(di[i] * kv.x, dj0[j], (i == j && r == c0) ? 1.0 : 0.0);
-                A[tix(i, j)].y = fma(di[i] * kv.y, dj1[j], (i == j && r == c0 + 1) ? 1.0 : 0.0);
+                A[tix(i, j)].x = fma(di * kv.x, dw[8 * j + c0], (i == j && r == c0) ? 1.0 : 0.0);
+                A[tix(i, j)].y = fma(di * kv.y, dw[8 * j + c0 + 1], (i == j && r == c0 + 1) ? 1.0 : 0.0);
             }
+        }
         // ---- blocked symmetric sweep -> tiles hold -B^-1 ----------------------------------------------------------
         bool ok = true;
 #pragma unroll
@@ -186,20 +181,22 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
         // ---- tr(B^-1) and (d B^-1 d) : dK ---------------------------------------------------------------------------
         double tr = 0.0, pd = 0.0;
 #pragma unroll
-        for (int i = 0; i < NB; ++i)
+        for (int i = 0; i < NB; ++i) {
+            const double di = dw[8 * i + r];            // sqrt(w) is re-read from SMEM: not kept live through the sweep
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
                 const double2 dv = dKs[tix(i, j) * 32 + lane];
                 const double bx = -A[tix(i, j)].x, by = -A[tix(i, j)].y;
-                const double wgt = (i == j) ? 1.0 : 2.0;
-                pd = fma(wgt * bx * di[i] * dj0[j], dv.x, pd);
-                pd = fma(wgt * by * di[i] * dj1[j], dv.y, pd);
+                const double wgt = (i == j) ? di : 2.0 * di;
+                pd = fma(wgt * bx * dw[8 * j + c0], dv.x, pd);
+                pd = fma(wgt * by * dw[8 * j + c0 + 1], dv.y, pd);
                 if (i == j) {
                     const int gi = 8 * i + r;
                     if (r == c0 && gi < W) tr += bx;
                     if (r == c0 + 1 && gi < W) tr += by;
                 }
             }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             tr += __shfl_xor_sync(FULL, tr, o);
