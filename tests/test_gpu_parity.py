@@ -372,6 +372,64 @@ def test_overlapping_windows_and_unequal_lengths(vl):
         assert t["mu"].shape == (t["y"].shape[0], 2) and np.all(np.isfinite(t["mu"])) and np.all(t["v"] > 0)
 
 
+def test_config3_shape_long_unequal_trials_vs_oracle(vl):
+    """BASELINE config 3 shape at reduced trial count: N = 200 neurons, L = 10 latents, unequal lengths in [500, 2000]
+    (fp64 here; the fp32 arithmetic of config 3 is not built).  The uncut-trial path (one prior factor per unique
+    length, T x 50 factors streamed from HBM) is compared with the oracle on every trial."""
+    from vlgp_b200 import core
+    from vlgp_b200.gp import make_cholesky
+    from vlgp_b200.synth import make_trials
+    from oracle import vlgp_oracle as orc
+
+    rng = np.random.default_rng(3)
+    N, L = 200, 10
+    trials = make_trials(3, (500, 2000), N, L, seed=7)
+    lengths = [t["y"].shape[0] for t in trials]
+    assert len(set(lengths)) == 3
+    params = dict(a=0.1 * rng.standard_normal((L, N)), b=np.full((1, N), np.log(0.08)), noise=np.ones(N),
+                  omega=np.exp(rng.uniform(np.log(2e-3), np.log(4e-2), L)), sigma=np.ones(L),
+                  likelihood=np.array(["poisson"] * N), zdim=L, ydim=N, xdim=1, rank=50, gp_noise=1e-4, dt=1)
+    for t in trials:
+        n = t["y"].shape[0]
+        t.update(x=np.ones((n, 1, N)), mu=0.1 * rng.standard_normal((n, L)), v=np.zeros((n, L)), w=np.zeros((n, L)),
+                 dmu=np.zeros((n, L)))
+    cfg = _cfg(Eniter=3)
+    make_cholesky(trials, params, cfg)
+    ref_chol = orc.make_cholesky(lengths, params["omega"], params["sigma"], 50)
+    for T in lengths:
+        assert relerr(params["cholesky"][T], ref_chol[T]) < 1e-11
+    t_ref, p_ref = copy.deepcopy(trials), copy.deepcopy(params)
+    orc.update_w(t_ref, p_ref)
+    orc.update_v(t_ref, p_ref, cfg)
+    orc.estep(t_ref, p_ref, cfg)
+    core.update_w(trials, params, cfg)
+    core.update_v(trials, params, cfg)
+    core.estep(trials, params, cfg)
+    for a, b in zip(trials, t_ref):
+        for k in ("mu", "v", "w"):
+            assert relerr(a[k], b[k]) < STEP_TOL, k
+
+
+def test_callbacks_and_constraints(vl):
+    """vem surface details: callbacks see coherent host dicts every iteration; constrain_latent='both' and the 'svd' /
+    row-norm loading constraints run on the device and match the oracle."""
+    from vlgp_b200 import core
+    from oracle import vlgp_oracle as orc
+
+    for loading, latent in (("fro", "both"), ("svd", False), (2, "location")):
+        segs, params = _problem(21, 2, 100, 15, 3)
+        cfg = _cfg(max_iter=2, min_iter=2, Eniter=3, Mniter=3, Hstep=False, constrain_loading=loading,
+                   constrain_latent=latent)
+        s_ref, p_ref, c_ref = copy.deepcopy(segs), copy.deepcopy(params), copy.deepcopy(cfg)
+        seen = []
+        cfg["callbacks"] = [lambda tr, pa, co: seen.append((co["runtime"]["it"], float(np.sum(tr[0]["mu"]))))]
+        core.vem(segs, params, cfg)
+        orc.vem(s_ref, p_ref, c_ref)
+        assert [it for it, _ in seen] == [1, 2] and np.isfinite(seen[-1][1])
+        assert relerr(np.stack([s["mu"] for s in segs]), np.stack([s["mu"] for s in s_ref])) < 1e-8, (loading, latent)
+        assert relerr(params["a"], p_ref["a"]) < 1e-8 and relerr(params["b"], p_ref["b"]) < 1e-8
+
+
 def test_errors_are_loud(vl):
     from vlgp_b200 import core
     from vlgp_b200._lib import VlgpNativeError

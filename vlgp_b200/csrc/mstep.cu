@@ -67,15 +67,41 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
         bn = p.b[n];
         pois = p.poisson[n] != 0;
     }
+    // Software pipeline: the (mu, v) rows and this thread's own counts of tile k+1 are fetched into registers while
+    // tile k is being processed, so the L2 latency of the loads is off the critical path.
+    constexpr int PFMAX = 2;                       // host guarantees 2 * TB * LT <= PFMAX * blockDim
+    double mvnext[PFMAX], ynext[MS_U];
+    auto prefetch = [&](int64_t t0) {
+        const int nb = (int)((b1 - t0 < TB) ? (b1 - t0) : TB);
+#pragma unroll
+        for (int q = 0; q < PFMAX; ++q) {
+            const int i = tid + q * blockDim.x;        // element i of the tile's [t][mu(LT) | v(LT)] block
+            mvnext[q] = 0.0;
+            if (t0 < b1 && i < nb * 2 * LT) {
+                const int t = i / (2 * LT), c = i - t * 2 * LT;
+                mvnext[q] = c < LT ? p.mu[(t0 + t) * LT + c] : p.v[(t0 + t) * LT + (c - LT)];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MS_U; ++u) {
+            const int t = j + u * p.J;
+            ynext[u] = (active && t0 < b1 && t < nb) ? load_y(p.y, p.ydtype, (t0 + t) * p.N + n) : 0.0;
+        }
+    };
+    prefetch(b0);
     for (int64_t t0 = b0; t0 < b1; t0 += TB) {
         const int nb = (int)((b1 - t0 < TB) ? (b1 - t0) : TB);
         __syncthreads();
-        for (int i = tid; i < nb * LT; i += blockDim.x) {          // coalesced: the tile's mu and v are contiguous
-            const int t = i / LT, l = i - t * LT;
-            muv[t * 2 * LT + l] = p.mu[t0 * LT + i];
-            muv[t * 2 * LT + LT + l] = p.v[t0 * LT + i];
+#pragma unroll
+        for (int q = 0; q < PFMAX; ++q) {
+            const int i = tid + q * blockDim.x;
+            if (i < nb * 2 * LT) muv[i] = mvnext[q];
         }
+        double ycur[MS_U];
+#pragma unroll
+        for (int u = 0; u < MS_U; ++u) ycur[u] = ynext[u];
         __syncthreads();
+        prefetch(t0 + TB);
         if (!active) continue;
         // phase A: MS_U independent rate evaluations
         double r[MS_U], yv[MS_U], eta[MS_U];
@@ -94,7 +120,7 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
                     h = fma(mv[LT + l], a2[l], h);
                 }
                 eta[u] = e;
-                yv[u] = load_y(p.y, p.ydtype, (t0 + t) * p.N + n);
+                yv[u] = ycur[u];
                 if (pois) r[u] = trunc_exp(e + 0.5 * h);
             }
         }
@@ -349,7 +375,8 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
     const int N = ctx->N;
     const int NC = N < MAXT ? N : MAXT;
     const int nchunk = (N + NC - 1) / NC;
-    const int J = (MAXT / NC) < (MS_TB_MAX / MS_U) ? (MAXT / NC) : (MS_TB_MAX / MS_U);
+    int J = (MAXT / NC) < (MS_TB_MAX / MS_U) ? (MAXT / NC) : (MS_TB_MAX / MS_U);
+    while (J > 1 && 2 * MS_U * J * LT > 2 * (((J * NC + 31) / 32) * 32)) --J;      // prefetch registers: PFMAX = 2
     int nt = ((J * NC + 31) / 32) * 32;
     const size_t smem = ((size_t)MS_TB_MAX * 2 * LT + 2 * (size_t)nt) * sizeof(double);
     int per_sm = 1;
