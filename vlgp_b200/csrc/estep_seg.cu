@@ -13,6 +13,7 @@
 //   * only the nc leading non-zero columns of each latent's prior factor are kept (compact copy in shared memory,
 //     loaded once per CTA): nc = 6..29 for the reference's omega bounds at W = 50.
 #include "common.cuh"
+#include "dmma.cuh"
 #include "linalg.cuh"
 
 namespace {
@@ -30,6 +31,8 @@ struct SegArgs {
     int pairoff[VLGP_MAX_L + 1];  // prefix sums of nc (nc + 1) / 2 : (latent, Gram entry) items
     int coloff[VLGP_MAX_L + 1];   // prefix sums of nc : (latent, column) items
     int pair_total, col_total;
+    int ldm[VLGP_MAX_L];          // leading dimension of latent l's r x r matrix in SMEM
+    int use_dmma;                 // every nc <= 16: Gram / inverse / variance on the FP64 tensor path
     const void *y;
     int ydtype;
     double *mu, *v, *w, *dmu;
@@ -164,8 +167,8 @@ __device__ __forceinline__ void gram_all(const SegArgs &p, const Smem<LT> &s) {
         if (t < W) c0 = fma(g[t * ldg + i] * wl[t * LT], g[t * ldg + j], c0);
         const double c = c0 + c1 + ((i == j) ? 1.0 : 0.0);
         double *M = s.Mi + p.moff[l];
-        M[i * ldg + j] = c;
-        M[j * ldg + i] = c;
+        M[i * p.ldm[l] + j] = c;
+        M[j * p.ldm[l] + i] = c;
     }
 }
 
@@ -196,20 +199,194 @@ __device__ __forceinline__ bool warp_sweep(double *M, int ldm, int nc, double *c
     return true;
 }
 
-// Gram + sweep for every latent: on return M_l = -(I + G_l' W_l G_l)^-1 and bad[l] says whether that failed.
+// One latent on the FP64 tensor path, by one warp, without block barriers: Gram matrix I + G' diag(w) G accumulated by
+// DMMA straight from the compact factor in SMEM (A operand = w-scaled column fragment, B operand = the same fragment
+// unscaled), blocked symmetric sweep on the NB x NB tile matrix in registers (dmma.cuh, as in the H-step kernel),
+// -Minv stored to SMEM (both triangles, ld = 8 NB + 4: conflict-free fragment reads), then the marginal variances
+// v_t = G_t Minv G_t' as (G row tile) x Minv by DMMA and a quad reduction.  Index math validated by a 32-lane NumPy
+// emulation (scripts/dmma_estep_emulation.py).
+template <int LT, int NB>
+__device__ __forceinline__ bool factor_variance_dmma_nb(const SegArgs &p, const Smem<LT> &s, int l, bool do_var) {
+    constexpr int NTL = NB * (NB + 1) / 2;
+    const int lane = threadIdx.x & 31, r = lane >> 2, c0 = 2 * (lane & 3);
+    const int W = p.W, nc = p.nc[l], ldg = ldodd(nc);
+    const double *G = s.Gs + p.goff[l];
+    const double *wl = s.w + l;
+    Tile A[NTL];
+#pragma unroll
+    for (int t = 0; t < NTL; ++t) A[t].x = A[t].y = 0.0;
+    for (int k = 0; 4 * k < W; ++k) {
+        const int t = 4 * k + (lane & 3);
+        const bool tin = t < W;
+        const double wt = tin ? wl[t * LT] : 0.0;
+        double g[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int c = 8 * b + r;
+            g[b] = (tin && c < nc) ? G[t * ldg + c] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const double gw = g[i] * wt;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) dmma(A[tix(i, j)], gw, g[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {           // + I (also on the padding, so the sweep stays well defined)
+        A[tix(i, i)].x += (r == c0) ? 1.0 : 0.0;
+        A[tix(i, i)].y += (r == c0 + 1) ? 1.0 : 0.0;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int kb = 0; kb < NB; ++kb) {
+        Tile P = A[tix(kb, kb)];
+        ok = tile_spd_inverse(P, lane) && ok;
+        const double Pt0 = tform(P, 0, lane), Pt1 = tform(P, 1, lane);
+        const double Pn0 = nform(P, 0, lane), Pn1 = nform(P, 1, lane);
+        double V0[NB], V1[NB];
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (m == kb) continue;
+            if (m > kb) {
+                V0[m] = nform(A[tix(m, kb)], 0, lane);
+                V1[m] = nform(A[tix(m, kb)], 1, lane);
+            } else {
+                V0[m] = tform(A[tix(kb, m)], 0, lane);
+                V1[m] = tform(A[tix(kb, m)], 1, lane);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (m == kb) continue;
+            Tile T{0.0, 0.0};
+            if (m > kb) {
+                dmma(T, V0[m], Pt0);
+                dmma(T, V1[m], Pt1);
+                A[tix(m, kb)] = T;
+            } else {
+                dmma(T, Pn0, V0[m]);
+                dmma(T, Pn1, V1[m]);
+                A[tix(kb, m)] = T;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (i == kb) continue;
+            double T0, T1;
+            if (i > kb) {
+                T0 = -nform(A[tix(i, kb)], 0, lane);
+                T1 = -nform(A[tix(i, kb)], 1, lane);
+            } else {
+                T0 = -tform(A[tix(kb, i)], 0, lane);
+                T1 = -tform(A[tix(kb, i)], 1, lane);
+            }
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                if (j == kb) continue;
+                dmma(A[tix(i, j)], T0, V0[j]);
+                dmma(A[tix(i, j)], T1, V1[j]);
+            }
+        }
+        A[tix(kb, kb)].x = -P.x;
+        A[tix(kb, kb)].y = -P.y;
+    }
+    // -Minv -> SMEM, row-major, both triangles
+    constexpr int LDM = 8 * NB + 4;
+    double *M = s.Mi + p.moff[l];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const Tile t = A[tix(i, j)];
+            M[(8 * i + r) * LDM + 8 * j + c0] = t.x;
+            M[(8 * i + r) * LDM + 8 * j + c0 + 1] = t.y;
+            if (i != j) {
+                M[(8 * j + c0) * LDM + 8 * i + r] = t.x;
+                M[(8 * j + c0 + 1) * LDM + 8 * i + r] = t.y;
+            }
+        }
+    __syncwarp();
+    if (!ok) return false;
+    if (do_var) {
+        double Bop[2 * NB][NB];                       // Minv as B operand: [c = 4 k + lane%4][j = 8 jt + lane/4]
+#pragma unroll
+        for (int k = 0; k < 2 * NB; ++k)
+#pragma unroll
+            for (int jt = 0; jt < NB; ++jt) Bop[k][jt] = M[(4 * k + (lane & 3)) * LDM + 8 * jt + r];
+        for (int tt = 0; 8 * tt < W; ++tt) {
+            const int trow = 8 * tt + r;
+            const bool tin = trow < W;
+            const double *grow = G + trow * ldg;
+            double aop[2 * NB];
+#pragma unroll
+            for (int k = 0; k < 2 * NB; ++k) {
+                const int c = 4 * k + (lane & 3);
+                aop[k] = (tin && c < nc) ? grow[c] : 0.0;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int jt = 0; jt < NB; ++jt) {
+                Tile T{0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < 2 * NB; ++k) dmma(T, aop[k], Bop[k][jt]);
+                const int c = 8 * jt + c0;
+                const double g0 = (tin && c < nc) ? grow[c] : 0.0;
+                const double g1 = (tin && c + 1 < nc) ? grow[c + 1] : 0.0;
+                acc = fma(T.x, g0, acc);
+                acc = fma(T.y, g1, acc);
+            }
+            acc += __shfl_xor_sync(FULL, acc, 1);
+            acc += __shfl_xor_sync(FULL, acc, 2);
+            if ((lane & 3) == 0 && tin) s.v[trow * LT + l] = -acc;
+        }
+    }
+    return true;
+}
+
 template <int LT>
-__device__ __forceinline__ void factor_all(const SegArgs &p, const Smem<LT> &s, int *bad) {
+__device__ __forceinline__ bool factor_variance_dmma(const SegArgs &p, const Smem<LT> &s, int l, bool do_var) {
+    // nc <= 16 only (the steady-state regime, nc = 6..12): instantiating the 24- and 32-column variants would raise
+    // the kernel's register count from ~80 to 128 and cost the rate passes a third of their occupancy; larger factors
+    // (omega at its upper bound, first EM iteration) take the scalar path.
+    if (p.nc[l] <= 8) return factor_variance_dmma_nb<LT, 1>(p, s, l, do_var);
+    return factor_variance_dmma_nb<LT, 2>(p, s, l, do_var);
+}
+
+// Factorisation for every latent: on return M_l = -(I + G_l' W_l G_l)^-1, bad[l] says whether that failed (not positive
+// definite), and -- if do_var -- v holds the new marginal variances of the latents that did not fail.  Ends with a
+// block barrier.
+template <int LT>
+__device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s, const int *bad);
+
+template <int LT>
+__device__ __forceinline__ void factor_all(const SegArgs &p, const Smem<LT> &s, int *bad, bool do_var) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (p.use_dmma) {
+        for (int l = wid; l < LT; l += NWARP) {
+            const bool ok = factor_variance_dmma<LT>(p, s, l, do_var);
+            if (lane == 0) {
+                bad[l] = ok ? 0 : 1;
+                if (!ok) atomicAdd(p.flags, 1);
+            }
+        }
+        __syncthreads();
+        return;
+    }
     gram_all<LT>(p, s);
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int l = wid; l < LT; l += NWARP) {
-        const bool ok = warp_sweep(s.Mi + p.moff[l], ldodd(p.nc[l]), p.nc[l], s.vec + (size_t)l * 192);
+        const bool ok = warp_sweep(s.Mi + p.moff[l], p.ldm[l], p.nc[l], s.vec + (size_t)l * 192);
         if (lane == 0) {
             bad[l] = ok ? 0 : 1;
             if (!ok) atomicAdd(p.flags, 1);
         }
     }
     __syncthreads();
+    if (do_var) {
+        variance_all<LT>(p, s, bad);
+        __syncthreads();
+    }
 }
 
 // v_t = G_t Minv G_t' for every (latent, bin)   (M holds -Minv)
@@ -221,13 +398,13 @@ __device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s
         const int l = (int)(((float)idx + 0.5f) * inv_w);
         const int t = idx - l * W;
         if (bad[l]) continue;                                      // failed solve: v keeps its value (core.py:112)
-        const int nc = p.nc[l], ld = ldodd(nc);
+        const int nc = p.nc[l], ld = ldodd(nc), ldm = p.ldm[l];
         const double *g = s.Gs + p.goff[l] + t * ld;
         const double *M = s.Mi + p.moff[l];
         double acc = 0.0;
         for (int i = 0; i < nc; ++i) {
             double inner = 0.0;
-            for (int j = 0; j < nc; ++j) inner = fma(M[i * ld + j], g[j], inner);
+            for (int j = 0; j < nc; ++j) inner = fma(M[i * ldm + j], g[j], inner);
             acc = fma(g[i], inner, acc);
         }
         s.v[t * LT + l] = -acc;
@@ -278,11 +455,11 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
     for (int idx = tid; idx < p.col_total; idx += NT) {
         int l = 0;
         while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
-        const int i = idx - p.coloff[l], nc = p.nc[l], ld = ldodd(nc);
+        const int i = idx - p.coloff[l], nc = p.nc[l], ldm = p.ldm[l];
         const double *M = s.Mi + p.moff[l];
         const double *cv = s.vec + l * 192 + 64;
         double acc = 0.0;
-        for (int j = 0; j < nc; ++j) acc = fma(M[j * ld + i], cv[j], acc);
+        for (int j = 0; j < nc; ++j) acc = fma(M[j * ldm + i], cv[j], acc);
         s.vec[l * 192 + i] = -acc;
     }
     __syncthreads();
@@ -305,7 +482,7 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
 }
 
 template <int LT>
-__global__ void __launch_bounds__(NT) estep_seg_kernel(SegArgs p) {
+__global__ void __launch_bounds__(NT, 3) estep_seg_kernel(SegArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<LT> s(smem_raw, p);
     __shared__ int bad[VLGP_MAX_L];
@@ -346,14 +523,10 @@ __global__ void __launch_bounds__(NT) estep_seg_kernel(SegArgs p) {
 
         for (int it = 0; it < p.n_iter; ++it) {
             if (!(p.skip & 1)) rate_pass<LT, 1>(p, s, bin0);    // ends with a barrier; part (aliases vec) is free again
-            if (it == 0) factor_all<LT>(p, s, bad);             // the first mean step uses the incoming w
+            if (it == 0) factor_all<LT>(p, s, bad, false);      // the first mean step uses the incoming w
             if (!(p.skip & 2)) mean_step_all<LT>(p, s, bad);
             if (!(p.skip & 1)) rate_pass<LT, 2>(p, s, bin0);
-            if (p.method_vb || it + 1 < p.n_iter) {
-                if (!(p.skip & 4)) factor_all<LT>(p, s, bad);
-                if (p.method_vb && !(p.skip & 8)) variance_all<LT>(p, s, bad);
-                __syncthreads();
-            }
+            if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT>(p, s, bad, p.method_vb != 0);
         }
         for (int i = tid; i < W * LT; i += NT) {
             p.mu[bin0 * LT + i] = s.mu[i];
@@ -424,6 +597,9 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     p.n_seg = ts->n_trials; p.W = W; p.N = N; p.rank = ctx->rank;
     p.G = ts->factors[0].d_G;
     int goff = 0, moff = 0, po = 0, co = 0;
+    p.use_dmma = getenv("VLGP_NO_DMMA_ESTEP") ? 0 : 1;
+    for (int l = 0; l < L; ++l)
+        if (ts->factors[0].h_ncol[l] > 16) p.use_dmma = 0;
     for (int l = 0; l < L; ++l) {
         const int nc = ts->factors[0].h_ncol[l];
         if (nc < 1) return VLGP_OK;          // degenerate factor: let the general kernel handle it
@@ -432,8 +608,10 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
         p.moff[l] = moff;
         p.pairoff[l] = po;
         p.coloff[l] = co;
+        const int nb8 = 8 * ((nc + 7) / 8);
+        p.ldm[l] = p.use_dmma ? nb8 + 4 : (nc | 1);
         goff += W * (nc | 1);
-        moff += nc * (nc | 1);
+        moff += p.use_dmma ? nb8 * (nb8 + 4) : nc * (nc | 1);
         po += nc * (nc + 1) / 2;
         co += nc;
     }
