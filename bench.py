@@ -254,9 +254,9 @@ def run_ours(args):
         eng.profile_enable(0x1)                  # E-step launches only: they end with a sync anyway
         c0 = eng.counters()
         sampler = ClockSampler(eng.device)
-        dist.barrier()
+        sampler.start()                          # spawn nvidia-smi BEFORE the barrier: its start-up time differs per rank
         eng.sync()
-        sampler.start()
+        dist.barrier()
         eng.timer_start()
         t0 = time.perf_counter()
         split = np.zeros(3)

@@ -172,6 +172,9 @@ int vlgp_create(int device, vlgp_ctx **out) {
         return rc;
     }
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->pev0) == cudaSuccess && cudaEventCreate(&ctx->pev1) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_flags, 16 * sizeof(int)) == cudaSuccess;
@@ -208,6 +211,8 @@ int vlgp_destroy(vlgp_ctx *ctx) {
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->pev0); cudaEventDestroy(ctx->pev1);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VLGP_OK;

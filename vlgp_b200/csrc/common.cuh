@@ -70,6 +70,8 @@ struct NcclApi;   // dlopen'ed subset of NCCL (comm.cu)
 struct vlgp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;              // side stream for the latency-bound K^-1 kernel of the H-step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaDeviceProp prop{};
     std::string err;
     // model

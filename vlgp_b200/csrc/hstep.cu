@@ -261,8 +261,19 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
     const int W = ts->max_len, S = ts->n_trials, n = eb.n;
     const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
     double *red = ts->d_hout + VLGP_MAX_L * 8;
-    hstep_global_kernel<<<n, NT, smem_g, ctx->stream>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout);
-    CKL();
+    // The K^-1 terms (one CTA per evaluation, latency-bound) run on a second stream concurrently with the per-segment
+    // kernel; the DMMA kernel builds K itself, only the W > 56 fallback reads the K written by the global kernel.
+    const bool dmma_ok = ts->max_len <= 56 && !getenv("VLGP_FORCE_SWEEP_HSTEP");
+    if (dmma_ok) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        hstep_global_kernel<<<n, NT, smem_g, ctx->stream2>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout);
+        CKL();
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    } else {
+        hstep_global_kernel<<<n, NT, smem_g, ctx->stream>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout);
+        CKL();
+    }
     {
         ProfScope ps(ctx, 2);
         bool handled = false;
@@ -274,6 +285,7 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
             CKL();
         }
     }
+    if (dmma_ok) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     hstep_final_kernel<<<n, NT, 0, ctx->stream>>>(S, ts->d_hpart, red);
     CKL();
     int rc = vlgp_allreduce_dev(ctx, red, 2 * n, 0);

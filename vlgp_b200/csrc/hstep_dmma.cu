@@ -7,8 +7,8 @@
 // Only the lower block triangle is stored (NB (NB+1) / 2 tiles, 2 doubles per lane each).  Operand fragments are
 // produced from accumulator-layout tiles with intra-warp shuffles ("N-form": element [lane/4][4h + lane%4], "T-form":
 // element [4h + lane%4][lane/4]); the 8 x 8 pivot block is inverted by an 8-step scalar sweep done with shuffles.
-// No shared-memory traffic and no block barrier inside a segment; K and dK/dlog(omega) sit in shared memory in tile
-// order and are reused by every segment the CTA processes.  The lane-level algorithm was validated against
+// No shared-memory traffic and no block barrier inside a segment; K and dK/dlog(omega) are built once per CTA into
+// shared memory in tile order and reused by every segment the CTA processes.  The lane-level algorithm was validated against
 // numpy.linalg.inv with a 32-lane emulation before it was written in CUDA (scripts/dmma_block_sweep_emulation.py).
 #include "common.cuh"
 #include "dmma.cuh"
@@ -19,12 +19,11 @@ constexpr int WARPS = 4;
 
 
 template <int NB>
-__global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBatch eb, int nseg, int W, int L,
+__global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBatch eb, int nseg, int W, int L, double dt,
                                                                         const double *__restrict__ w,
-                                                                        const double *__restrict__ Kall,
                                                                         double *__restrict__ partall) {
     const int ev = blockIdx.y, l = eb.latent[ev];          // blockIdx.y = evaluation of the batch
-    const double *K = Kall + (size_t)ev * 2 * W * W, *dK = K + (size_t)W * W;
+    const double sigmasq = eb.sigmasq[ev], omega = eb.omega[ev], eps = eb.eps[ev];
     double *part = partall + (size_t)ev * 2 * nseg;
     constexpr int NT = NB * (NB + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -39,11 +38,21 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
         while (tix(i + 1, 0) <= t) ++i;
         const int j = t - tix(i, 0);
         const int gi = 8 * i + r, gj = 8 * j + c0;
-        double2 kv, dv;
-        kv.x = (gi < W && gj < W) ? K[gi * W + gj] : 0.0;
-        kv.y = (gi < W && gj + 1 < W) ? K[gi * W + gj + 1] : 0.0;
-        dv.x = (gi < W && gj < W) ? dK[gi * W + gj] : 0.0;
-        dv.y = (gi < W && gj + 1 < W) ? dK[gi * W + gj + 1] : 0.0;
+        // K = sigma^2 exp(-omega D^2) + eps I and dK/dlog(omega) = -omega D^2 o (K - eps I), built here with the same
+        // expressions as hstep_global_kernel (vlgp/gp.py:46-62) so that the two kernels can run concurrently
+        double2 kv = make_double2(0.0, 0.0), dv = make_double2(0.0, 0.0);
+        if (gi < W && gj < W) {
+            const double dx = (double)(gi - gj) * dt, d2 = dx * dx;
+            const double ks = sigmasq * exp(-omega * d2);
+            kv.x = ks + (gi == gj ? eps : 0.0);
+            dv.x = -ks * d2 * omega;
+        }
+        if (gi < W && gj + 1 < W) {
+            const double dx = (double)(gi - gj - 1) * dt, d2 = dx * dx;
+            const double ks = sigmasq * exp(-omega * d2);
+            kv.y = ks + (gi == gj + 1 ? eps : 0.0);
+            dv.y = -ks * d2 * omega;
+        }
         Ks[t * 32 + lane] = kv;
         dKs[t * 32 + lane] = dv;
     }
@@ -171,8 +180,8 @@ int launch_t(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
         if (ts->dmma_grid > (S + WARPS - 1) / WARPS) ts->dmma_grid = (S + WARPS - 1) / WARPS;
     }
     const int grid = ts->dmma_grid;
-    hstep_segment_dmma_kernel<NB><<<dim3(grid, eb.n), WARPS * 32, smem, ctx->stream>>>(eb, S, ts->max_len, ctx->L, ts->d_w,
-                                                                                      ts->d_K, ts->d_hpart);
+    hstep_segment_dmma_kernel<NB><<<dim3(grid, eb.n), WARPS * 32, smem, ctx->stream>>>(eb, S, ts->max_len, ctx->L, ctx->dt,
+                                                                                      ts->d_w, ts->d_hpart);
     CKL();
     return VLGP_OK;
 }

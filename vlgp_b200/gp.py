@@ -148,6 +148,94 @@ def _lbfgsb(fun, x0, bounds, maxcor=10, ftol=2.2204460492503131e-09, gtol=1e-5, 
         return res.x, float(res.fun), int(res.nfev)
 
 
+class _LbfgsbState:
+    """Reverse-communication state of one L-BFGS-B run (the arrays scipy's driver keeps between setulb calls)."""
+
+    def __init__(self, setulb, int_dtype, x0, bounds, maxcor=10, ftol=2.2204460492503131e-09, gtol=1e-5,
+                 maxfun=15000, maxiter=15000, maxls=20):
+        n = x0.size
+        self.setulb, self.m, self.maxls, self.gtol = setulb, maxcor, maxls, gtol
+        self.low, self.up = np.ascontiguousarray(bounds[:, 0]), np.ascontiguousarray(bounds[:, 1])
+        self.nbd = np.full(n, 2, dtype=int_dtype)
+        self.x = np.clip(x0, self.low, self.up).astype(np.float64)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros((n,), dtype=np.float64)
+        m = maxcor
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=int_dtype)
+        self.task = np.zeros(2, dtype=int_dtype)
+        self.ln_task = np.zeros(2, dtype=int_dtype)
+        self.lsave = np.zeros(4, dtype=int_dtype)
+        self.isave = np.zeros(44, dtype=int_dtype)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.factr = ftol / np.finfo(float).eps
+        self.nfev = self.nit = 0
+        self.maxfun, self.maxiter = maxfun, maxiter
+        self.done = False
+
+    def advance(self):
+        """Run the optimiser until it needs f, g at self.x (returns True) or terminates (returns False)."""
+        while True:
+            self.g = self.g.astype(np.float64)
+            self.setulb(self.m, self.x, self.low, self.up, self.nbd, self.f, self.g, self.factr, self.gtol, self.wa,
+                        self.iwa, self.task, self.lsave, self.isave, self.dsave, self.maxls, self.ln_task)
+            if self.task[0] == 3:
+                return True
+            if self.task[0] == 1:
+                self.nit += 1
+                if self.nit >= self.maxiter:
+                    self.task[0], self.task[1] = 5, 504
+                elif self.nfev > self.maxfun:
+                    self.task[0], self.task[1] = 5, 502
+            else:
+                self.done = True
+                return False
+
+
+def _lockstep_lbfgsb(ts, latents, initials, bounds, mask):
+    """All per-latent L-BFGS-B runs advanced together in ONE host thread: every round collects the points the still
+    active optimisers ask for and evaluates them in one batched device call.  Each optimiser sees exactly the values
+    it would see alone (same setulb routine, same inputs), so the iterates equal the reference's sequential runs;
+    the device sees one set of launches / one allreduce / one synchronisation per round.
+    Returns [(x, f, nfev)] or None when scipy's private entry point is unavailable."""
+    try:
+        from scipy.optimize import _lbfgsb_py as _L
+
+        setulb = _L._lbfgsb.setulb
+        int_dtype = np.int64 if getattr(_L, "HAS_ILP64", False) else np.int32
+        states = [_LbfgsbState(setulb, int_dtype, np.log(np.asarray(x0, dtype=np.float64)),
+                               np.log(np.asarray(bounds, dtype=np.float64))) for x0 in initials]
+        pending = [k for k, st in enumerate(states) if st.advance()]
+    except (ImportError, AttributeError, TypeError):
+        return None
+    maskf = np.asarray(mask, dtype=float)
+    while pending:
+        hypers = np.array([np.exp(states[k].x) for k in pending])
+        todo = list(range(len(pending)))
+        ll = np.empty(len(pending))
+        dll = np.empty(len(pending))
+        while todo:      # the reference's retry when K is not PD (vlgp/gp.py:133-135)
+            l_, d_, info = ts.hstep_objective_batch([latents[pending[i]] for i in todo], hypers[todo])
+            again = []
+            for q, i in enumerate(todo):
+                if info[q] == 1:
+                    hypers[i, 1] += np.log(10)
+                    again.append(i)
+                else:
+                    ll[i], dll[i] = l_[q], d_[q]
+            todo = again
+        nxt = []
+        for i, k in enumerate(pending):
+            st = states[k]
+            st.f = -ll[i]
+            st.g = -(np.array([0.0, dll[i], 0.0]) * maskf)
+            st.nfev += 1
+            if st.advance():
+                nxt.append(k)
+        pending = nxt
+    return [(st.x, float(st.f), st.nfev) for st in states]
+
+
 def optimze1d(ts, latent, initial, bounds, mask, evaluate=None):
     """L-BFGS-B over log(sigma^2, omega, eps) of one latent (name kept from the reference, vlgp/gp.py:100-123).
     ``ts`` is a device TrialSet on which ``hstep_prepare`` has been called."""
@@ -168,7 +256,13 @@ def _optimize_dev(s, params, config):
     mask = np.array([0, 1, 0])
     bounds = ((1e-3, 1), config["omega_bound"], (gp_noise / 2, gp_noise * 2))
     results = [None] * zdim
-    if zdim > 1 and not os.environ.get("VLGP_SEQUENTIAL_HSTEP"):
+    lock = None
+    if not os.environ.get("VLGP_SEQUENTIAL_HSTEP") and not os.environ.get("VLGP_THREADED_HSTEP"):
+        lock = _lockstep_lbfgsb(ts, list(range(zdim)), [(sigma[l] ** 2, omega[l], gp_noise) for l in range(zdim)],
+                                bounds, mask)
+    if lock is not None:
+        results = [(np.exp(x), f, nf) for x, f, nf in lock]
+    elif zdim > 1 and not os.environ.get("VLGP_SEQUENTIAL_HSTEP"):
         ev = _LockstepEvaluator(ts, zdim)
         errors = []
 
