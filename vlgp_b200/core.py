@@ -82,6 +82,12 @@ class Session:
             L = eng.L
 
             def blocks(key):
+                try:
+                    out = [tr[key] for tr in trials]
+                    if not any(b is None for b in out):
+                        return out
+                except KeyError:
+                    pass
                 return [tr[key] if tr.get(key) is not None else np.zeros((n, L)) for tr, n in zip(trials, lengths)]
 
             self.ts.set_state_parts(mu=blocks("mu"), v=blocks("v"), w=blocks("w"))
@@ -113,27 +119,31 @@ class Session:
         """Device state -> trial dicts with the reference's aliasing: mu and v are written IN PLACE (segment arrays are
         views of their trial), w and dmu are rebound to fresh arrays (views of one new block per key)."""
         L = self.eng.L
-        inplace, fresh = {}, {}
+        fresh = {}
         for k in which:
-            ok = k in ("mu", "v") and all(
-                isinstance(tr.get(k), np.ndarray) and tr[k].dtype == np.float64 and tr[k].flags.c_contiguous
-                and tr[k].flags.writeable and tr[k].shape == (int(n), L) for tr, n in zip(trials, self.ts.lengths))
-            if ok:
-                inplace[k] = [tr[k] for tr in trials]
-            else:
+            done = False
+            if k in ("mu", "v"):
+                try:      # in place when every trial already holds a writable C-contiguous float64 block of its shape
+                    self.ts.get_state_parts(**{k: [tr[k] for tr in trials]})
+                    done = True
+                except (KeyError, TypeError, ValueError):
+                    done = False
+            if not done:
                 fresh[k] = np.empty((self.ts.nbin, L))
-        if inplace:
-            self.ts.get_state_parts(**inplace)
         if fresh:
             self.ts.get_state_parts(**{k: [a] for k, a in fresh.items()})
-            for i, tr in enumerate(trials):
-                s0 = int(self.ts.starts[i])
-                s1 = s0 + int(self.ts.lengths[i])
-                for k, a in fresh.items():
-                    if k in ("mu", "v") and isinstance(tr.get(k), np.ndarray) and tr[k].shape == (s1 - s0, L):
-                        tr[k][...] = a[s0:s1]
-                    else:
-                        tr[k] = a[s0:s1]
+            cuts = [int(x) for x in self.ts.starts[1:]]
+            for k, a in fresh.items():
+                views = np.split(a, cuts) if cuts else [a]
+                if k in ("mu", "v"):
+                    for tr, val in zip(trials, views):
+                        if isinstance(tr.get(k), np.ndarray) and tr[k].shape == val.shape:
+                            tr[k][...] = val
+                        else:
+                            tr[k] = val
+                else:
+                    for tr, val in zip(trials, views):
+                        tr[k] = val
 
     def close(self):
         self.ts.free()

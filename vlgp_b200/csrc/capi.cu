@@ -133,9 +133,12 @@ __global__ void fill_kernel(double4 *dst, size_t n) {
         dst[i] = make_double4(0.0, 0.0, 0.0, 0.0);
 }
 
-void free_set(TrialSet &ts) {
-    auto F = [](auto *&p) {
-        if (p) cudaFree((void *)p);
+void free_set(TrialSet &ts, cudaStream_t stream = nullptr) {
+    auto F = [&](auto *&p) {
+        if (p) {
+            if (stream) cudaFreeAsync((void *)p, stream);
+            else cudaFree((void *)p);
+        }
         p = nullptr;
     };
     F(ts.d_len); F(ts.d_start); F(ts.d_fidx); F(ts.d_Gptr); F(ts.d_ncolptr); F(ts.d_y);
@@ -182,6 +185,14 @@ int vlgp_create(int device, vlgp_ctx **out) {
     ok = ok && cudaMallocHost(&ctx->h_pin, 4096) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_small, 4096) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_flags, 0, 16 * sizeof(int)) == cudaSuccess;
+    {   // trial-set buffers come from the stream-ordered pool: keep freed blocks cached instead of returning them to
+        // the OS at every synchronisation, so creating / freeing a trial set costs microseconds, not milliseconds
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     if (!ok) {
         int rc = vlgp_fail(nullptr, VLGP_ERR_CUDA, "vlgp_create: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -197,7 +208,7 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     vlgp_comm_destroy(ctx);
     for (auto &ts : ctx->sets)
-        if (ts.used) free_set(ts);
+        if (ts.used) free_set(ts, ctx->stream);
     auto F = [](auto *&p) {
         if (p) cudaFree((void *)p);
         p = nullptr;
@@ -268,7 +279,7 @@ int vlgp_set_model(vlgp_ctx *ctx, int N, int L, int rank, const uint8_t *poisson
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto &ts : ctx->sets)
-        if (ts.used) free_set(ts);
+        if (ts.used) free_set(ts, ctx->stream);
     auto F = [](auto *&p) {
         if (p) cudaFree((void *)p);
         p = nullptr;
@@ -375,42 +386,43 @@ int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int 
     for (int i = 0; i < n_trials; ++i) ts.h_fidx[i] = uniq[lengths[i]];
 
     const size_t L = ctx->L, N = ctx->N, R = ctx->rank;
-    CK(cudaMalloc(&ts.d_len, n_trials * sizeof(int)));
-    CK(cudaMalloc(&ts.d_start, n_trials * sizeof(int64_t)));
-    CK(cudaMalloc(&ts.d_fidx, n_trials * sizeof(int)));
-    CK(cudaMemcpy(ts.d_len, ts.h_len.data(), n_trials * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ts.d_start, ts.h_start.data(), n_trials * sizeof(int64_t), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ts.d_fidx, ts.h_fidx.data(), n_trials * sizeof(int), cudaMemcpyHostToDevice));
+    CK(vlgp_dalloc(ctx, &ts.d_len, n_trials * sizeof(int)));
+    CK(vlgp_dalloc(ctx, &ts.d_start, n_trials * sizeof(int64_t)));
+    CK(vlgp_dalloc(ctx, &ts.d_fidx, n_trials * sizeof(int)));
+    CK(cudaMemcpyAsync(ts.d_len, ts.h_len.data(), n_trials * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ts.d_start, ts.h_start.data(), n_trials * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ts.d_fidx, ts.h_fidx.data(), n_trials * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<double *> gp(ts.factors.size());
     std::vector<int *> np_(ts.factors.size());
     for (size_t f = 0; f < ts.factors.size(); ++f) {
         PriorFactor &pf = ts.factors[f];
-        CK(cudaMalloc(&pf.d_G, L * pf.length * R * sizeof(double)));
-        CK(cudaMemset(pf.d_G, 0, L * pf.length * R * sizeof(double)));
-        CK(cudaMalloc(&pf.d_ncol, L * sizeof(int)));
-        CK(cudaMemset(pf.d_ncol, 0, L * sizeof(int)));
-        CK(cudaMalloc(&pf.d_piv, L * R * sizeof(int)));
-        CK(cudaMemset(pf.d_piv, 0xff, L * R * sizeof(int)));
+        CK(vlgp_dalloc(ctx, &pf.d_G, L * pf.length * R * sizeof(double)));
+        CK(cudaMemsetAsync(pf.d_G, 0, L * pf.length * R * sizeof(double), ctx->stream));
+        CK(vlgp_dalloc(ctx, &pf.d_ncol, L * sizeof(int)));
+        CK(cudaMemsetAsync(pf.d_ncol, 0, L * sizeof(int), ctx->stream));
+        CK(vlgp_dalloc(ctx, &pf.d_piv, L * R * sizeof(int)));
+        CK(cudaMemsetAsync(pf.d_piv, 0xff, L * R * sizeof(int), ctx->stream));
         pf.h_ncol.assign(L, 0);
         gp[f] = pf.d_G;
         np_[f] = pf.d_ncol;
     }
-    CK(cudaMalloc(&ts.d_Gptr, gp.size() * sizeof(double *)));
-    CK(cudaMalloc(&ts.d_ncolptr, np_.size() * sizeof(int *)));
-    CK(cudaMemcpy(ts.d_Gptr, gp.data(), gp.size() * sizeof(double *), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ts.d_ncolptr, np_.data(), np_.size() * sizeof(int *), cudaMemcpyHostToDevice));
+    CK(vlgp_dalloc(ctx, &ts.d_Gptr, gp.size() * sizeof(double *)));
+    CK(vlgp_dalloc(ctx, &ts.d_ncolptr, np_.size() * sizeof(int *)));
+    CK(cudaMemcpyAsync(ts.d_Gptr, gp.data(), gp.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ts.d_ncolptr, np_.data(), np_.size() * sizeof(int *), cudaMemcpyHostToDevice, ctx->stream));
     const size_t nb = (size_t)ts.nbin;
-    CK(cudaMalloc(&ts.d_mu, nb * L * sizeof(double)));
-    CK(cudaMalloc(&ts.d_v, nb * L * sizeof(double)));
-    CK(cudaMalloc(&ts.d_w, nb * L * sizeof(double)));
-    CK(cudaMalloc(&ts.d_dmu, nb * L * sizeof(double)));
-    CK(cudaMalloc(&ts.d_ra, nb * L * sizeof(double)));
-    CK(cudaMalloc(&ts.d_u, nb * sizeof(double)));
-    CK(cudaMemset(ts.d_mu, 0, nb * L * sizeof(double)));
-    CK(cudaMemset(ts.d_v, 0, nb * L * sizeof(double)));
-    CK(cudaMemset(ts.d_w, 0, nb * L * sizeof(double)));
-    CK(cudaMemset(ts.d_dmu, 0, nb * L * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &ts.d_mu, nb * L * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &ts.d_v, nb * L * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &ts.d_w, nb * L * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &ts.d_dmu, nb * L * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &ts.d_ra, nb * L * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &ts.d_u, nb * sizeof(double)));
+    CK(cudaMemsetAsync(ts.d_mu, 0, nb * L * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ts.d_v, 0, nb * L * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ts.d_w, 0, nb * L * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ts.d_dmu, 0, nb * L * sizeof(double), ctx->stream));
     (void)N;
+    CK(cudaStreamSynchronize(ctx->stream));     // the host tables above are borrowed by the async copies
     *set_id = id;
     return VLGP_OK;
 }
@@ -419,8 +431,7 @@ int vlgp_trials_free(vlgp_ctx *ctx, int set_id) {
     TrialSet *ts = get_set(ctx, set_id);
     if (!ts) return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_free: bad set %d", set_id);
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
-    free_set(*ts);
+    free_set(*ts, ctx->stream);
     return VLGP_OK;
 }
 
@@ -431,11 +442,10 @@ int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydtype) {
     CK(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)ts->nbin * ctx->N * (ydtype == VLGP_Y_U8 ? 1 : sizeof(double));
     if (ts->d_y && ts->ydtype != ydtype) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaFree(ts->d_y));
+        CK(vlgp_dfree(ctx, ts->d_y));
         ts->d_y = nullptr;
     }
-    if (!ts->d_y) CK(cudaMalloc(&ts->d_y, bytes));
+    if (!ts->d_y) CK(vlgp_dalloc(ctx, &ts->d_y, bytes));
     ts->ydtype = ydtype;
     CK(cudaMemcpyAsync(ts->d_y, y, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -478,11 +488,10 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
         if (attempt == 1 && src_dtype == VLGP_Y_U8) break;
         const size_t esz = dst_dtype == VLGP_Y_U8 ? 1 : sizeof(double);
         if (ts->d_y && ts->ydtype != dst_dtype) {
-            CK(cudaStreamSynchronize(ctx->stream));
-            CK(cudaFree(ts->d_y));
+            CK(vlgp_dfree(ctx, ts->d_y));
             ts->d_y = nullptr;
         }
-        if (!ts->d_y) CK(cudaMalloc(&ts->d_y, (size_t)nelem * esz));
+        if (!ts->d_y) CK(vlgp_dalloc(ctx, &ts->d_y, (size_t)nelem * esz));
         ts->ydtype = dst_dtype;
         const int64_t chunk = (int64_t)(STAGE / esz);
         std::atomic<bool> exact(true);
@@ -703,7 +712,7 @@ int vlgp_make_cholesky(vlgp_ctx *ctx, int set_id) {
     }
     CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, 2 * VLGP_MAX_L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     double *work = nullptr;
-    CK(cudaMalloc(&work, (size_t)L * R * ts->max_len * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &work, (size_t)L * R * ts->max_len * sizeof(double)));
     int rc = VLGP_OK;
     for (auto &pf : ts->factors) {
         rc = vlgp_launch_ichol(ctx, pf, ctx->d_small, ctx->d_small + VLGP_MAX_L, work);
@@ -716,7 +725,7 @@ int vlgp_make_cholesky(vlgp_ctx *ctx, int set_id) {
         }
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(work);
+    vlgp_dfree(ctx, work);
     if (!rc && e != cudaSuccess) rc = vlgp_fail(ctx, VLGP_ERR_CUDA, "make_cholesky: %s", cudaGetErrorString(e));
     return rc;
 }
@@ -898,18 +907,18 @@ static int moments(vlgp_ctx *ctx, TrialSet *ts, std::vector<double> &out) {
     int grid = 2 * ctx->prop.multiProcessorCount;
     if ((int64_t)grid * 256 > ts->nbin) grid = (int)((ts->nbin + 255) / 256);
     double *part = nullptr;
-    CK(cudaMalloc(&part, (size_t)(grid + 1) * K * sizeof(double)));
+    CK(vlgp_dalloc(ctx, &part, (size_t)(grid + 1) * K * sizeof(double)));
     moments_kernel<<<grid, 256, 0, ctx->stream>>>(ts->nbin, L, ts->d_mu, ts->d_dmu, part);
     CKL();
     double *res = part + (size_t)grid * K;
     reduce_parts_kernel3<<<1, 64, 0, ctx->stream>>>(part, grid, K, res);
     CKL();
     int rc = vlgp_allreduce_dev(ctx, res, K, 0);
-    if (rc) { cudaFree(part); return rc; }
+    if (rc) { vlgp_dfree(ctx, part); return rc; }
     CK(cudaMemcpyAsync(ctx->h_pin, res, K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     out.assign(ctx->h_pin, ctx->h_pin + K);
-    CK(cudaFree(part));
+    CK(vlgp_dfree(ctx, part));
     return VLGP_OK;
 }
 

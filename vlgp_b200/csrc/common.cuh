@@ -111,6 +111,17 @@ struct vlgp_ctx {
 };
 
 int vlgp_fail(vlgp_ctx *ctx, int code, const char *fmt, ...);
+
+// Trial-set buffers are allocated / freed in stream order from the device's default memory pool (release threshold
+// raised in vlgp_create): a Session per vem() call then costs microseconds of allocator time instead of milliseconds.
+template <typename T>
+static inline cudaError_t vlgp_dalloc(vlgp_ctx *ctx, T **p, size_t bytes) {
+    return cudaMallocAsync((void **)p, bytes, ctx->stream);
+}
+template <typename T>
+static inline cudaError_t vlgp_dfree(vlgp_ctx *ctx, T *p) {
+    return p ? cudaFreeAsync((void *)p, ctx->stream) : cudaSuccess;
+}
 int vlgp_allreduce_dev(vlgp_ctx *ctx, double *d_buf, size_t n, int op);   // comm.cu; no-op when n_ranks == 1
 
 #define CK(call)                                                                                              \

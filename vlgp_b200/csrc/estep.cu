@@ -280,9 +280,9 @@ int launch_estep_t(vlgp_ctx *ctx, TrialSet *ts, EstepArgs &p) {
     if (grid > p.n_trials) grid = p.n_trials;
     if (grid < 1) grid = 1;
     if (ts->minv_grid < grid) {
-        if (ts->d_minv) CK(cudaFree(ts->d_minv));
+        if (ts->d_minv) CK(vlgp_dfree(ctx, ts->d_minv));
         ts->d_minv = nullptr;
-        CK(cudaMalloc(&ts->d_minv, (size_t)grid * LT * rank * rank * sizeof(double)));
+        CK(vlgp_dalloc(ctx, &ts->d_minv, (size_t)grid * LT * rank * rank * sizeof(double)));
         ts->minv_grid = grid;
     }
     p.minv = ts->d_minv;

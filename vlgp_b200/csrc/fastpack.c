@@ -9,13 +9,15 @@
 #include <Python.h>
 #include <stdint.h>
 
-/* pointers(seq, itemsize, ncols, writable) -> (ptrs: bytes of uint64, rows: bytes of int64)
- * Every item must expose a C-contiguous 2-D buffer with the given itemsize and second dimension. */
+/* pointers(seq, itemsize, ncols, writable, fmt) -> (ptrs: bytes of uint64, rows: bytes of int64)
+ * Every item must expose a C-contiguous 2-D buffer with the given itemsize, second dimension and (when fmt is a
+ * non-empty string) struct format character, e.g. "d" for float64, "B" for uint8. */
 static PyObject *fp_pointers(PyObject *self, PyObject *args) {
     PyObject *seq;
     Py_ssize_t itemsize, ncols;
     int writable = 0;
-    if (!PyArg_ParseTuple(args, "Onn|p", &seq, &itemsize, &ncols, &writable)) return NULL;
+    const char *fmt = "";
+    if (!PyArg_ParseTuple(args, "Onn|ps", &seq, &itemsize, &ncols, &writable, &fmt)) return NULL;
     PyObject *fast = PySequence_Fast(seq, "expected a sequence of arrays");
     if (!fast) return NULL;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
@@ -29,7 +31,12 @@ static PyObject *fp_pointers(PyObject *self, PyObject *args) {
         for (Py_ssize_t i = 0; i < n; ++i) {
             Py_buffer view;
             if (PyObject_GetBuffer(PySequence_Fast_GET_ITEM(fast, i), &view, flags) != 0) goto fail;
-            const int ok = view.ndim == 2 && view.itemsize == itemsize && view.shape[1] == ncols;
+            int ok = view.ndim == 2 && view.itemsize == itemsize && view.shape[1] == ncols;
+            if (ok && fmt[0]) {
+                const char *f = view.format ? view.format : "B";
+                while (*f == '<' || *f == '>' || *f == '=' || *f == '@' || *f == '!') ++f;
+                ok = (f[0] == fmt[0]);
+            }
             if (!ok) {
                 PyBuffer_Release(&view);
                 PyErr_Format(PyExc_TypeError, "item %zd: expected a C-contiguous (rows, %zd) array of %zd-byte items", i,

@@ -219,12 +219,12 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     const int maxc = 4 * ctx->prop.multiProcessorCount / (L > 0 ? L : 1) + 1;
     if (chunks > maxc) chunks = maxc;
     if (chunks < 1) chunks = 1;
-    if (!ts->d_mompart) CK(cudaMalloc(&ts->d_mompart, (size_t)maxc * L * WW * sizeof(double)));
+    if (!ts->d_mompart) CK(vlgp_dalloc(ctx, &ts->d_mompart, (size_t)maxc * L * WW * sizeof(double)));
     double *part = ts->d_mompart;
-    if (!ts->d_M) CK(cudaMalloc(&ts->d_M, (size_t)L * WW * sizeof(double)));
-    if (!ts->d_K) CK(cudaMalloc(&ts->d_K, (size_t)VLGP_MAX_L * 2 * WW * sizeof(double)));
-    if (!ts->d_hpart) CK(cudaMalloc(&ts->d_hpart, (size_t)VLGP_MAX_L * 2 * S * sizeof(double)));
-    if (!ts->d_hout) CK(cudaMalloc(&ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double)));
+    if (!ts->d_M) CK(vlgp_dalloc(ctx, &ts->d_M, (size_t)L * WW * sizeof(double)));
+    if (!ts->d_K) CK(vlgp_dalloc(ctx, &ts->d_K, (size_t)VLGP_MAX_L * 2 * WW * sizeof(double)));
+    if (!ts->d_hpart) CK(vlgp_dalloc(ctx, &ts->d_hpart, (size_t)VLGP_MAX_L * 2 * S * sizeof(double)));
+    if (!ts->d_hout) CK(vlgp_dalloc(ctx, &ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double)));
     hstep_moment_kernel<<<dim3(chunks, L), NT, 0, ctx->stream>>>(S, W, L, ts->d_mu, part);
     CKL();
     reduce_parts_kernel2<<<(L * WW + 127) / 128, 128, 0, ctx->stream>>>(part, chunks, L * WW, ts->d_M);

@@ -53,26 +53,26 @@ def pack_y(ys):
 def _pointer_table(arrs, dtype, ncols, writable=False):
     """(arrays kept alive, packed uint64 pointers, packed int64 row counts) of a sequence of 2-D blocks.  Blocks that
     are not C-contiguous arrays of ``dtype`` are converted (copied) first -- except when ``writable``."""
-    itemsize = np.dtype(dtype).itemsize
-    keep = list(arrs)
-    if _fastpack is not None and all(isinstance(a, np.ndarray) and a.dtype == dtype for a in keep):
-        try:
-            ptrs, rows = _fastpack.pointers(keep, itemsize, ncols, writable)
+    dt = np.dtype(dtype)
+    keep = arrs if isinstance(arrs, list) else list(arrs)
+    if _fastpack is not None:
+        try:      # dtype / shape / contiguity / writability are all verified in C
+            ptrs, rows = _fastpack.pointers(keep, dt.itemsize, ncols, writable, dt.char)
             return keep, ptrs, rows
         except (TypeError, ValueError, BufferError):
             pass
     fixed = []
     for a in keep:
         a = np.asarray(a)
-        if a.dtype != dtype or not a.flags.c_contiguous:
+        if a.dtype != dt or not a.flags.c_contiguous or (writable and not a.flags.writeable):
             if writable:
-                raise ValueError("expected writable C-contiguous %s blocks" % np.dtype(dtype).name)
-            a = np.ascontiguousarray(a, dtype=dtype)
+                raise ValueError("expected writable C-contiguous %s blocks" % dt.name)
+            a = np.ascontiguousarray(a, dtype=dt)
         if a.ndim != 2 or a.shape[1] != ncols:
             raise ValueError("expected blocks of shape (rows, %d), got %s" % (ncols, a.shape))
         fixed.append(a)
     if _fastpack is not None:
-        ptrs, rows = _fastpack.pointers(fixed, itemsize, ncols, writable)
+        ptrs, rows = _fastpack.pointers(fixed, dt.itemsize, ncols, writable, dt.char)
     else:
         ptrs = np.array([a.ctypes.data for a in fixed], dtype=np.uint64).tobytes()
         rows = np.array([a.shape[0] for a in fixed], dtype=np.int64).tobytes()
@@ -276,7 +276,7 @@ class TrialSet:
         N = self.eng.N
         if len(ys) != self.lengths.size:
             raise ValueError("expected %d observation blocks, got %d" % (self.lengths.size, len(ys)))
-        src_u8 = all(isinstance(y, np.ndarray) and y.dtype == np.uint8 for y in ys)
+        src_u8 = isinstance(ys[0], np.ndarray) and ys[0].dtype == np.uint8     # mixed dtypes fall to the slow path
         want = np.uint8 if src_u8 else np.float64
         keep, ptrs, rows = _pointer_table(ys, want, N)
         if not np.array_equal(np.frombuffer(rows, dtype=np.int64), self.lengths):
@@ -307,8 +307,6 @@ class TrialSet:
             if arrs is None:
                 continue
             keep, ptrs, rows = _pointer_table(arrs, np.float64, self.eng.L, writable=True)
-            if any(k is not a for k, a in zip(keep, arrs)):
-                raise ValueError("get_state_parts needs writable C-contiguous float64 blocks")
             self.eng._ck(lib.vlgp_trials_get_state_parts(ctx, self.id, self._WHICH[key], len(keep), ptrs, rows),
                          "trials_get_state_parts")
             self.d2h_bytes += self.nbin * self.eng.L * 8
