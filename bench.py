@@ -149,7 +149,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
-                                       "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "50", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -316,13 +316,18 @@ def run_ours(args):
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = None
+    try:        # DRAM bytes per E-step launch from the committed `ncu --set full` capture of the same workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "estep_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roof = {"bound": "fp64", "kernel": "estep (all %d Newton iterations of every segment in one launch)" % config["Eniter"],
             "achieved": f_eff / (e_avg_ms * 1e-3) / 1e12 if e_avg_ms else None,
             "achieved_reference_flops": f_full / (e_avg_ms * 1e-3) / 1e12 if e_avg_ms else None,
             "peak": peak, "unit": "TFLOP/s", "peak_source": "measured in this run: register-resident DFMA loop "
             "(vlgp_peak_fp64); mma.sync.m8n8k4.f64 gives %.1f" % peaks.get("dmma_tflops", float("nan")),
             "frac": (f_eff / (e_avg_ms * 1e-3) / 1e12 / peak) if (e_avg_ms and peak) else None,
-            "traffic": None, "ms_per_launch": e_avg_ms, "launches_timed": e_n,
+            "traffic": traffic, "ms_per_launch": e_avg_ms, "launches_timed": e_n,
             "share_of_step": e_avg_ms / ms_per_step if ms_per_step else None,
             "factor_columns": ncols,
             "hbm": {"peak_copy_gbs_this_run": peaks.get("hbm_gbs_copy"), "peak_measured_json": mp.get("hbm_gbs")}}
@@ -355,7 +360,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="config2")
-    ap.add_argument("--cpu-sample-trials", type=int, default=2)
+    ap.add_argument("--cpu-sample-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
