@@ -70,7 +70,8 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
     // Software pipeline: the (mu, v) rows and this thread's own counts of tile k+1 are fetched into registers while
     // tile k is being processed, so the L2 latency of the loads is off the critical path.
     constexpr int PFMAX = 2;                       // host guarantees 2 * TB * LT <= PFMAX * blockDim
-    double mvnext[PFMAX], ynext[MS_U];
+    double mvnext[PFMAX], ynext_d[MS_U];
+    unsigned int ynext_b[MS_U];                    // raw count bytes: converted at use, so the prefetch does not wait
     auto prefetch = [&](int64_t t0) {
         const int nb = (int)((b1 - t0 < TB) ? (b1 - t0) : TB);
 #pragma unroll
@@ -85,7 +86,13 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
 #pragma unroll
         for (int u = 0; u < MS_U; ++u) {
             const int t = j + u * p.J;
-            ynext[u] = (active && t0 < b1 && t < nb) ? load_y(p.y, p.ydtype, (t0 + t) * p.N + n) : 0.0;
+            ynext_b[u] = 0u;
+            ynext_d[u] = 0.0;
+            if (active && t0 < b1 && t < nb) {
+                const int64_t idx = (t0 + t) * p.N + n;
+                if (p.ydtype == VLGP_Y_U8) ynext_b[u] = ((const uint8_t *)p.y)[idx];
+                else ynext_d[u] = ((const double *)p.y)[idx];
+            }
         }
     };
     prefetch(b0);
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
         }
         double ycur[MS_U];
 #pragma unroll
-        for (int u = 0; u < MS_U; ++u) ycur[u] = ynext[u];
+        for (int u = 0; u < MS_U; ++u) ycur[u] = p.ydtype == VLGP_Y_U8 ? (double)ynext_b[u] : ynext_d[u];
         __syncthreads();
         prefetch(t0 + TB);
         if (!active) continue;
