@@ -134,6 +134,9 @@ VLGP_API int vlgp_comm_unique_id(vlgp_ctx *ctx, const char *libnccl_path, char i
 VLGP_API int vlgp_comm_init(vlgp_ctx *ctx, const char *libnccl_path, int rank, int n_ranks, const char id[128]);
 /* In-place allreduce of a small host buffer through the device (op: 0 = sum, 1 = max). */
 VLGP_API int vlgp_comm_allreduce(vlgp_ctx *ctx, double *buf, int n, int op);
+/* In-place sum-allreduce of a large host array (staged through a temporary device buffer): used by the SPMD fit() to
+ * give every rank the posterior of every trial. */
+VLGP_API int vlgp_comm_allreduce_bulk(vlgp_ctx *ctx, double *buf, int64_t n);
 
 /* ---- measurement helpers (used by bench.py only) ------------------------------------------------------------------ */
 /* Measured FP64 FMA peak (TFLOP/s) of this GPU with a register-resident DFMA loop, and with mma.sync.m8n8k4.f64. */

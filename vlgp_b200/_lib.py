@@ -62,6 +62,7 @@ EXPORTS = {
     "vlgp_comm_unique_id": (C.c_int, [ctx_p, C.c_char_p, C.c_char_p]),
     "vlgp_comm_init": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "vlgp_comm_allreduce": (C.c_int, [ctx_p, c_double_p, C.c_int, C.c_int]),
+    "vlgp_comm_allreduce_bulk": (C.c_int, [ctx_p, c_double_p, C.c_int64]),
     "vlgp_peak_fp64": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "vlgp_peak_hbm": (C.c_int, [ctx_p, C.c_uint64, c_double_p]),
     "vlgp_flush_l2": (C.c_int, [ctx_p]),

@@ -120,4 +120,20 @@ int vlgp_comm_allreduce(vlgp_ctx *ctx, double *buf, int n, int op) {
     return VLGP_OK;
 }
 
+int vlgp_comm_allreduce_bulk(vlgp_ctx *ctx, double *buf, int64_t n) {
+    if (!ctx || !buf) return VLGP_ERR_ARG;
+    REQUIRE(n >= 0, "comm_allreduce_bulk: negative length");
+    if (ctx->n_ranks <= 1 || n == 0) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CK(vlgp_dalloc(ctx, &d, (size_t)n * sizeof(double)));
+    CK(cudaMemcpyAsync(d, buf, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = vlgp_allreduce_dev(ctx, d, (size_t)n, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(buf, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(vlgp_dfree(ctx, d));
+    return VLGP_OK;
+}
+
 }   // extern "C"

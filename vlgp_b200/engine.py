@@ -202,6 +202,13 @@ class Engine:
                 a[i:i + 256] = chunk
         return a.reshape(np.shape(x))
 
+    def allreduce_bulk(self, a):
+        """In-place sum-allreduce of a large C-contiguous float64 host array."""
+        if self.world_size > 1:
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            self._ck(self.lib.vlgp_comm_allreduce_bulk(self.ctx, dptr(a), int(a.size)), "comm_allreduce_bulk")
+        return a
+
     # -- measurement -------------------------------------------------------------------------------------------------
     def peak_fp64(self):
         a, b = C.c_double(), C.c_double()

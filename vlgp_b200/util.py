@@ -57,13 +57,33 @@ def cut_trials(trials, params, config):
     return arr
 
 
-def save(obj, fname, warnings=True):
-    """np.save of the (pickled) result dict, like vlgp/util.py:181-196; callables (params['transform']) are dropped."""
-    if isinstance(obj, dict) and isinstance(obj.get("params"), dict) and "transform" in obj["params"]:
-        obj = dict(obj, params={k: v for k, v in obj["params"].items() if k != "transform"})
-    np.save(fname, obj, allow_pickle=True)
+def save(result, path, ext="npy"):
+    """np.save / np.savez of the result dict, same file naming as vlgp/util.py:181-191 (suffix forced to .npy/.npz).
+    The bound sklearn method ``params['transform']`` is dropped: it is not picklable across library versions."""
+    import pathlib
+
+    path = pathlib.Path(path)
+    if isinstance(result, dict) and isinstance(result.get("params"), dict) and "transform" in result["params"]:
+        result = dict(result, params={k: v for k, v in result["params"].items() if k != "transform"})
+    if ext == "npy":
+        np.save(path.with_suffix(".npy"), result, allow_pickle=True)
+    elif ext == "npz":
+        np.savez(path.with_suffix(".npz"), **result)
+    else:
+        raise NotImplementedError("unknown file type {}".format(ext))
 
 
-def load(fname):
-    out = np.load(fname, allow_pickle=True)
-    return out.item() if out.dtype == object and out.shape == () else out
+def load(path):
+    """Load a result / trial file written by ``save`` or by the reference (vlgp/util.py:194-208); object arrays need
+    ``allow_pickle=True`` on current NumPy, which the reference's loader does not pass."""
+    import pathlib
+
+    path = pathlib.Path(path)
+    if not path.exists():
+        raise FileNotFoundError(path.as_posix())
+    if path.suffix == ".npy":
+        rez = np.load(path, allow_pickle=True)
+        return rez[()] if rez.shape == () else rez
+    if path.suffix == ".npz":
+        return {**np.load(path, allow_pickle=True)}
+    raise NotImplementedError("unknown file type {}".format(path.suffix))
