@@ -8,6 +8,7 @@ import logging
 
 import numpy as np
 
+from . import dist
 from .core import vem, update_w, update_v, infer, _echo
 from .gp import make_cholesky
 from .preprocess import get_params, get_config, fill_trials, fill_params, initialize
@@ -39,11 +40,28 @@ def fit(trials, n_factors, **kwargs):
 
     fill_params(params)
     fill_trials(trials)
-    make_cholesky(trials, params, config)
-    update_w(trials, params, config)
-    update_v(trials, params, config)
 
-    splits = cut_trials(trials, params, config)
+    # Multi-GPU (one process per GPU, vlgp_b200.dist.init_from_env() called first): SPMD -- every rank makes the same
+    # call on the same trials, the host set-up above is replicated, each rank runs the device work of its contiguous
+    # shard of trials (the M-/H-step statistics are allreduced inside vem), and at the end every rank holds the
+    # posterior of every trial.  With one process this is exactly the reference's sequence (vlgp/api.py:49-71).
+    world, rank = dist.world_size(), dist.rank()
+    lo, hi = dist.shard_bounds(len(trials), world, rank)
+    mine = trials[lo:hi] if world > 1 else trials
+
+    make_cholesky(mine, params, config)
+    update_w(mine, params, config)
+    update_v(mine, params, config)
+
+    splits = cut_trials(trials, params, config)      # all trials: the RNG stream equals the single-process run's
+    if world > 1 and config["window"]:
+        import math
+
+        per_trial = [math.ceil(tr["y"].shape[0] / config["window"]) for tr in trials]
+        first = sum(per_trial[:lo])
+        splits = splits[first:first + sum(per_trial[lo:hi])]
+    elif world > 1:
+        splits = mine
     make_cholesky(splits, params, config)
     fill_trials(splits)
 
@@ -52,15 +70,41 @@ def fit(trials, n_factors, **kwargs):
     _echo("Fitting")
     vem(splits, params, config)
 
-    make_cholesky(trials, params, config)
-    update_w(trials, params, config)
-    update_v(trials, params, config)
+    make_cholesky(mine, params, config)
+    update_w(mine, params, config)
+    update_v(mine, params, config)
 
     _echo("Inferring")
-    infer(trials, params, config)
+    infer(mine, params, config)
+    if world > 1:
+        _gather_trials(trials, lo, hi, params)
+        make_cholesky(trials, params, config)        # params["cholesky"] for every trial length, on every rank
     _echo("Done")
 
     return {"trials": trials, "params": params, "config": config}
+
+
+def _gather_trials(trials, lo, hi, params):
+    """Give every rank the (mu, v, w, dmu) of every trial: zero-filled concatenation + one sum-allreduce per key."""
+    from .engine import get_engine
+
+    eng = get_engine()
+    L = params["zdim"]
+    lengths = [tr["y"].shape[0] for tr in trials]
+    starts = np.concatenate([[0], np.cumsum(lengths)])
+    for key in ("mu", "v", "w", "dmu"):
+        buf = np.zeros((int(starts[-1]), L))
+        for i in range(lo, hi):
+            buf[starts[i]:starts[i + 1]] = trials[i][key]
+        eng.allreduce_bulk(buf)
+        for i, tr in enumerate(trials):
+            if lo <= i < hi:
+                continue
+            val = buf[starts[i]:starts[i + 1]]
+            if key in ("mu", "v") and isinstance(tr.get(key), np.ndarray) and tr[key].shape == val.shape:
+                tr[key][...] = val
+            else:
+                tr[key] = val.copy()
 
 
 def transform(trials, params, config):
