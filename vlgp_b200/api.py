@@ -9,7 +9,7 @@ import logging
 import numpy as np
 
 from . import dist
-from .core import vem, update_w, update_v, infer, _echo
+from .core import Session, vem, update_w, update_v, infer, _echo
 from .gp import make_cholesky
 from .preprocess import get_params, get_config, fill_trials, fill_params, initialize
 from .util import cut_trials
@@ -49,9 +49,18 @@ def fit(trials, n_factors, **kwargs):
     lo, hi = dist.shard_bounds(len(trials), world, rank)
     mine = trials[lo:hi] if world > 1 else trials
 
-    make_cholesky(mine, params, config)
-    update_w(mine, params, config)
-    update_v(mine, params, config)
+    # the uncut trials stay on the device from here to the final infer (one upload of y instead of five)
+    full = Session(mine, params, upload_factors=False)
+    try:
+        return _fit_on_device(trials, mine, lo, hi, world, full, params, config)
+    finally:
+        full.close()
+
+
+def _fit_on_device(trials, mine, lo, hi, world, full, params, config):
+    full.make_cholesky(params)                       # make_cholesky(trials): params["cholesky"][T] per trial length
+    update_w(mine, params, config, session=full)
+    update_v(mine, params, config, session=full)
 
     splits = cut_trials(trials, params, config)      # all trials: the RNG stream equals the single-process run's
     if world > 1 and config["window"]:
@@ -70,12 +79,14 @@ def fit(trials, n_factors, **kwargs):
     _echo("Fitting")
     vem(splits, params, config)
 
-    make_cholesky(mine, params, config)
-    update_w(mine, params, config)
-    update_v(mine, params, config)
+    # the segments are views of the trials: vem wrote mu and v through them; parameters and omega changed
+    full.refresh(mine, params, which=("mu", "v"))
+    full.make_cholesky(params)
+    update_w(mine, params, config, session=full)
+    update_v(mine, params, config, session=full)
 
     _echo("Inferring")
-    infer(mine, params, config)
+    infer(mine, params, config, session=full)
     if world > 1:
         _gather_trials(trials, lo, hi, params)
         make_cholesky(trials, params, config)        # params["cholesky"] for every trial length, on every rank

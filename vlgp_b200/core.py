@@ -103,6 +103,11 @@ class Session:
             self.ts.free()
             raise
 
+    def refresh(self, trials, params, which=("mu", "v", "w")):
+        """Re-send parameters and the given per-bin arrays from the host dicts (after another session changed them)."""
+        self.eng.push_params(params)
+        self.ts.set_state_parts(**{k: [tr[k] for tr in trials] for k in which})
+
     def require_factors(self):
         if not self.have_factors:
             raise KeyError("params['cholesky'] lacks the prior factor of a trial length: call make_cholesky first")
@@ -159,11 +164,18 @@ class Session:
 # ----------------------------------------------------------------------------------------------------------------------
 # single steps (stateless: upload, run, download)
 # ----------------------------------------------------------------------------------------------------------------------
-def estep(trials, params, config):
+def _with_session(trials, params, session, **kw):
+    """An open session of the caller (state already on the device) or a temporary one for this call."""
+    import contextlib
+
+    return contextlib.nullcontext(session) if session is not None else Session(trials, params, **kw)
+
+
+def estep(trials, params, config, session=None):
     """Update the variational posterior q (E-step) of every trial."""
     if config["Eniter"] < 1:
         return
-    with Session(trials, params) as s:
+    with _with_session(trials, params, session) as s:
         s.require_factors()
         nfail = s.ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
         if nfail:
@@ -171,33 +183,33 @@ def estep(trials, params, config):
         s.pull(trials)
 
 
-def infer(trials, params, config):
+def infer(trials, params, config, session=None):
     """E-step with Eniter := max_iter on the given (uncut) trials -- vlgp/core.py:260-266."""
     niter = config["Eniter"]
     config["Eniter"] = config["max_iter"]
     t0 = time.perf_counter()
     try:
-        estep(trials, params, config)
+        estep(trials, params, config, session=session)
     finally:
         config["Eniter"] = niter
     _echo("{:.2f}s".format(time.perf_counter() - t0))
 
 
-def update_w(trials, params, config):
-    with Session(trials, params, upload_factors=False) as s:
+def update_w(trials, params, config, session=None):
+    with _with_session(trials, params, session, upload_factors=False) as s:
         s.ts.update_w()
         s.pull(trials, ("w",))
     for tr in trials:
         tr.setdefault("v", np.zeros_like(tr["mu"]))
 
 
-def update_v(trials, params, config):
+def update_v(trials, params, config, session=None):
     if config["method"] != "VB":
         return
     for tr in trials:
         tr.setdefault("w", np.zeros_like(tr["mu"]))
         tr.setdefault("v", np.zeros_like(tr["mu"]))
-    with Session(trials, params) as s:
+    with _with_session(trials, params, session) as s:
         s.require_factors()
         nfail = s.ts.update_v()
         if nfail:
