@@ -32,7 +32,7 @@ struct SegArgs {
     int coloff[VLGP_MAX_L + 1];   // prefix sums of nc : (latent, column) items
     int pair_total, col_total;
     int ldm[VLGP_MAX_L];          // leading dimension of latent l's r x r matrix in SMEM
-    int use_dmma;                 // every nc <= 16: Gram / inverse / variance on the FP64 tensor path
+    int use_dmma;                 // every nc <= 32: Gram / inverse / variance on the FP64 tensor path
     const void *y;
     int ydtype;
     double *mu, *v, *w, *dmu;
@@ -344,13 +344,16 @@ __device__ __forceinline__ bool factor_variance_dmma_nb(const SegArgs &p, const 
     return true;
 }
 
-template <int LT>
+template <int LT, int NBMAX>
 __device__ __forceinline__ bool factor_variance_dmma(const SegArgs &p, const Smem<LT> &s, int l, bool do_var) {
-    // nc <= 16 only (the steady-state regime, nc = 6..12): instantiating the 24- and 32-column variants would raise
-    // the kernel's register count from ~80 to 128 and cost the rate passes a third of their occupancy; larger factors
-    // (omega at its upper bound, first EM iteration) take the scalar path.
+    // The kernel is instantiated twice: NBMAX = 2 serves nc <= 16 (the steady-state regime, nc = 6..12) at ~80
+    // registers / 3 CTAs per SM; NBMAX = 4 serves nc <= 32 (omega near its upper bound: the first EM iterations) at
+    // 128 registers / 2 CTAs per SM.  Keeping the 24- and 32-column code out of the first instantiation is what keeps
+    // the rate passes at full occupancy.
     if (p.nc[l] <= 8) return factor_variance_dmma_nb<LT, 1>(p, s, l, do_var);
-    return factor_variance_dmma_nb<LT, 2>(p, s, l, do_var);
+    if (NBMAX == 2 || p.nc[l] <= 16) return factor_variance_dmma_nb<LT, 2>(p, s, l, do_var);
+    if (p.nc[l] <= 24) return factor_variance_dmma_nb<LT, (NBMAX >= 3 ? 3 : 2)>(p, s, l, do_var);
+    return factor_variance_dmma_nb<LT, (NBMAX >= 4 ? 4 : 2)>(p, s, l, do_var);
 }
 
 // Factorisation for every latent: on return M_l = -(I + G_l' W_l G_l)^-1, bad[l] says whether that failed (not positive
@@ -359,12 +362,12 @@ __device__ __forceinline__ bool factor_variance_dmma(const SegArgs &p, const Sme
 template <int LT>
 __device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s, const int *bad);
 
-template <int LT>
+template <int LT, int NBMAX>
 __device__ __forceinline__ void factor_all(const SegArgs &p, const Smem<LT> &s, int *bad, bool do_var) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (p.use_dmma) {
         for (int l = wid; l < LT; l += NWARP) {
-            const bool ok = factor_variance_dmma<LT>(p, s, l, do_var);
+            const bool ok = factor_variance_dmma<LT, NBMAX>(p, s, l, do_var);
             if (lane == 0) {
                 bad[l] = ok ? 0 : 1;
                 if (!ok) atomicAdd(p.flags, 1);
@@ -481,8 +484,8 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
     __syncthreads();
 }
 
-template <int LT>
-__global__ void __launch_bounds__(NT, 3) estep_seg_kernel(SegArgs p) {
+template <int LT, int NBMAX>
+__global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(SegArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<LT> s(smem_raw, p);
     __shared__ int bad[VLGP_MAX_L];
@@ -523,10 +526,10 @@ __global__ void __launch_bounds__(NT, 3) estep_seg_kernel(SegArgs p) {
 
         for (int it = 0; it < p.n_iter; ++it) {
             if (!(p.skip & 1)) rate_pass<LT, 1>(p, s, bin0);    // ends with a barrier; part (aliases vec) is free again
-            if (it == 0) factor_all<LT>(p, s, bad, false);      // the first mean step uses the incoming w
+            if (it == 0) factor_all<LT, NBMAX>(p, s, bad, false);      // the first mean step uses the incoming w
             if (!(p.skip & 2)) mean_step_all<LT>(p, s, bad);
             if (!(p.skip & 1)) rate_pass<LT, 2>(p, s, bin0);
-            if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT>(p, s, bad, p.method_vb != 0);
+            if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT, NBMAX>(p, s, bad, p.method_vb != 0);
         }
         for (int i = tid; i < W * LT; i += NT) {
             p.mu[bin0 * LT + i] = s.mu[i];
@@ -548,7 +551,7 @@ __global__ void pack_params_kernel(int LN, int N, const double *__restrict__ a, 
     if (i < N) pb[i] = make_double2(b[i], 1.0 / noise[i]);
 }
 
-template <int LT>
+template <int LT, int NBMAX>
 int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *handled) {
     const int LN = LT * p.N;
     if (!ctx->d_ppack) CK(cudaMalloc(&ctx->d_ppack, (size_t)(VLGP_MAX_L + 1) * p.N * sizeof(double2)));
@@ -557,13 +560,13 @@ int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *han
     pack_params_kernel<<<(LN + 255) / 256, 256, 0, ctx->stream>>>(LN, p.N, p.a, p.b, p.noise, (double2 *)p.pa,
                                                                   (double2 *)p.pb);
     CKL();
-    CK(cudaFuncSetAttribute(estep_seg_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(estep_seg_kernel<LT, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_seg_kernel<LT>, NT, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_seg_kernel<LT, NBMAX>, NT, smem));
     if (per_sm < 1) return VLGP_OK;       // does not fit: let the general kernel handle it
     int grid = per_sm * ctx->prop.multiProcessorCount;
     if (grid > p.n_seg) grid = p.n_seg;
-    estep_seg_kernel<LT><<<grid, NT, smem, ctx->stream>>>(p);
+    estep_seg_kernel<LT, NBMAX><<<grid, NT, smem, ctx->stream>>>(p);
     CKL();
     *handled = true;
     return VLGP_OK;
@@ -599,7 +602,7 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     int goff = 0, moff = 0, po = 0, co = 0;
     p.use_dmma = getenv("VLGP_NO_DMMA_ESTEP") ? 0 : 1;
     for (int l = 0; l < L; ++l)
-        if (ts->factors[0].h_ncol[l] > 16) p.use_dmma = 0;
+        if (ts->factors[0].h_ncol[l] > 32) p.use_dmma = 0;
     for (int l = 0; l < L; ++l) {
         const int nc = ts->factors[0].h_ncol[l];
         if (nc < 1) return VLGP_OK;          // degenerate factor: let the general kernel handle it
@@ -630,6 +633,13 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     const size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8);
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
     int rc = VLGP_OK;
-    DISPATCH_L(L, rc = launch_seg_t<LT>(ctx, ts, p, smem, handled));
+    bool big = false;
+    for (int l = 0; l < L; ++l)
+        if (p.nc[l] > 16) big = true;
+    if (big && p.use_dmma) {
+        DISPATCH_L(L, (rc = launch_seg_t<LT, 4>(ctx, ts, p, smem, handled)));
+    } else {
+        DISPATCH_L(L, (rc = launch_seg_t<LT, 2>(ctx, ts, p, smem, handled)));
+    }
     return rc;
 }
