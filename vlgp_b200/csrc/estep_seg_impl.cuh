@@ -1,0 +1,652 @@
+// K2: SMEM-resident E-step for window-length segments (W <= 64 bins): all Eniter Newton iterations of a segment run
+// inside one CTA without touching HBM between the first load and the final store of (mu, v, w, dmu).
+//
+// Replaces core.infer_single_trial (vlgp/core.py:22-120) for the segments vem works on (vlgp/api.py:56,
+// vlgp/util.py:457-499).  Same algebra as estep.cu (mean step through Minv = (I + G'WG)^-1, variance as the quadratic
+// form G_t Minv G_t', one factorisation per latent per iteration shared by the variance and the next mean step).
+//
+// Mapping (256 threads, persistent CTAs looping over segments):
+//   * rate passes (exp link, the residual and weight contractions over neurons) use ALL threads: thread = (bin,
+//     neuron-chunk); the loading a, a^2, bias and the uint8 count tile of the segment are staged in shared memory;
+//   * the per-latent r x r work (Gram, symmetric sweep, variance, mean step) runs in ONE WARP PER LATENT with only
+//     __syncwarp between its stages, so the L latents proceed concurrently and an iteration needs six block barriers;
+//   * only the nc leading non-zero columns of each latent's prior factor are kept (compact copy in shared memory,
+//     loaded once per CTA): nc = 6..29 for the reference's omega bounds at W = 50.
+#pragma once
+#include "common.cuh"
+#include "dmma.cuh"
+#include "linalg.cuh"
+
+namespace segk {
+
+constexpr int NT = 256;
+constexpr int NWARP = NT / 32;
+
+struct SegArgs {
+    int n_seg, W, N, rank;
+    const double *G;              // L x W x rank
+    int nc[VLGP_MAX_L];           // leading non-zero columns per latent
+    int goff[VLGP_MAX_L];         // offsets (doubles) of the compact factor / Minv of latent l inside their regions
+    int moff[VLGP_MAX_L];
+    int g_total, m_total;         // region sizes (doubles)
+    int pairoff[VLGP_MAX_L + 1];  // prefix sums of nc (nc + 1) / 2 : (latent, Gram entry) items
+    int coloff[VLGP_MAX_L + 1];   // prefix sums of nc : (latent, column) items
+    int pair_total, col_total;
+    int ldm[VLGP_MAX_L];          // leading dimension of latent l's r x r matrix in SMEM
+    int use_dmma;                 // every nc <= 32: Gram / inverse / variance on the FP64 tensor path
+    const void *y;
+    int ydtype;
+    double *mu, *v, *w, *dmu;
+    const double *a, *b, *noise;
+    const uint8_t *poisson;
+    const double2 *pa;            // L x N (a, a^2) pairs and N (b, 1/noise) pairs, packed by pack_params_kernel
+    const double2 *pb;
+    int n_iter;
+    double dmu_bound;
+    int method_vb;
+    int *flags;
+    int tpb, chunk;               // threads per bin and neurons per thread in the rate passes
+    int skip;                     // debug/timing only (VLGP_DEBUG_SKIP): 1 rate passes, 2 mean step, 4 factor, 8 variance
+};
+
+__device__ __forceinline__ int ldodd(int n) { return n | 1; }
+
+template <int LT>
+struct Smem {
+    double *a, *a2, *b, *inv_noise, *Gs, *Mi, *mu, *v, *w, *ra, *dmu, *part, *vec;
+    uint8_t *pois, *ys;
+    __device__ Smem(unsigned char *base, const SegArgs &p) {
+        double *d = (double *)base;
+        const int N = p.N, W = p.W;
+        a = d; d += 2 * LT * N;                  // interleaved (a, a^2) pairs: one 128-bit load per (latent, neuron)
+        a2 = a;
+        b = d; d += 2 * N;                       // interleaved (bias, 1 / noise) pairs
+        inv_noise = b;
+        Gs = d; d += p.g_total;
+        Mi = d; d += p.m_total;
+        mu = d; d += W * LT;
+        v = d; d += W * LT;
+        w = d; d += W * LT;
+        ra = d; d += W * LT;
+        dmu = d; d += W * LT;
+        part = d;                                 // rate passes: tpb x W x LT partial sums ...
+        vec = d;                                  // ... aliased with the per-latent vectors (3 x 64) of the r x r phases
+        d += max(p.tpb * W * LT, LT * 192);
+        pois = (uint8_t *)d;
+        ys = pois + ((N + 15) / 16) * 16;
+    }
+};
+
+__host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8) {
+    const size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
+    size_t d = (size_t)2 * LT * N + 2 * N + g_total + m_total + (size_t)5 * W * LT + un;
+    size_t bytes = d * sizeof(double) + ((N + 15) / 16) * 16;
+    if (y_u8) bytes += ((size_t)W * N + 15) / 16 * 16;
+    return bytes;
+}
+
+// One rate pass over the segment.  STAGE 1: part <- partial sums of resid * a_l ; STAGE 2: of U * a_l^2.
+template <int LT, int STAGE, bool FAST>
+__device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, int64_t bin0) {
+    const int tid = threadIdx.x;
+    const int t = tid / p.tpb, k = tid - t * p.tpb;
+    if (t < p.W) {
+        const int N = p.N;
+        double mu_t[LT], v_t[LT], acc[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            mu_t[l] = s.mu[t * LT + l];
+            v_t[l] = s.v[t * LT + l];
+            acc[l] = 0.0;
+        }
+        const double2 *aa = (const double2 *)s.a;
+        const double2 *bb = (const double2 *)s.b;
+        // neurons are interleaved over the tpb threads of a bin (n = k, k + tpb, ...): at every step the threads of a
+        // warp touch tpb CONSECUTIVE neurons, so the (a, a^2), bias and count loads are bank-conflict-free broadcasts
+        if (FAST) {
+            // all channels Poisson, counts staged as uint8: straight-line code, two neurons in flight per iteration
+            const uint8_t *yrow = s.ys + t * N;
+            int n = k;
+            for (; n + p.tpb < N; n += 2 * p.tpb) {
+                const int n2 = n + p.tpb;
+                double al0[LT], al1[LT];
+                double eta0 = bb[n].x, eta1 = bb[n2].x, h0 = 0.0, h1 = 0.0;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    const double2 p0 = aa[l * N + n], p1 = aa[l * N + n2];
+                    eta0 = fma(mu_t[l], p0.x, eta0);
+                    eta1 = fma(mu_t[l], p1.x, eta1);
+                    h0 = fma(v_t[l], p0.y, h0);
+                    h1 = fma(v_t[l], p1.y, h1);
+                    al0[l] = (STAGE == 1) ? p0.x : p0.y;
+                    al1[l] = (STAGE == 1) ? p1.x : p1.y;
+                }
+                const double r0 = trunc_exp(fma(0.5, h0, eta0)), r1 = trunc_exp(fma(0.5, h1, eta1));
+                const double c0 = (STAGE == 1) ? (double)yrow[n] - r0 : r0;
+                const double c1 = (STAGE == 1) ? (double)yrow[n2] - r1 : r1;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) acc[l] = fma(c1, al1[l], fma(c0, al0[l], acc[l]));
+            }
+            if (n < N) {
+                double al0[LT];
+                double eta0 = bb[n].x, h0 = 0.0;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    const double2 p0 = aa[l * N + n];
+                    eta0 = fma(mu_t[l], p0.x, eta0);
+                    h0 = fma(v_t[l], p0.y, h0);
+                    al0[l] = (STAGE == 1) ? p0.x : p0.y;
+                }
+                const double r0 = trunc_exp(fma(0.5, h0, eta0));
+                const double c0 = (STAGE == 1) ? (double)yrow[n] - r0 : r0;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) acc[l] = fma(c0, al0[l], acc[l]);
+            }
+        } else {
+#pragma unroll 2
+            for (int n = k; n < N; n += p.tpb) {
+                const double2 bn = bb[n];                       // (bias, 1 / noise)
+                double al[LT], eta = bn.x, h = 0.0;
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    const double2 p2 = aa[l * N + n];          // (a, a^2)
+                    eta = fma(mu_t[l], p2.x, eta);
+                    h = fma(v_t[l], p2.y, h);
+                    al[l] = (STAGE == 1) ? p2.x : p2.y;
+                }
+                const bool pois = s.pois[n] != 0;
+                const double rate = trunc_exp(fma(0.5, h, eta));       // computed for every channel: no branch
+                double coef;
+                if (STAGE == 1) {
+                    const double yv = p.ydtype == VLGP_Y_U8 ? (double)s.ys[t * N + n]
+                                                           : ((const double *)p.y)[(bin0 + t) * N + n];
+                    coef = pois ? yv - rate : (yv - eta) * bn.y;
+                } else {
+                    coef = pois ? rate : bn.y;
+                }
+#pragma unroll
+                for (int l = 0; l < LT; ++l) acc[l] = fma(coef, al[l], acc[l]);
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < LT; ++l) s.part[(k * p.W + t) * LT + l] = acc[l];
+    }
+    __syncthreads();
+    double *out = (STAGE == 1) ? s.ra : s.w;
+    for (int idx = tid; idx < p.W * LT; idx += NT) {
+        double r = 0.0;
+        for (int kk = 0; kk < p.tpb; ++kk) r += s.part[kk * p.W * LT + idx];
+        out[idx] = r;
+    }
+    __syncthreads();
+}
+
+// ---- per-latent r x r work.  Gram, variance and the mean-step mat-vecs are flattened over ALL threads of the CTA as
+// (latent, entry) items so no warp idles; only the short symmetric sweep runs one warp per latent. --------------------
+
+// idx -> (latent, lower-triangle entry (i, j)) of the per-latent Gram matrices; pairoff[l] = first item of latent l
+__device__ __forceinline__ void decode_pair(const SegArgs &p, int LT, int idx, int &l, int &i, int &j) {
+    l = 0;
+    while (l + 1 < LT && idx >= p.pairoff[l + 1]) ++l;
+    tri_decode(idx - p.pairoff[l], i, j);
+}
+
+// M_l <- I + G_l' diag(w_l) G_l for every latent (both triangles written)
+template <int LT>
+__device__ __forceinline__ void gram_all(const SegArgs &p, const Smem<LT> &s) {
+    const int W = p.W;
+    for (int idx = threadIdx.x; idx < p.pair_total; idx += NT) {
+        int l, i, j;
+        decode_pair(p, LT, idx, l, i, j);
+        const int ldg = ldodd(p.nc[l]);
+        const double *g = s.Gs + p.goff[l];
+        const double *wl = s.w + l;
+        double c0 = 0.0, c1 = 0.0;
+        int t = 0;
+        for (; t + 1 < W; t += 2) {
+            c0 = fma(g[t * ldg + i] * wl[t * LT], g[t * ldg + j], c0);
+            c1 = fma(g[(t + 1) * ldg + i] * wl[(t + 1) * LT], g[(t + 1) * ldg + j], c1);
+        }
+        if (t < W) c0 = fma(g[t * ldg + i] * wl[t * LT], g[t * ldg + j], c0);
+        const double c = c0 + c1 + ((i == j) ? 1.0 : 0.0);
+        double *M = s.Mi + p.moff[l];
+        M[i * p.ldm[l] + j] = c;
+        M[j * p.ldm[l] + i] = c;
+    }
+}
+
+// In-place symmetric sweep of one latent's matrix by one warp: M <- -M^-1.  Returns false (warp-uniform) if a pivot is
+// not positive (the matrix is not positive definite).
+__device__ __forceinline__ bool warp_sweep(double *M, int ldm, int nc, double *colk) {
+    const int lane = threadIdx.x & 31;
+    const float inv_nc = 1.0f / (float)nc;
+    const int nn = nc * nc;
+    for (int k = 0; k < nc; ++k) {
+        for (int i = lane; i < nc; i += 32) colk[i] = M[i * ldm + k];
+        __syncwarp();
+        const double d = colk[k];
+        if (!(d > 0.0)) return false;
+        const double pinv = fast_rcp(d);
+        for (int e = lane; e < nn; e += 32) {
+            const int i = (int)(((float)e + 0.5f) * inv_nc);      // exact floor(e / nc) for e < 4096, nc <= 64
+            const int j = e - i * nc;
+            const double ci = colk[i], cj = colk[j];
+            double val;
+            if (i == k) val = (j == k) ? -pinv : cj * pinv;
+            else if (j == k) val = ci * pinv;
+            else val = fma(-ci * pinv, cj, M[i * ldm + j]);
+            M[i * ldm + j] = val;
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// One latent on the FP64 tensor path, by one warp, without block barriers: Gram matrix I + G' diag(w) G accumulated by
+// DMMA straight from the compact factor in SMEM (A operand = w-scaled column fragment, B operand = the same fragment
+// unscaled), blocked symmetric sweep on the NB x NB tile matrix in registers (dmma.cuh, as in the H-step kernel),
+// -Minv stored to SMEM (both triangles, ld = 8 NB + 4: conflict-free fragment reads), then the marginal variances
+// v_t = G_t Minv G_t' as (G row tile) x Minv by DMMA and a quad reduction.  Index math validated by a 32-lane NumPy
+// emulation (scripts/dmma_estep_emulation.py).
+template <int LT, int NB>
+__device__ __forceinline__ bool factor_variance_dmma_nb(const SegArgs &p, const Smem<LT> &s, int l, bool do_var) {
+    constexpr int NTL = NB * (NB + 1) / 2;
+    const int lane = threadIdx.x & 31, r = lane >> 2, c0 = 2 * (lane & 3);
+    const int W = p.W, nc = p.nc[l], ldg = ldodd(nc);
+    const double *G = s.Gs + p.goff[l];
+    const double *wl = s.w + l;
+    Tile A[NTL];
+#pragma unroll
+    for (int t = 0; t < NTL; ++t) A[t].x = A[t].y = 0.0;
+    for (int k = 0; 4 * k < W; ++k) {
+        const int t = 4 * k + (lane & 3);
+        const bool tin = t < W;
+        const double wt = tin ? wl[t * LT] : 0.0;
+        double g[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int c = 8 * b + r;
+            g[b] = (tin && c < nc) ? G[t * ldg + c] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const double gw = g[i] * wt;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) dmma(A[tix(i, j)], gw, g[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {           // + I (also on the padding, so the sweep stays well defined)
+        A[tix(i, i)].x += (r == c0) ? 1.0 : 0.0;
+        A[tix(i, i)].y += (r == c0 + 1) ? 1.0 : 0.0;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int kb = 0; kb < NB; ++kb) {
+        Tile P = A[tix(kb, kb)];
+        ok = tile_spd_inverse(P, lane) && ok;
+        const double Pt0 = tform(P, 0, lane), Pt1 = tform(P, 1, lane);
+        const double Pn0 = nform(P, 0, lane), Pn1 = nform(P, 1, lane);
+        double V0[NB], V1[NB];
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (m == kb) continue;
+            if (m > kb) {
+                V0[m] = nform(A[tix(m, kb)], 0, lane);
+                V1[m] = nform(A[tix(m, kb)], 1, lane);
+            } else {
+                V0[m] = tform(A[tix(kb, m)], 0, lane);
+                V1[m] = tform(A[tix(kb, m)], 1, lane);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (m == kb) continue;
+            Tile T{0.0, 0.0};
+            if (m > kb) {
+                dmma(T, V0[m], Pt0);
+                dmma(T, V1[m], Pt1);
+                A[tix(m, kb)] = T;
+            } else {
+                dmma(T, Pn0, V0[m]);
+                dmma(T, Pn1, V1[m]);
+                A[tix(kb, m)] = T;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (i == kb) continue;
+            double T0, T1;
+            if (i > kb) {
+                T0 = -nform(A[tix(i, kb)], 0, lane);
+                T1 = -nform(A[tix(i, kb)], 1, lane);
+            } else {
+                T0 = -tform(A[tix(kb, i)], 0, lane);
+                T1 = -tform(A[tix(kb, i)], 1, lane);
+            }
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                if (j == kb) continue;
+                dmma(A[tix(i, j)], T0, V0[j]);
+                dmma(A[tix(i, j)], T1, V1[j]);
+            }
+        }
+        A[tix(kb, kb)].x = -P.x;
+        A[tix(kb, kb)].y = -P.y;
+    }
+    // -Minv -> SMEM, row-major, both triangles
+    constexpr int LDM = 8 * NB + 4;
+    double *M = s.Mi + p.moff[l];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const Tile t = A[tix(i, j)];
+            M[(8 * i + r) * LDM + 8 * j + c0] = t.x;
+            M[(8 * i + r) * LDM + 8 * j + c0 + 1] = t.y;
+            if (i != j) {
+                M[(8 * j + c0) * LDM + 8 * i + r] = t.x;
+                M[(8 * j + c0 + 1) * LDM + 8 * i + r] = t.y;
+            }
+        }
+    __syncwarp();
+    if (!ok) return false;
+    if (do_var) {
+        double Bop[2 * NB][NB];                       // Minv as B operand: [c = 4 k + lane%4][j = 8 jt + lane/4]
+#pragma unroll
+        for (int k = 0; k < 2 * NB; ++k)
+#pragma unroll
+            for (int jt = 0; jt < NB; ++jt) Bop[k][jt] = M[(4 * k + (lane & 3)) * LDM + 8 * jt + r];
+        for (int tt = 0; 8 * tt < W; ++tt) {
+            const int trow = 8 * tt + r;
+            const bool tin = trow < W;
+            const double *grow = G + trow * ldg;
+            double aop[2 * NB];
+#pragma unroll
+            for (int k = 0; k < 2 * NB; ++k) {
+                const int c = 4 * k + (lane & 3);
+                aop[k] = (tin && c < nc) ? grow[c] : 0.0;
+            }
+            double acc = 0.0;
+#pragma unroll
+            for (int jt = 0; jt < NB; ++jt) {
+                Tile T{0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < 2 * NB; ++k) dmma(T, aop[k], Bop[k][jt]);
+                const int c = 8 * jt + c0;
+                const double g0 = (tin && c < nc) ? grow[c] : 0.0;
+                const double g1 = (tin && c + 1 < nc) ? grow[c + 1] : 0.0;
+                acc = fma(T.x, g0, acc);
+                acc = fma(T.y, g1, acc);
+            }
+            acc += __shfl_xor_sync(FULL, acc, 1);
+            acc += __shfl_xor_sync(FULL, acc, 2);
+            if ((lane & 3) == 0 && tin) s.v[trow * LT + l] = -acc;
+        }
+    }
+    return true;
+}
+
+template <int LT, int NBMAX>
+__device__ __forceinline__ bool factor_variance_dmma(const SegArgs &p, const Smem<LT> &s, int l, bool do_var) {
+    // The kernel is instantiated twice: NBMAX = 2 serves nc <= 16 (the steady-state regime, nc = 6..12) at ~80
+    // registers / 3 CTAs per SM; NBMAX = 4 serves nc <= 32 (omega near its upper bound: the first EM iterations) at
+    // 128 registers / 2 CTAs per SM.  Keeping the 24- and 32-column code out of the first instantiation is what keeps
+    // the rate passes at full occupancy.
+    if (p.nc[l] <= 8) return factor_variance_dmma_nb<LT, 1>(p, s, l, do_var);
+    if (NBMAX == 2 || p.nc[l] <= 16) return factor_variance_dmma_nb<LT, 2>(p, s, l, do_var);
+    if (p.nc[l] <= 24) return factor_variance_dmma_nb<LT, (NBMAX >= 3 ? 3 : 2)>(p, s, l, do_var);
+    return factor_variance_dmma_nb<LT, (NBMAX >= 4 ? 4 : 2)>(p, s, l, do_var);
+}
+
+// Factorisation for every latent: on return M_l = -(I + G_l' W_l G_l)^-1, bad[l] says whether that failed (not positive
+// definite), and -- if do_var -- v holds the new marginal variances of the latents that did not fail.  Ends with a
+// block barrier.
+template <int LT>
+__device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s, const int *bad);
+
+template <int LT, int NBMAX>
+__device__ __forceinline__ void factor_all(const SegArgs &p, const Smem<LT> &s, int *bad, bool do_var) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (p.use_dmma) {
+        for (int l = wid; l < LT; l += NWARP) {
+            const bool ok = factor_variance_dmma<LT, NBMAX>(p, s, l, do_var);
+            if (lane == 0) {
+                bad[l] = ok ? 0 : 1;
+                if (!ok) atomicAdd(p.flags, 1);
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    gram_all<LT>(p, s);
+    __syncthreads();
+    for (int l = wid; l < LT; l += NWARP) {
+        const bool ok = warp_sweep(s.Mi + p.moff[l], p.ldm[l], p.nc[l], s.vec + (size_t)l * 192);
+        if (lane == 0) {
+            bad[l] = ok ? 0 : 1;
+            if (!ok) atomicAdd(p.flags, 1);
+        }
+    }
+    __syncthreads();
+    if (do_var) {
+        variance_all<LT>(p, s, bad);
+        __syncthreads();
+    }
+}
+
+// v_t = G_t Minv G_t' for every (latent, bin)   (M holds -Minv)
+template <int LT>
+__device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s, const int *bad) {
+    const int W = p.W;
+    const float inv_w = 1.0f / (float)W;
+    for (int idx = threadIdx.x; idx < LT * W; idx += NT) {
+        const int l = (int)(((float)idx + 0.5f) * inv_w);
+        const int t = idx - l * W;
+        if (bad[l]) continue;                                      // failed solve: v keeps its value (core.py:112)
+        const int nc = p.nc[l], ld = ldodd(nc), ldm = p.ldm[l];
+        const double *g = s.Gs + p.goff[l] + t * ld;
+        const double *M = s.Mi + p.moff[l];
+        double acc = 0.0;
+        for (int i = 0; i < nc; ++i) {
+            double inner = 0.0;
+            for (int j = 0; j < nc; ++j) inner = fma(M[i * ldm + j], g[j], inner);
+            acc = fma(g[i], inner, acc);
+        }
+        s.v[t * LT + l] = -acc;
+    }
+}
+
+// Newton step of the posterior mean of every latent (vlgp/core.py:81-97), Jacobi over latents.
+// vec: per latent 3 x 64 doubles (pv / cv / uv).
+template <int LT>
+__device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &s, const int *bad) {
+    const int W = p.W, tid = threadIdx.x;
+    const float inv_w = 1.0f / (float)W;
+    // p = G' (resid a_l)
+    for (int idx = tid; idx < p.col_total; idx += NT) {
+        int l = 0;
+        while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+        const int j = idx - p.coloff[l], ld = ldodd(p.nc[l]);
+        const double *g = s.Gs + p.goff[l];
+        double acc = 0.0;
+        for (int t = 0; t < W; ++t) acc = fma(g[t * ld + j], s.ra[t * LT + l], acc);
+        s.vec[l * 192 + j] = acc;
+    }
+    __syncthreads();
+    // u = G p - mu_l
+    for (int idx = tid; idx < LT * W; idx += NT) {
+        const int l = (int)(((float)idx + 0.5f) * inv_w), t = idx - l * W;
+        const int nc = p.nc[l], ld = ldodd(nc);
+        const double *g = s.Gs + p.goff[l] + t * ld;
+        const double *pv = s.vec + l * 192;
+        double acc = 0.0;
+        for (int j = 0; j < nc; ++j) acc = fma(g[j], pv[j], acc);
+        s.vec[l * 192 + 128 + t] = acc - s.mu[t * LT + l];
+    }
+    __syncthreads();
+    // c = G' (w_l o u)
+    for (int idx = tid; idx < p.col_total; idx += NT) {
+        int l = 0;
+        while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+        const int j = idx - p.coloff[l], ld = ldodd(p.nc[l]);
+        const double *g = s.Gs + p.goff[l];
+        const double *uv = s.vec + l * 192 + 128;
+        double acc = 0.0;
+        for (int t = 0; t < W; ++t) acc = fma(g[t * ld + j], s.w[t * LT + l] * uv[t], acc);
+        s.vec[l * 192 + 64 + j] = acc;
+    }
+    __syncthreads();
+    // m = Minv c   (M = -Minv, symmetric)
+    for (int idx = tid; idx < p.col_total; idx += NT) {
+        int l = 0;
+        while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+        const int i = idx - p.coloff[l], nc = p.nc[l], ldm = p.ldm[l];
+        const double *M = s.Mi + p.moff[l];
+        const double *cv = s.vec + l * 192 + 64;
+        double acc = 0.0;
+        for (int j = 0; j < nc; ++j) acc = fma(M[j * ldm + i], cv[j], acc);
+        s.vec[l * 192 + i] = -acc;
+    }
+    __syncthreads();
+    // delta = clip(u - G m); a failed factorisation zeroes the step (vlgp/core.py:92-94)
+    for (int idx = tid; idx < LT * W; idx += NT) {
+        const int l = (int)(((float)idx + 0.5f) * inv_w), t = idx - l * W;
+        double d = 0.0;
+        if (!bad[l]) {
+            const int nc = p.nc[l], ld = ldodd(nc);
+            const double *g = s.Gs + p.goff[l] + t * ld;
+            const double *mv = s.vec + l * 192;
+            double acc = 0.0;
+            for (int j = 0; j < nc; ++j) acc = fma(g[j], mv[j], acc);
+            d = clipd(s.vec[l * 192 + 128 + t] - acc, p.dmu_bound);
+        }
+        s.dmu[t * LT + l] = d;
+        s.mu[t * LT + l] += d;
+    }
+    __syncthreads();
+}
+
+template <int LT, int NBMAX, bool FAST>
+__global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(SegArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<LT> s(smem_raw, p);
+    __shared__ int bad[VLGP_MAX_L];
+    const int tid = threadIdx.x;
+    const int W = p.W, N = p.N;
+
+    // ---- once per CTA: parameters and the compact prior factors ------------------------------------------------------
+    for (int i = tid; i < LT * N; i += NT) ((double2 *)s.a)[i] = p.pa[i];
+    for (int n = tid; n < N; n += NT) {
+        ((double2 *)s.b)[n] = p.pb[n];
+        s.pois[n] = p.poisson[n];
+    }
+    for (int l = 0; l < LT; ++l) {
+        const int nc = p.nc[l], ldg = ldodd(nc);
+        const double *Gsrc = p.G + (size_t)l * W * p.rank;
+        double *Gd = s.Gs + p.goff[l];
+        for (int i = tid; i < W * nc; i += NT) {
+            const int t = i / nc, c = i - t * nc;
+            Gd[t * ldg + c] = Gsrc[(size_t)t * p.rank + c];
+        }
+    }
+    __syncthreads();
+
+    for (int seg = blockIdx.x; seg < p.n_seg; seg += gridDim.x) {
+        const int64_t bin0 = (int64_t)seg * W;
+        for (int i = tid; i < W * LT; i += NT) {
+            s.mu[i] = p.mu[bin0 * LT + i];
+            s.v[i] = p.v[bin0 * LT + i];
+            s.w[i] = p.w[bin0 * LT + i];
+            s.dmu[i] = 0.0;
+        }
+        if (p.ydtype == VLGP_Y_U8) {
+            const uint8_t *ysrc = (const uint8_t *)p.y + bin0 * N;
+            for (int i = tid; i < W * N; i += NT) s.ys[i] = ysrc[i];
+        }
+        if (tid < LT) bad[tid] = 0;
+        __syncthreads();
+
+        for (int it = 0; it < p.n_iter; ++it) {
+            if (!(p.skip & 1)) rate_pass<LT, 1, FAST>(p, s, bin0);    // ends with a barrier; part (aliases vec) is free again
+            if (it == 0) factor_all<LT, NBMAX>(p, s, bad, false);      // the first mean step uses the incoming w
+            if (!(p.skip & 2)) mean_step_all<LT>(p, s, bad);
+            if (!(p.skip & 1)) rate_pass<LT, 2, FAST>(p, s, bin0);
+            if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT, NBMAX>(p, s, bad, p.method_vb != 0);
+        }
+        for (int i = tid; i < W * LT; i += NT) {
+            p.mu[bin0 * LT + i] = s.mu[i];
+            p.v[bin0 * LT + i] = s.v[i];
+            p.w[bin0 * LT + i] = s.w[i];
+            p.dmu[bin0 * LT + i] = s.dmu[i];
+        }
+        __syncthreads();
+    }
+}
+
+static __global__ void pack_params_kernel(int LN, int N, const double *__restrict__ a, const double *__restrict__ b,
+                                   const double *__restrict__ noise, double2 *__restrict__ pa, double2 *__restrict__ pb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < LN) {
+        const double x = a[i];
+        pa[i] = make_double2(x, x * x);
+    }
+    if (i < N) pb[i] = make_double2(b[i], 1.0 / noise[i]);
+}
+
+template <int LT, int NBMAX, bool FAST>
+int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *handled) {
+    const int LN = LT * p.N;
+    if (!ctx->d_ppack) CK(cudaMalloc(&ctx->d_ppack, (size_t)(VLGP_MAX_L + 1) * p.N * sizeof(double2)));
+    p.pa = (const double2 *)ctx->d_ppack;
+    p.pb = p.pa + LN;
+    pack_params_kernel<<<(LN + 255) / 256, 256, 0, ctx->stream>>>(LN, p.N, p.a, p.b, p.noise, (double2 *)p.pa,
+                                                                  (double2 *)p.pb);
+    CKL();
+    CK(cudaFuncSetAttribute(estep_seg_kernel<LT, NBMAX, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_seg_kernel<LT, NBMAX, FAST>, NT, smem));
+    if (per_sm < 1) return VLGP_OK;       // does not fit: let the general kernel handle it
+    int grid = per_sm * ctx->prop.multiProcessorCount;
+    if (grid > p.n_seg) grid = p.n_seg;
+    estep_seg_kernel<LT, NBMAX, FAST><<<grid, NT, smem, ctx->stream>>>(p);
+    CKL();
+    *handled = true;
+    return VLGP_OK;
+}
+
+
+template <int NBMAX, bool FAST>
+int launch_seg_variant(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *handled);
+
+}   // namespace segk
+
+#define DISPATCH_L(L, CALL)                                                            \
+    switch (L) {                                                                       \
+        case 1: { constexpr int LT = 1; CALL; } break;                                 \
+        case 2: { constexpr int LT = 2; CALL; } break;                                 \
+        case 3: { constexpr int LT = 3; CALL; } break;                                 \
+        case 4: { constexpr int LT = 4; CALL; } break;                                 \
+        case 5: { constexpr int LT = 5; CALL; } break;                                 \
+        case 6: { constexpr int LT = 6; CALL; } break;                                 \
+        case 7: { constexpr int LT = 7; CALL; } break;                                 \
+        case 8: { constexpr int LT = 8; CALL; } break;                                 \
+        case 9: { constexpr int LT = 9; CALL; } break;                                 \
+        case 10: { constexpr int LT = 10; CALL; } break;                               \
+        case 11: { constexpr int LT = 11; CALL; } break;                               \
+        case 12: { constexpr int LT = 12; CALL; } break;                               \
+        default: return vlgp_fail(ctx, VLGP_ERR_UNSUPPORTED, "n_latents %d > 12", L);  \
+    }
+
+
+// Each variant of the kernel is instantiated in its own translation unit (estep_seg_v*.cu) so that they compile in
+// parallel and do not share a register budget.
+#define VLGP_DEFINE_SEG_VARIANT(NBMAX, FAST)                                                                       \
+    namespace segk {                                                                                               \
+    template <>                                                                                                    \
+    int launch_seg_variant<NBMAX, FAST>(vlgp_ctx * ctx, TrialSet * ts, SegArgs & p, size_t smem, bool *handled) { \
+        int rc = VLGP_OK;                                                                                          \
+        DISPATCH_L(ctx->L, (rc = launch_seg_t<LT, NBMAX, FAST>(ctx, ts, p, smem, handled)));                      \
+        return rc;                                                                                                 \
+    }                                                                                                              \
+    }
