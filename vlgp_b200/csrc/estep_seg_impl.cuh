@@ -121,7 +121,8 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
                     al0[l] = (STAGE == 1) ? p0.x : p0.y;
                     al1[l] = (STAGE == 1) ? p1.x : p1.y;
                 }
-                const double r0 = trunc_exp(fma(0.5, h0, eta0)), r1 = trunc_exp(fma(0.5, h1, eta1));
+                double r0, r1;
+                trunc_exp2(fma(0.5, h0, eta0), fma(0.5, h1, eta1), r0, r1);
                 const double c0 = (STAGE == 1) ? (double)yrow[n] - r0 : r0;
                 const double c1 = (STAGE == 1) ? (double)yrow[n2] - r1 : r1;
 #pragma unroll

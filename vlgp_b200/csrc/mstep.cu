@@ -110,14 +110,16 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
         __syncthreads();
         prefetch(t0 + TB);
         if (!active) continue;
-        // phase A: MS_U independent rate evaluations
-        double r[MS_U], yv[MS_U], eta[MS_U];
+        // phase A: MS_U independent rate evaluations (arguments first, then the exponentials two at a time with
+        // interleaved Horner chains)
+        double r[MS_U], yv[MS_U], eta[MS_U], lin[MS_U];
 #pragma unroll
         for (int u = 0; u < MS_U; ++u) {
             const int t = j + u * p.J;
             r[u] = 0.0;
             yv[u] = 0.0;
             eta[u] = 0.0;
+            lin[u] = 0.0;
             if (t < nb) {
                 const double *mv = muv + t * 2 * LT;
                 double e = bn, h = 0.0;
@@ -128,8 +130,12 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
                 }
                 eta[u] = e;
                 yv[u] = ycur[u];
-                if (pois) r[u] = trunc_exp(e + 0.5 * h);
+                lin[u] = e + 0.5 * h;
             }
+        }
+        if (pois) {
+#pragma unroll
+            for (int u = 0; u < MS_U; u += 2) trunc_exp2(lin[u], lin[u + 1], r[u], r[u + 1]);
         }
         // phase B: accumulate
 #pragma unroll
