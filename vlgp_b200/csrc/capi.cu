@@ -566,7 +566,19 @@ static int pipeline_copy(vlgp_ctx *ctx, void *dev, size_t esz, int n_parts, void
     const int64_t nelem = part_off[n_parts];
     const int64_t chunk = (int64_t)(STAGE / esz);
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+    int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+    if (!to_device) {
+        // Overlapping destination blocks (segments of a trial whose length is not a multiple of the window are
+        // overlapping views): scatter with one thread so that the blocks are written in order and the last one wins,
+        // like the reference's sequential loop over segments.
+        for (int i = 0; i + 1 < n_parts && nthreads > 1; ++i) {
+            const unsigned char *a0 = (const unsigned char *)parts[i];
+            const unsigned char *a1 = a0 + (size_t)(part_off[i + 1] - part_off[i]) * esz;
+            const unsigned char *b0 = (const unsigned char *)parts[i + 1];
+            const unsigned char *b1 = b0 + (size_t)(part_off[i + 2] - part_off[i + 1]) * esz;
+            if (a0 < b1 && b0 < a1) nthreads = 1;
+        }
+    }
     auto copy_chunk = [&](int buf, int64_t e0, int64_t e1) {
         int ip = 0;
         {   // binary search of the part containing e0
