@@ -30,7 +30,7 @@ struct MstatArgs {
     int last;                    // accumulate the noise moments
 };
 
-constexpr int MS_U = 4;          // bins per thread per tile: MS_U independent exp chains in flight
+constexpr int MS_U = 2;          // bins per thread per tile: MS_U independent exp chains in flight
 constexpr int MS_TB_MAX = 128;   // bins per SMEM tile (= MS_U * J <= 128)
 
 template <int LT, bool FIRST>
