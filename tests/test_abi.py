@@ -102,3 +102,40 @@ def test_cut_trials_views_and_rng_stream():
     assert [int(s["mu"][0, 0]) // 2 for s in segs] == starts.tolist()
     assert all(np.shares_memory(s["mu"], tr["mu"]) for s in segs)
     assert segs.dtype == object and all(s["y"].shape == (50, 3) for s in segs)
+
+
+def test_save_load_roundtrip_and_cli_parser(tmp_path):
+    """util.save / util.load keep the reference's file naming (suffix forced to .npy) and drop the unpicklable
+    sklearn method; the CLI takes the reference's positional arguments (vlgp/__main__.py:6-11)."""
+    from vlgp_b200 import util
+    from vlgp_b200.__main__ import cli
+
+    res = {"trials": [{"y": np.zeros((3, 2)), "mu": np.ones((3, 1))}], "params": {"a": np.ones((1, 2)), "transform": print},
+           "config": {"window": 50}}
+    util.save(res, tmp_path / "out")
+    back = util.load(tmp_path / "out.npy")
+    assert sorted(back) == ["config", "params", "trials"] and "transform" not in back["params"]
+    assert np.array_equal(back["trials"][0]["mu"], np.ones((3, 1)))
+    with pytest.raises(FileNotFoundError):
+        util.load(tmp_path / "missing.npy")
+    with pytest.raises(SystemExit):
+        cli(["--help"])
+
+
+def test_pointer_tables_and_fastpack():
+    """Host packing helper: dtype / shape / contiguity are verified in C; mismatches fall back to a converting copy
+    (read path) or raise (write path)."""
+    from vlgp_b200.engine import _pointer_table
+
+    blocks = [np.zeros((5, 3)), np.ones((2, 3))]
+    keep, ptrs, rows = _pointer_table(blocks, np.float64, 3)
+    assert np.frombuffer(rows, np.int64).tolist() == [5, 2]
+    assert np.frombuffer(ptrs, np.uint64).tolist() == [b.ctypes.data for b in blocks] and keep[0] is blocks[0]
+    keep, _, _ = _pointer_table([np.arange(6).reshape(2, 3)], np.float64, 3)          # int64 -> converted copy
+    assert keep[0].dtype == np.float64 and keep[0][1, 2] == 5.0
+    keep, _, _ = _pointer_table([np.zeros((4, 6))[:, ::2]], np.float64, 3)             # non-contiguous -> copy
+    assert keep[0].flags.c_contiguous
+    with pytest.raises(ValueError):
+        _pointer_table([np.zeros((4, 6))[:, ::2]], np.float64, 3, writable=True)
+    with pytest.raises(ValueError):
+        _pointer_table([np.zeros((4, 2))], np.float64, 3)
