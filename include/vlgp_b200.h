@@ -107,6 +107,13 @@ VLGP_API int vlgp_update_v(vlgp_ctx *ctx, int set_id, int *n_failed);
 /* n_fallback: number of per-neuron Newton systems that fell back to the gradient step (vlgp/core.py:194-198). */
 VLGP_API int vlgp_mstep(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double eps, double learning_rate,
                double da_bound, double db_bound, int *n_fallback);
+/* The same M-step split in two so that the host can drive the H-step while it runs: vem's M-step (vlgp/core.py:318-320)
+ * reads mu, v, y and writes a, b, noise; its H-step (:322-325) reads mu, w and writes sigma, omega -- independent given
+ * the E-step.  _begin enqueues the whole M-step on a second stream (and, with several ranks, a second communicator)
+ * and returns; _end waits for it.  Calls that touch what the M-step reads or writes wait for it by themselves. */
+VLGP_API int vlgp_mstep_begin(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double eps, double learning_rate,
+                     double da_bound, double db_bound);
+VLGP_API int vlgp_mstep_end(vlgp_ctx *ctx, int *n_fallback);
 
 /* ---- H-step objective: gp.construct_posterior_cov + gp.elbo (vlgp/gp.py:12-62,126-147) --------------------------- */
 /* Once per H-step (mu, w fixed during it): per-latent second moments of mu over the segments (all of length W). */

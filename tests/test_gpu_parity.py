@@ -479,6 +479,40 @@ def test_vem_shapes_vs_oracle(vl, N, L, window, big_counts):
     assert relerr(np.stack([s["v"] for s in segs]), np.stack([s["v"] for s in s_ref])) < tol
 
 
+def test_overlapped_m_and_h_step_is_bit_identical(vl):
+    """vem runs the M-step on a second stream under the H-step (independent given the E-step, vlgp/core.py:318-325):
+    the result must be bit-for-bit what the sequential order gives, and begin/end must behave when misused."""
+    from vlgp_b200 import core
+    from vlgp_b200.gp import make_cholesky
+    from vlgp_b200._lib import VlgpNativeError
+
+    out = []
+    for overlap in (True, False):
+        segs, params = _problem(77, 6, 200, 23, 3)
+        cfg = _cfg(max_iter=3, min_iter=3, Eniter=5, Mniter=6)
+        cfg["overlap_mh"] = overlap
+        make_cholesky(segs, params, cfg)
+        core.vem(segs, params, cfg)
+        out.append((params, np.stack([s["mu"] for s in segs]), np.stack([s["v"] for s in segs])))
+    (p1, mu1, v1), (p0, mu0, v0) = out
+    for k in ("a", "b", "noise", "da", "db", "omega", "sigma"):
+        assert np.array_equal(p1[k], p0[k]), k
+    assert np.array_equal(mu1, mu0) and np.array_equal(v1, v0)
+
+    segs, params = _problem(78, 2, 100, 8, 2)
+    with core.Session(segs, params) as s:
+        assert s.ts.mstep_end() == 0                       # nothing pending: a no-op
+        s.ts.mstep_begin(3)
+        with pytest.raises(VlgpNativeError):
+            s.ts.mstep_begin(3)                            # one at a time
+        a_dev = s.eng.pull_params({})["a"]                 # waits for the pending M-step by itself
+        assert s.ts.mstep_end() == 0
+        assert np.array_equal(a_dev, s.eng.pull_params({})["a"])
+        ref_segs, ref_params = _problem(78, 2, 100, 8, 2)
+        core.mstep(ref_segs, ref_params, _cfg(Mniter=3))
+        assert np.array_equal(a_dev, ref_params["a"])
+
+
 def test_errors_are_loud(vl):
     from vlgp_b200 import core
     from vlgp_b200._lib import VlgpNativeError

@@ -52,6 +52,8 @@ EXPORTS = {
     "vlgp_update_v": (C.c_int, [ctx_p, C.c_int, c_int_p]),
     "vlgp_mstep": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                              c_int_p]),
+    "vlgp_mstep_begin": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "vlgp_mstep_end": (C.c_int, [ctx_p, c_int_p]),
     "vlgp_hstep_prepare": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_hstep_objective": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int_p]),
     "vlgp_hstep_objective_batch": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i32_p, c_double_p, c_double_p, c_double_p,

@@ -12,6 +12,7 @@ library every function raises ``VlgpNativeError``.
 from __future__ import annotations
 
 import logging
+import os
 import time
 import weakref
 
@@ -326,6 +327,24 @@ def _em_iteration(s: Session, trials, params, config):
             logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
     t1 = time.perf_counter()
     _constrain_latent_dev(s, params, config)
+    if (config["Mniter"] >= 1 and config["Hstep"] and config.get("overlap_mh", True)
+            and not os.environ.get("VLGP_NO_OVERLAP")):
+        # The M-step (reads mu, v, y; writes a, b, noise) and the H-step (reads mu, w; writes sigma, omega) of one
+        # iteration are independent: the device works through the M-step on a second stream while the host drives
+        # the L-BFGS-B rounds of the H-step.  m_elapsed is then the host time the M-step cost on top of the H-step.
+        ts.mstep_begin(config["Mniter"], config["use_hessian"], config["eps"], config["learning_rate"],
+                       config["da_bound"], config["db_bound"])
+        tb = time.perf_counter()
+        try:
+            _hstep_dev(s, trials, params, config)
+        finally:
+            tc = time.perf_counter()
+            nfb = ts.mstep_end()
+        if nfb:
+            logger.error("M-step: %d Newton systems fell back to the gradient step", nfb)
+        s.eng.pull_params(params)
+        t3 = time.perf_counter()
+        return t1 - t0, (tb - t1) + (t3 - tc), tc - tb
     if config["Mniter"] >= 1:
         _mstep_dev(s, params, config)
     t2 = time.perf_counter()

@@ -10,6 +10,18 @@
 #include "common.cuh"
 #include "linalg.cuh"
 
+// An M-step begun with vlgp_mstep_begin may still be running on stream_m: calls that read or overwrite what it writes
+// (a, b, noise, da, db) or what it reads (mu, v, y) wait for it first.  vlgp_mstep_end still reports its counter.
+static int settle_mstep(vlgp_ctx *ctx) {
+    if (ctx->mstep_pending) CK(cudaStreamSynchronize(ctx->stream_m));
+    return VLGP_OK;
+}
+#define SETTLE()                          \
+    do {                                  \
+        int rs_ = settle_mstep(ctx);      \
+        if (rs_) return rs_;              \
+    } while (0)
+
 // kernels.cu files
 int vlgp_launch_ichol(vlgp_ctx *ctx, PriorFactor &pf, const double *d_omega, const double *d_sigma, double *d_work);
 int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter, double dmu_bound, int method_vb);
@@ -174,8 +186,15 @@ int vlgp_create(int device, vlgp_ctx **out) {
         delete ctx;
         return rc;
     }
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    // The overlapped M-step is the background job: its stream has the lowest priority so that the short kernels of the
+    // host-driven H-step rounds on the main stream are scheduled ahead of its queued CTAs.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&ctx->stream_m, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_m_start, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_m_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
@@ -206,6 +225,7 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     if (!ctx) return VLGP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream_m);
     vlgp_comm_destroy(ctx);
     for (auto &ts : ctx->sets)
         if (ts.used) free_set(ts, ctx->stream);
@@ -223,6 +243,8 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->pev0); cudaEventDestroy(ctx->pev1);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_m_start); cudaEventDestroy(ctx->ev_m_done);
+    cudaStreamDestroy(ctx->stream_m);
     cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -277,6 +299,7 @@ int vlgp_set_model(vlgp_ctx *ctx, int N, int L, int rank, const uint8_t *poisson
     REQUIRE(rank >= 1 && rank <= VLGP_MAX_RANK, "set_model: rank %d outside [1, %d]", rank, VLGP_MAX_RANK);
     REQUIRE(poisson_mask != nullptr, "set_model: poisson_mask is NULL");
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto &ts : ctx->sets)
         if (ts.used) free_set(ts, ctx->stream);
@@ -317,6 +340,7 @@ int vlgp_set_params(vlgp_ctx *ctx, const double *a, const double *b, const doubl
     REQUIRE(ctx->N > 0, "set_params before set_model");
     const size_t N = ctx->N, L = ctx->L;
     CK(cudaSetDevice(ctx->device));
+    if (a || b || noise) SETTLE();
     if (a) CK(cudaMemcpyAsync(ctx->d_a, a, L * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (b) CK(cudaMemcpyAsync(ctx->d_b, b, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (noise) CK(cudaMemcpyAsync(ctx->d_noise, noise, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -332,6 +356,7 @@ int vlgp_get_params(vlgp_ctx *ctx, double *a, double *b, double *noise, double *
     REQUIRE(ctx->N > 0, "get_params before set_model");
     const size_t N = ctx->N, L = ctx->L;
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     if (a) CK(cudaMemcpyAsync(a, ctx->d_a, L * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (da) CK(cudaMemcpyAsync(da, ctx->d_da, L * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (b) CK(cudaMemcpyAsync(b, ctx->d_b, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -431,6 +456,7 @@ int vlgp_trials_free(vlgp_ctx *ctx, int set_id) {
     TrialSet *ts = get_set(ctx, set_id);
     if (!ts) return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_free: bad set %d", set_id);
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     free_set(*ts, ctx->stream);
     return VLGP_OK;
 }
@@ -440,6 +466,7 @@ int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydtype) {
     REQUIRE(ts && y, "trials_set_y: bad set %d or NULL y", set_id);
     REQUIRE(ydtype == VLGP_Y_F64 || ydtype == VLGP_Y_U8, "trials_set_y: bad dtype %d", ydtype);
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     const size_t bytes = (size_t)ts->nbin * ctx->N * (ydtype == VLGP_Y_U8 ? 1 : sizeof(double));
     if (ts->d_y && ts->ydtype != ydtype) {
         CK(vlgp_dfree(ctx, ts->d_y));
@@ -462,6 +489,7 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
     REQUIRE(ts && parts && rows && n_parts >= 1, "trials_set_y_parts: bad arguments");
     REQUIRE(src_dtype == VLGP_Y_F64 || src_dtype == VLGP_Y_U8, "trials_set_y_parts: bad dtype %d", src_dtype);
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     const size_t N = ctx->N;
     int64_t total = 0;
     for (int i = 0; i < n_parts; ++i) total += rows[i];
@@ -670,6 +698,7 @@ static int state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, void *
     double *dev = state_array(ts, which);
     REQUIRE(dev != nullptr && (which != 3 || !to_device), "trials_state_parts: bad array selector %d", which);
     CK(cudaSetDevice(ctx->device));
+    if (to_device) SETTLE();
     std::vector<int64_t> off(n_parts + 1, 0);
     for (int i = 0; i < n_parts; ++i) off[i + 1] = off[i] + rows[i] * (int64_t)ctx->L;
     REQUIRE(off[n_parts] == ts->nbin * (int64_t)ctx->L, "trials_state_parts: blocks hold %lld rows, the set has %lld bins",
@@ -691,6 +720,7 @@ int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const dou
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts, "trials_set_state: bad set %d", set_id);
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     const size_t bytes = (size_t)ts->nbin * ctx->L * sizeof(double);
     if (mu) CK(cudaMemcpyAsync(ts->d_mu, mu, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (v) CK(cudaMemcpyAsync(ts->d_v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -703,6 +733,7 @@ int vlgp_trials_get_state(vlgp_ctx *ctx, int set_id, double *mu, double *v, doub
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts, "trials_get_state: bad set %d", set_id);
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     const size_t bytes = (size_t)ts->nbin * ctx->L * sizeof(double);
     if (mu) CK(cudaMemcpyAsync(mu, ts->d_mu, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (v) CK(cudaMemcpyAsync(v, ts->d_v, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -804,6 +835,7 @@ int vlgp_estep(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int meth
     if (n_failed) *n_failed = 0;
     if (n_iter < 1) return VLGP_OK;
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     {
         ProfScope ps(ctx, 0);
@@ -822,6 +854,7 @@ int vlgp_update_w(vlgp_ctx *ctx, int set_id) {
     int rc = check_ready(ctx, ts, "update_w");
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     rc = vlgp_launch_estep_generic(ctx, ts, 1, 1, 0.0, 0);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -833,6 +866,7 @@ int vlgp_update_v(vlgp_ctx *ctx, int set_id, int *n_failed) {
     int rc = check_ready(ctx, ts, "update_v");
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     rc = vlgp_launch_estep_generic(ctx, ts, 2, 1, 0.0, 1);
     if (rc) return rc;
@@ -849,9 +883,53 @@ int vlgp_mstep(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double ep
     if (n_fallback) *n_fallback = 0;
     if (n_iter < 1) return VLGP_OK;
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     CK(cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream));
     rc = vlgp_launch_mstep(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound);
     if (rc) return rc;
+    return read_flag(ctx, 1, n_fallback);
+}
+
+// The M-step on its own stream: everything vlgp_launch_mstep enqueues (statistics, reductions, allreduces, solves) goes
+// to stream_m behind an event that orders it after the E-step, so the host can drive the H-step on the main stream in
+// the meantime.  With several ranks the allreduces use the duplicate communicator comm_m (two streams must not share a
+// communicator); without one the M-step simply runs on the main stream here and vlgp_mstep_end has nothing to wait for.
+int vlgp_mstep_begin(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double eps, double lr, double da_bound,
+                     double db_bound) {
+    TrialSet *ts = get_set(ctx, set_id);
+    int rc = check_ready(ctx, ts, "mstep_begin");
+    if (rc) return rc;
+    REQUIRE(!ctx->mstep_pending, "mstep_begin: the previous M-step has not been ended");
+    if (n_iter < 1) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const bool aside = ctx->n_ranks <= 1 || ctx->comm_m != nullptr;
+    cudaStream_t main_stream = ctx->stream;
+    void *main_comm = ctx->comm;
+    if (aside) {
+        CK(cudaEventRecord(ctx->ev_m_start, main_stream));
+        CK(cudaStreamWaitEvent(ctx->stream_m, ctx->ev_m_start, 0));
+        ctx->stream = ctx->stream_m;
+        if (ctx->comm_m) ctx->comm = ctx->comm_m;
+    }
+    cudaError_t e = cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream);
+    rc = e == cudaSuccess ? vlgp_launch_mstep(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound)
+                          : vlgp_fail(ctx, VLGP_ERR_CUDA, "mstep_begin: %s", cudaGetErrorString(e));
+    if (aside && rc == VLGP_OK) e = cudaEventRecord(ctx->ev_m_done, ctx->stream_m);
+    ctx->stream = main_stream;
+    ctx->comm = main_comm;
+    if (rc) return rc;
+    if (e != cudaSuccess) return vlgp_fail(ctx, VLGP_ERR_CUDA, "mstep_begin: %s", cudaGetErrorString(e));
+    ctx->mstep_pending = true;
+    return VLGP_OK;
+}
+
+int vlgp_mstep_end(vlgp_ctx *ctx, int *n_fallback) {
+    if (!ctx) return VLGP_ERR_ARG;
+    if (n_fallback) *n_fallback = 0;
+    if (!ctx->mstep_pending) return VLGP_OK;
+    ctx->mstep_pending = false;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream_m));     // whatever the host enqueues from here on sees the new a, b, noise
     return read_flag(ctx, 1, n_fallback);
 }
 
@@ -902,6 +980,7 @@ int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const dou
     REQUIRE(ts, "latent_affine: bad set %d", set_id);
     if (!shift && !M) return VLGP_OK;
     CK(cudaSetDevice(ctx->device));
+    SETTLE();
     const int L = ctx->L;
     for (int l = 0; l < L; ++l) ctx->h_pin[l] = shift ? shift[l] : 0.0;
     for (int i = 0; i < L * L; ++i) ctx->h_pin[L + i] = M ? M[i] : 0.0;

@@ -18,6 +18,7 @@ struct NcclApi {
     int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm,
                      cudaStream_t s) = nullptr;
     int (*CommDestroy)(void *comm) = nullptr;
+    int (*CommSplit)(void *comm, int color, int key, void **newcomm, void *config) = nullptr;   // NCCL >= 2.18
     const char *(*GetErrorString)(int) = nullptr;
 };
 
@@ -36,6 +37,7 @@ static int load_nccl(vlgp_ctx *ctx, const char *path) {
     api->AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
     api->CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
     api->GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    api->CommSplit = (int (*)(void *, int, int, void **, void *))dlsym(h, "ncclCommSplit");     // optional
     if (!api->GetUniqueId || !api->CommInitRank || !api->AllReduce || !api->CommDestroy || !api->GetErrorString) {
         delete api;
         dlclose(h);
@@ -62,6 +64,8 @@ int vlgp_allreduce_dev(vlgp_ctx *ctx, double *d_buf, size_t n, int op) {
 }
 
 void vlgp_comm_destroy(vlgp_ctx *ctx) {
+    if (ctx->comm_m && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm_m);
+    ctx->comm_m = nullptr;
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
     ctx->comm = nullptr;
     if (ctx->nccl) {
@@ -100,6 +104,13 @@ int vlgp_comm_init(vlgp_ctx *ctx, const char *libnccl_path, int rank, int n_rank
     ctx->comm = comm;
     ctx->rank_id = rank;
     ctx->n_ranks = n_ranks;
+    // A duplicate communicator for the M-step stream (vlgp_mstep_begin), so that its allreduces can be in flight
+    // while the H-step's run on the main stream.  Every rank issues the operations of both in the same order.
+    if (ctx->nccl->CommSplit && !getenv("VLGP_NO_COMM_SPLIT")) {
+        void *dup = nullptr;
+        NCK(ctx->nccl->CommSplit(comm, 0, rank, &dup, nullptr));
+        ctx->comm_m = dup;
+    }
     return VLGP_OK;
 }
 

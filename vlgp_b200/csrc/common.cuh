@@ -52,6 +52,7 @@ struct TrialSet {
     double *d_hout = nullptr;          // MAX_L x 8 per-evaluation outputs + MAX_L x 2 reducible sums
     bool h_prepared = false;
     double h_nseg_total = 0.0;         // segments over all ranks
+    double nbin_all_ranks = 0.0;       // bins over all ranks (M-step divisor); 0 until the first M-step asked for it
     int h_seg_grid = 1;
     bool h_geometry = false;
     int dmma_grid = 0;                 // cached launch geometry of the DMMA segment kernel
@@ -72,6 +73,11 @@ struct vlgp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;              // side stream for the latency-bound K^-1 kernel of the H-step
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // The M-step reads only what the E-step left (mu, v, y, a, b) and the H-step only (mu, w): vlgp_mstep_begin puts
+    // the M-step on its own stream (and, with several ranks, its own communicator) so that the two overlap.
+    cudaStream_t stream_m = nullptr;
+    cudaEvent_t ev_m_start = nullptr, ev_m_done = nullptr;
+    bool mstep_pending = false;
     cudaDeviceProp prop{};
     std::string err;
     // model
@@ -98,6 +104,7 @@ struct vlgp_ctx {
     // comm
     NcclApi *nccl = nullptr;
     void *comm = nullptr;
+    void *comm_m = nullptr;      // ncclCommSplit duplicate of comm for the overlapped M-step (null: no overlap when n_ranks > 1)
     int rank_id = 0, n_ranks = 1;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -412,7 +412,9 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
 
     // total bin count over all ranks (the divisor of np.var / the Gaussian bias)
     double count = (double)ts->nbin;
-    if (ctx->n_ranks > 1) {
+    if (ctx->n_ranks > 1 && ts->nbin_all_ranks > 0.0) {
+        count = ts->nbin_all_ranks;
+    } else if (ctx->n_ranks > 1) {
         ctx->h_pin[0] = count;
         CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         int rc = vlgp_allreduce_dev(ctx, ctx->d_small, 1, 0);
@@ -420,6 +422,7 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_small, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         count = ctx->h_pin[0];
+        ts->nbin_all_ranks = count;
     }
 
     double *gshared = nullptr;

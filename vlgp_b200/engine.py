@@ -381,6 +381,18 @@ class TrialSet:
                                     float(da_bound), float(db_bound), C.byref(nf)), "mstep")
         return nf.value
 
+    def mstep_begin(self, n_iter, use_hessian=True, eps=1e-8, learning_rate=1.0, da_bound=5.0, db_bound=5.0):
+        """Enqueue the M-step on its own stream and return; ``mstep_end`` waits for it (H-step runs in between)."""
+        lib, ctx = self._lib()
+        self.eng._ck(lib.vlgp_mstep_begin(ctx, self.id, int(n_iter), int(bool(use_hessian)), float(eps),
+                                          float(learning_rate), float(da_bound), float(db_bound)), "mstep_begin")
+
+    def mstep_end(self):
+        lib, ctx = self._lib()
+        nf = C.c_int()
+        self.eng._ck(lib.vlgp_mstep_end(ctx, C.byref(nf)), "mstep_end")
+        return nf.value
+
     def hstep_prepare(self):
         lib, ctx = self._lib()
         self.eng._ck(lib.vlgp_hstep_prepare(ctx, self.id), "hstep_prepare")
