@@ -13,7 +13,10 @@
 // An M-step begun with vlgp_mstep_begin may still be running on stream_m: calls that read or overwrite what it writes
 // (a, b, noise, da, db) or what it reads (mu, v, y) wait for it first.  vlgp_mstep_end still reports its counter.
 static int settle_mstep(vlgp_ctx *ctx) {
-    if (ctx->mstep_pending) CK(cudaStreamSynchronize(ctx->stream_m));
+    if (!ctx->mstep_pending) return VLGP_OK;
+    int rc = vlgp_mstep_pump(ctx, 1 << 30);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream_m));
     return VLGP_OK;
 }
 #define SETTLE()                          \
@@ -28,6 +31,11 @@ int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter,
 int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled);
 int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
                       double da_bound, double db_bound);
+int vlgp_mstep_job_setup(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
+                         double da_bound, double db_bound);
+int vlgp_mstep_job_pump(vlgp_ctx *ctx, int max_iters);
+int vlgp_mstep_job_remaining(vlgp_ctx *ctx);
+void vlgp_mstep_job_free(vlgp_ctx *ctx);
 int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts);
 int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, double *ll, double *dll, int *info);
 void vlgp_comm_destroy(vlgp_ctx *ctx);
@@ -226,6 +234,7 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream_m);
+    vlgp_mstep_job_free(ctx);
     vlgp_comm_destroy(ctx);
     for (auto &ts : ctx->sets)
         if (ts.used) free_set(ts, ctx->stream);
@@ -890,10 +899,26 @@ int vlgp_mstep(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double ep
     return read_flag(ctx, 1, n_fallback);
 }
 
-// The M-step on its own stream: everything vlgp_launch_mstep enqueues (statistics, reductions, allreduces, solves) goes
-// to stream_m behind an event that orders it after the E-step, so the host can drive the H-step on the main stream in
-// the meantime.  With several ranks the allreduces use the duplicate communicator comm_m (two streams must not share a
-// communicator); without one the M-step simply runs on the main stream here and vlgp_mstep_end has nothing to wait for.
+// The M-step on its own stream: statistics, reductions, allreduces and solves go to stream_m behind an event that orders
+// them after the E-step, so the host can drive the H-step on the main stream in the meantime.  With several ranks the
+// allreduces use the duplicate communicator comm_m (two streams must not share a communicator); without one the
+// M-step simply runs on the main stream here and vlgp_mstep_end has nothing left to do.
+// Only the first Newton iteration is enqueued here; vlgp_mstep_pump adds the rest a few at a time from inside the
+// H-step objective calls (and vlgp_mstep_end / any call that needs the result adds whatever is left).
+struct StreamSwap {      // run a piece of host code with ctx->stream / ctx->comm pointing at the M-step's
+    vlgp_ctx *ctx;
+    cudaStream_t s;
+    void *c;
+    explicit StreamSwap(vlgp_ctx *x) : ctx(x), s(x->stream), c(x->comm) {
+        ctx->stream = ctx->stream_m;
+        if (ctx->comm_m) ctx->comm = ctx->comm_m;
+    }
+    ~StreamSwap() {
+        ctx->stream = s;
+        ctx->comm = c;
+    }
+};
+
 int vlgp_mstep_begin(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, double eps, double lr, double da_bound,
                      double db_bound) {
     TrialSet *ts = get_set(ctx, set_id);
@@ -902,34 +927,45 @@ int vlgp_mstep_begin(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, dou
     REQUIRE(!ctx->mstep_pending, "mstep_begin: the previous M-step has not been ended");
     if (n_iter < 1) return VLGP_OK;
     CK(cudaSetDevice(ctx->device));
-    const bool aside = ctx->n_ranks <= 1 || ctx->comm_m != nullptr;
-    cudaStream_t main_stream = ctx->stream;
-    void *main_comm = ctx->comm;
-    if (aside) {
-        CK(cudaEventRecord(ctx->ev_m_start, main_stream));
-        CK(cudaStreamWaitEvent(ctx->stream_m, ctx->ev_m_start, 0));
-        ctx->stream = ctx->stream_m;
-        if (ctx->comm_m) ctx->comm = ctx->comm_m;
+    if (ctx->n_ranks > 1 && !ctx->comm_m) {        // no second communicator: run it here, in order, on the main stream
+        CK(cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream));
+        rc = vlgp_launch_mstep(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound);
+        if (rc) return rc;
+        ctx->mstep_pending = true;
+        return VLGP_OK;
     }
-    cudaError_t e = cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream);
-    rc = e == cudaSuccess ? vlgp_launch_mstep(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound)
-                          : vlgp_fail(ctx, VLGP_ERR_CUDA, "mstep_begin: %s", cudaGetErrorString(e));
-    if (aside && rc == VLGP_OK) e = cudaEventRecord(ctx->ev_m_done, ctx->stream_m);
-    ctx->stream = main_stream;
-    ctx->comm = main_comm;
-    if (rc) return rc;
-    if (e != cudaSuccess) return vlgp_fail(ctx, VLGP_ERR_CUDA, "mstep_begin: %s", cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev_m_start, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream_m, ctx->ev_m_start, 0));
+    {
+        StreamSwap swap(ctx);
+        CK(cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream));
+        rc = vlgp_mstep_job_setup(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound);
+        if (rc) return rc;
+        rc = vlgp_mstep_job_pump(ctx, 1);
+        if (rc) return rc;
+    }
     ctx->mstep_pending = true;
     return VLGP_OK;
 }
+
+}   // extern "C"  (vlgp_mstep_pump is internal: C++ linkage, declared in common.cuh)
+
+int vlgp_mstep_pump(vlgp_ctx *ctx, int max_iters) {
+    if (!ctx->mstep_pending || vlgp_mstep_job_remaining(ctx) <= 0) return VLGP_OK;
+    StreamSwap swap(ctx);
+    return vlgp_mstep_job_pump(ctx, max_iters);
+}
+
+extern "C" {
 
 int vlgp_mstep_end(vlgp_ctx *ctx, int *n_fallback) {
     if (!ctx) return VLGP_ERR_ARG;
     if (n_fallback) *n_fallback = 0;
     if (!ctx->mstep_pending) return VLGP_OK;
-    ctx->mstep_pending = false;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream_m));     // whatever the host enqueues from here on sees the new a, b, noise
+    int rc = settle_mstep(ctx);      // enqueue what is left, wait: whatever the host enqueues from here on sees a, b, noise
+    ctx->mstep_pending = false;
+    if (rc) return rc;
     return read_flag(ctx, 1, n_fallback);
 }
 

@@ -78,6 +78,7 @@ struct vlgp_ctx {
     cudaStream_t stream_m = nullptr;
     cudaEvent_t ev_m_start = nullptr, ev_m_done = nullptr;
     bool mstep_pending = false;
+    void *mstep_job = nullptr;                   // MstepJob (mstep.cu): the M-step being enqueued piecewise
     cudaDeviceProp prop{};
     std::string err;
     // model
@@ -130,6 +131,9 @@ static inline cudaError_t vlgp_dfree(vlgp_ctx *ctx, T *p) {
     return p ? cudaFreeAsync((void *)p, ctx->stream) : cudaSuccess;
 }
 int vlgp_allreduce_dev(vlgp_ctx *ctx, double *d_buf, size_t n, int op);   // comm.cu; no-op when n_ranks == 1
+// capi.cu: enqueue up to max_iters further Newton iterations of a pending overlapped M-step (no-op otherwise); called
+// by the H-step objective between its launches and its synchronisation, where the host would otherwise idle.
+int vlgp_mstep_pump(vlgp_ctx *ctx, int max_iters);
 
 #define CK(call)                                                                                              \
     do {                                                                                                      \

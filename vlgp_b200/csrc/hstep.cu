@@ -292,6 +292,8 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->h_pin, ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
+    rc = vlgp_mstep_pump(ctx, 2);      // an overlapped M-step gets its next launches while this round runs
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     const double *o = ctx->h_pin, *r = ctx->h_pin + VLGP_MAX_L * 8;
     for (int e = 0; e < n; ++e) {

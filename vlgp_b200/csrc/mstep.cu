@@ -380,9 +380,22 @@ __global__ void mstep_solve_kernel(MsolveArgs p) {
     }
 }
 
+// One M-step as a resumable job: set-up once, then Newton iterations enqueued a few at a time (vlgp_mstep_job_pump), so
+// that an overlapped M-step's ~100 launches are issued while the host waits for H-step rounds instead of ahead of them.
+struct MstepJob {
+    MstatArgs sa{};
+    MsolveArgs so{};
+    dim3 grid;
+    int nt = 0, K = 0, KY = 0, LT = 0;
+    size_t smem = 0;
+    int64_t gx = 0;
+    double *ypart = nullptr;
+    int n_iter = 0, next_it = 0;
+};
+
 template <int LT>
-int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr, double da_bound,
-            double db_bound) {
+int mstep_setup_t(vlgp_ctx *ctx, TrialSet *ts, MstepJob &job, int n_iter, int use_hessian, double eps, double lr,
+                  double da_bound, double db_bound) {
     constexpr int NS = nstat_of(LT);
     constexpr int MAXT = (LT <= 5) ? 512 : 256;
     const int N = ctx->N;
@@ -454,31 +467,41 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
     so.a = ctx->d_a; so.b = ctx->d_b; so.noise = ctx->d_noise; so.da = ctx->d_da; so.db = ctx->d_db;
     so.use_hessian = use_hessian; so.eps = eps; so.lr = lr; so.da_bound = da_bound; so.db_bound = db_bound;
     so.flags = ctx->d_flags;
+    job.sa = sa; job.so = so;
+    job.grid = dim3((unsigned)gx, nchunk);
+    job.nt = nt; job.K = K; job.KY = KY; job.LT = LT; job.smem = smem; job.gx = gx; job.ypart = ypart;
+    job.n_iter = n_iter; job.next_it = 0;
+    return VLGP_OK;
+}
 
-    for (int it = 0; it < n_iter; ++it) {
-        sa.last = so.last = (it == n_iter - 1);
-        {
-            ProfScope ps(ctx, 1);
-            if (it == 0)
-                mstep_stats_kernel<LT, true><<<dim3((unsigned)gx, nchunk), nt, smem, ctx->stream>>>(sa);
-            else
-                mstep_stats_kernel<LT, false><<<dim3((unsigned)gx, nchunk), nt, smem, ctx->stream>>>(sa);
-            CKL();
-        }
-        int rc;
-        if (it == 0) {      // y-moments mu'y, sum y: once per M-step
-            reduce_parts_kernel<<<(KY + 127) / 128, 128, 0, ctx->stream>>>(ypart, (int)gx, KY, ctx->d_ymom);
-            CKL();
-            rc = vlgp_allreduce_dev(ctx, ctx->d_ymom, KY, 0);
-            if (rc) return rc;
-        }
-        reduce_parts_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_mpart, (int)gx, K, ctx->d_mstat);
-        CKL();
-        rc = vlgp_allreduce_dev(ctx, ctx->d_mstat, K, 0);
-        if (rc) return rc;
-        mstep_solve_kernel<LT><<<(N + 63) / 64, 64, 0, ctx->stream>>>(so);
+template <int LT>
+int mstep_iter_t(vlgp_ctx *ctx, MstepJob &job, int it) {
+    MstatArgs &sa = job.sa;
+    MsolveArgs &so = job.so;
+    const int K = job.K, KY = job.KY, N = so.N;
+    const int64_t gx = job.gx;
+    sa.last = so.last = (it == job.n_iter - 1);
+    {
+        ProfScope ps(ctx, 1);
+        if (it == 0)
+            mstep_stats_kernel<LT, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
+        else
+            mstep_stats_kernel<LT, false><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
         CKL();
     }
+    int rc;
+    if (it == 0) {      // y-moments mu'y, sum y: once per M-step
+        reduce_parts_kernel<<<(KY + 127) / 128, 128, 0, ctx->stream>>>(job.ypart, (int)gx, KY, ctx->d_ymom);
+        CKL();
+        rc = vlgp_allreduce_dev(ctx, ctx->d_ymom, KY, 0);
+        if (rc) return rc;
+    }
+    reduce_parts_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_mpart, (int)gx, K, ctx->d_mstat);
+    CKL();
+    rc = vlgp_allreduce_dev(ctx, ctx->d_mstat, K, 0);
+    if (rc) return rc;
+    mstep_solve_kernel<LT><<<(N + 63) / 64, 64, 0, ctx->stream>>>(so);
+    CKL();
     return VLGP_OK;
 }
 
@@ -501,9 +524,46 @@ int mstep_t(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps
         default: return vlgp_fail(ctx, VLGP_ERR_UNSUPPORTED, "n_latents %d > 12", L);  \
     }
 
+// Job state lives behind vlgp_ctx::mstep_job (one M-step at a time per context).
+static MstepJob *job_of(vlgp_ctx *ctx) {
+    if (!ctx->mstep_job) ctx->mstep_job = new MstepJob();
+    return (MstepJob *)ctx->mstep_job;
+}
+
+void vlgp_mstep_job_free(vlgp_ctx *ctx) {
+    delete (MstepJob *)ctx->mstep_job;
+    ctx->mstep_job = nullptr;
+}
+
+// Set-up on ctx->stream (grids, scratch, bin count over ranks, Gaussian-channel moments); enqueues no Newton iteration.
+int vlgp_mstep_job_setup(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
+                         double da_bound, double db_bound) {
+    MstepJob &job = *job_of(ctx);
+    int rc = VLGP_OK;
+    DISPATCH_L(ctx->L, rc = mstep_setup_t<LT>(ctx, ts, job, n_iter, use_hessian, eps, lr, da_bound, db_bound));
+    return rc;
+}
+
+int vlgp_mstep_job_remaining(vlgp_ctx *ctx) {
+    const MstepJob *job = (const MstepJob *)ctx->mstep_job;
+    return job ? job->n_iter - job->next_it : 0;
+}
+
+// Enqueue up to max_iters further Newton iterations on ctx->stream.
+int vlgp_mstep_job_pump(vlgp_ctx *ctx, int max_iters) {
+    MstepJob &job = *job_of(ctx);
+    for (int k = 0; k < max_iters && job.next_it < job.n_iter; ++k) {
+        int rc = VLGP_OK;
+        DISPATCH_L(job.LT, rc = mstep_iter_t<LT>(ctx, job, job.next_it));
+        if (rc) return rc;
+        job.next_it++;
+    }
+    return VLGP_OK;
+}
+
 int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
                       double da_bound, double db_bound) {
-    int rc = VLGP_OK;
-    DISPATCH_L(ctx->L, rc = mstep_t<LT>(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound));
-    return rc;
+    int rc = vlgp_mstep_job_setup(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound);
+    if (rc) return rc;
+    return vlgp_mstep_job_pump(ctx, n_iter);
 }
