@@ -479,6 +479,35 @@ def test_vem_shapes_vs_oracle(vl, N, L, window, big_counts):
     assert relerr(np.stack([s["v"] for s in segs]), np.stack([s["v"] for s in s_ref])) < tol
 
 
+def test_reference_api_smoke(vl):
+    """The reference's own API test (tests/test_api.py:4-38 there) with `import vlgp_b200 as vlgp`: integer counts from
+    np.random.poisson, an extra user key per trial, fit with every default, then transform on the fitted trials."""
+    import vlgp_b200 as vlgp
+
+    np.random.seed(3)
+    ydim, zdim, length, ntrial = 5, 2, 100, 5
+    a = np.random.randn(zdim, ydim)
+    trials = []
+    for i in range(ntrial):
+        z = np.column_stack((np.sin(np.linspace(0, 8 * np.pi, length)), np.cos(np.linspace(0, 8 * np.pi, length))))
+        trials.append({"y": np.random.poisson(np.exp(z @ a - 2)), "id": i})
+    result = vlgp.fit(trials, n_factors=2)
+    out, params, config = result["trials"], result["params"], result["config"]
+    assert out is trials and [t["id"] for t in out] == list(range(ntrial))
+    assert 5 <= config["runtime"]["it"] <= config["max_iter"]
+    for t in out:
+        assert t["y"].dtype.kind == "i"                      # the caller's array is not converted in place
+        for k in ("mu", "v", "w", "dmu"):
+            assert t[k].shape == (length, zdim) and np.isfinite(t[k]).all(), k
+        assert (t["v"] > 0).all() and (t["w"] > 0).all()
+    assert params["a"].shape == (zdim, ydim) and params["b"].shape == (1, ydim)
+    assert set(params["cholesky"]) == {length}
+    mu_fit = np.stack([t["mu"] for t in out])
+    vlgp.transform(out, params, config)                      # keeps mu as the starting point, 20 more E-iterations
+    mu_tr = np.stack([t["mu"] for t in out])
+    assert np.isfinite(mu_tr).all() and relerr(mu_tr, mu_fit) < 0.2
+
+
 def test_overlapped_m_and_h_step_is_bit_identical(vl):
     """vem runs the M-step on a second stream under the H-step (independent given the E-step, vlgp/core.py:318-325):
     the result must be bit-for-bit what the sequential order gives, and begin/end must behave when misused."""
