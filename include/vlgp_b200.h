@@ -145,6 +145,18 @@ VLGP_API int vlgp_comm_allreduce(vlgp_ctx *ctx, double *buf, int n, int op);
  * give every rank the posterior of every trial. */
 VLGP_API int vlgp_comm_allreduce_bulk(vlgp_ctx *ctx, double *buf, int64_t n);
 
+/* ---- host-side allreduce between the processes of one node (POSIX shared memory; no GPU involved) ------------------
+ * The scalars the HOST consumes every round -- (ll, dll) of each H-step objective evaluation for L-BFGS-B
+ * (vlgp/gp.py:107-114), the norms of vem's convergence test (vlgp/core.py:300-305,350-354) -- are summed over ranks here
+ * instead of through an NCCL launch + device round trip.  name: "/something", the same on every rank of the job; rank 0
+ * creates the segment.  op: 0 sum, 1 max; n <= 256.  Results are bit-identical on every rank (fixed rank order).
+ * vlgp_comm_attach_shm hands the handle to a context (which closes it on destroy): from then on vlgp_comm_allreduce,
+ * vlgp_norms, vlgp_latent_moments and the H-step objective use it; every rank must attach, or none. */
+VLGP_API int vlgp_shm_open(const char *name, int rank, int n_ranks, void **handle);
+VLGP_API int vlgp_shm_allreduce(void *handle, double *buf, int n, int op);
+VLGP_API int vlgp_shm_close(void *handle, int unlink_name);
+VLGP_API int vlgp_comm_attach_shm(vlgp_ctx *ctx, void *handle);
+
 /* ---- measurement helpers (used by bench.py only) ------------------------------------------------------------------ */
 /* Measured FP64 FMA peak (TFLOP/s) of this GPU with a register-resident DFMA loop, and with mma.sync.m8n8k4.f64. */
 VLGP_API int vlgp_peak_fp64(vlgp_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

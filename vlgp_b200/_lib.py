@@ -65,6 +65,10 @@ EXPORTS = {
     "vlgp_comm_init": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "vlgp_comm_allreduce": (C.c_int, [ctx_p, c_double_p, C.c_int, C.c_int]),
     "vlgp_comm_allreduce_bulk": (C.c_int, [ctx_p, c_double_p, C.c_int64]),
+    "vlgp_shm_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vlgp_shm_allreduce": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int]),
+    "vlgp_shm_close": (C.c_int, [C.c_void_p, C.c_int]),
+    "vlgp_comm_attach_shm": (C.c_int, [ctx_p, C.c_void_p]),
     "vlgp_peak_fp64": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "vlgp_peak_hbm": (C.c_int, [ctx_p, C.c_uint64, c_double_p]),
     "vlgp_flush_l2": (C.c_int, [ctx_p]),

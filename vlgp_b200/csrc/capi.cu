@@ -1040,11 +1040,15 @@ static int moments(vlgp_ctx *ctx, TrialSet *ts, std::vector<double> &out) {
     double *res = part + (size_t)grid * K;
     reduce_parts_kernel3<<<1, 64, 0, ctx->stream>>>(part, grid, K, res);
     CKL();
-    int rc = vlgp_allreduce_dev(ctx, res, K, 0);
+    int rc = ctx->shm ? VLGP_OK : vlgp_allreduce_dev(ctx, res, K, 0);
     if (rc) { vlgp_dfree(ctx, part); return rc; }
     CK(cudaMemcpyAsync(ctx->h_pin, res, K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     out.assign(ctx->h_pin, ctx->h_pin + K);
+    if (ctx->shm) {      // the host consumes these: sum them on the host
+        rc = vlgp_comm_allreduce(ctx, out.data(), K, 0);
+        if (rc) { vlgp_dfree(ctx, part); return rc; }
+    }
     CK(vlgp_dfree(ctx, part));
     return VLGP_OK;
 }

@@ -64,6 +64,8 @@ int vlgp_allreduce_dev(vlgp_ctx *ctx, double *d_buf, size_t n, int op) {
 }
 
 void vlgp_comm_destroy(vlgp_ctx *ctx) {
+    if (ctx->shm) vlgp_shm_close(ctx->shm, 0);
+    ctx->shm = nullptr;
     if (ctx->comm_m && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm_m);
     ctx->comm_m = nullptr;
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
@@ -118,6 +120,11 @@ int vlgp_comm_allreduce(vlgp_ctx *ctx, double *buf, int n, int op) {
     if (!ctx || !buf) return VLGP_ERR_ARG;
     REQUIRE(n >= 0 && n <= 256, "comm_allreduce: n %d outside [0, 256]", n);
     if (ctx->n_ranks <= 1 || n == 0) return VLGP_OK;
+    if (ctx->shm) {
+        if (vlgp_shm_allreduce(ctx->shm, buf, n, op) != VLGP_OK)
+            return vlgp_fail(ctx, VLGP_ERR_NCCL, "comm_allreduce: shared-memory allreduce timed out (a rank is gone or out of step)");
+        return VLGP_OK;
+    }
     CK(cudaSetDevice(ctx->device));
     double *stage = ctx->h_pin + 256;          // second half of the 4 KB pinned block
     double *dstage = ctx->d_small + 256;
@@ -128,6 +135,13 @@ int vlgp_comm_allreduce(vlgp_ctx *ctx, double *buf, int n, int op) {
     CK(cudaMemcpyAsync(stage, dstage, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     memcpy(buf, stage, n * sizeof(double));
+    return VLGP_OK;
+}
+
+int vlgp_comm_attach_shm(vlgp_ctx *ctx, void *handle) {
+    if (!ctx || !handle) return VLGP_ERR_ARG;
+    REQUIRE(ctx->shm == nullptr, "comm_attach_shm: a handle is already attached");
+    ctx->shm = handle;
     return VLGP_OK;
 }
 

@@ -106,6 +106,7 @@ struct vlgp_ctx {
     NcclApi *nccl = nullptr;
     void *comm = nullptr;
     void *comm_m = nullptr;      // ncclCommSplit duplicate of comm for the overlapped M-step (null: no overlap when n_ranks > 1)
+    void *shm = nullptr;         // host-side allreduce handle (shmcomm.cu) for the scalars the host consumes
     int rank_id = 0, n_ranks = 1;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

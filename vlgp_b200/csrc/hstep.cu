@@ -233,14 +233,19 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     if (rc) return rc;
     // number of segments over all ranks (the S of the log-determinant term)
     ctx->h_pin[0] = (double)S;
-    if (ctx->n_ranks > 1) {
+    if (ctx->n_ranks > 1 && !ctx->shm) {
         CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         rc = vlgp_allreduce_dev(ctx, ctx->d_small, 1, 0);
         if (rc) return rc;
         CK(cudaMemcpyAsync(ctx->h_pin, ctx->d_small, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    ts->h_nseg_total = ctx->h_pin[0];
+    double nseg_all = ctx->h_pin[0];
+    if (ctx->n_ranks > 1 && ctx->shm) {
+        rc = vlgp_comm_allreduce(ctx, &nseg_all, 1, 0);
+        if (rc) return rc;
+    }
+    ts->h_nseg_total = nseg_all;
     if (!ts->h_geometry) {
         // launch geometry of the per-segment fallback kernel (the DMMA kernel sizes its own grid), once per set
         int per_sm = 1;
@@ -288,13 +293,18 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
     if (dmma_ok) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     hstep_final_kernel<<<n, NT, 0, ctx->stream>>>(S, ts->d_hpart, red);
     CKL();
-    int rc = vlgp_allreduce_dev(ctx, red, 2 * n, 0);
+    // (tr, pd) sums over ranks: on the host through shared memory when attached (they are consumed there), else NCCL
+    int rc = ctx->shm ? VLGP_OK : vlgp_allreduce_dev(ctx, red, 2 * n, 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->h_pin, ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
     rc = vlgp_mstep_pump(ctx, 2);      // an overlapped M-step gets its next launches while this round runs
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->shm && ctx->n_ranks > 1) {
+        rc = vlgp_comm_allreduce(ctx, ctx->h_pin + VLGP_MAX_L * 8, 2 * n, 0);
+        if (rc) return rc;
+    }
     const double *o = ctx->h_pin, *r = ctx->h_pin + VLGP_MAX_L * 8;
     for (int e = 0; e < n; ++e) {
         const double *oe = o + e * 8;

@@ -49,7 +49,29 @@ def init_from_env(backend: str = "gloo"):
     box = [eng.comm_unique_id() if r == 0 else None]
     td.broadcast_object_list(box, src=0)
     eng.comm_init(r, world, box[0])
+    # One node, one process per GPU: scalars that end up on the host are reduced through shared memory (shmcomm.cu).
+    # The name is derived from the job's NCCL id, so concurrent jobs on a box do not collide.
+    if not os.environ.get("VLGP_NO_SHM") and _single_node(td, world):
+        import hashlib
+
+        name = "/vlgp_" + hashlib.sha1(box[0]).hexdigest()[:20]
+        eng.attach_host_allreduce(name)
+        td.barrier()                     # every rank has mapped the segment: the name can go
+        if r == 0:
+            try:
+                os.unlink("/dev/shm" + name)
+            except OSError:
+                pass
     return eng
+
+
+def _single_node(td, world):
+    """True when every rank of the job runs on this host (the shared-memory path needs that)."""
+    import socket
+
+    names = [None] * world
+    td.all_gather_object(names, socket.gethostname())
+    return len(set(names)) == 1
 
 
 def barrier():

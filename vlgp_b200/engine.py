@@ -191,6 +191,18 @@ class Engine:
                                              C.create_string_buffer(unique_id, 128)), "comm_init")
         self.world_size, self.rank_id = int(world_size), int(rank)
 
+    def attach_host_allreduce(self, name: str):
+        """Open the job's shared-memory segment (same ``name`` on every rank of the node) and hand it to the context:
+        host-consumed scalars (H-step objective values, norms) are then summed on the host instead of through NCCL."""
+        if self.world_size <= 1:
+            return
+        h = C.c_void_p()
+        rc = self.lib.vlgp_shm_open(name.encode(), self.rank_id, self.world_size, C.byref(h))
+        if rc:
+            raise _lib.VlgpNativeError("vlgp_shm_open(%s) failed with status %d" % (name, rc))
+        self._ck(self.lib.vlgp_comm_attach_shm(self.ctx, h), "comm_attach_shm")
+        self.host_allreduce = True
+
     def allreduce(self, x, op="sum"):
         """In-place allreduce of a small host array (<= 256 doubles per call; chunked here)."""
         a = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
