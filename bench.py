@@ -27,6 +27,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -100,6 +101,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    out_fd = _claim_stdout()
     from vlgp_b200.synth import CONFIGS
 
     c = CONFIGS[args.config]
@@ -121,7 +123,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
 
 
 def workload_config(name, c, gpus):
@@ -145,8 +147,41 @@ class ClockSampler:
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.nvml = []              # (sm MHz, max MHz, reasons bitmask) polled in-process every 10 ms
+        self._stop = threading.Event()
+        self._thr = None
+        self._armed = threading.Event()
+
+    def _poll(self):
+        # nvidia-smi needs up to a second to start and then reports every 50 ms: too coarse for a 100 ms timed region
+        # (8 GPUs).  NVML in a thread answers in ~50 us per query and releases the GIL while it does.
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                if self._armed.is_set():
+                    self.nvml.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx), int(reasons(h))))
+                self._stop.wait(0.01)
+        except Exception:      # noqa: BLE001 -- no NVML: the nvidia-smi samples remain
+            pass
+
+    def arm(self):
+        """Samples count from here (the sampler itself is started earlier so that it is up by now)."""
+        self._armed.set()
+        try:
+            self._mark = os.path.getsize(self.f.name)
+        except OSError:
+            self._mark = 0
 
     def start(self):
+        self._mark = 0
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
                                        "50", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
@@ -155,17 +190,25 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
         self.f.flush()
-        self.f.seek(0)
+        self.f.seek(self._mark)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for v, m, bits in self.nvml:
+            sm.append(v)
+            mx.append(m)
+            for nm, bit in zip(names, (0x8, 0x40, 0x20, 0x4)):
+                if bits & bit:
+                    reasons.add(nm)
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 9:
@@ -206,7 +249,22 @@ def estep_flops(S, W, N, L, ncols, n_iter, rank):
     return full, eff
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded below may print there on their own (NCCL announces
+    its version from C when a communicator is split): point file descriptor 1 at stderr for the rest of the process and
+    return a private duplicate of the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(fd, line):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def run_ours(args):
+    out_fd = _claim_stdout()
     from vlgp_b200 import core, dist
     from vlgp_b200.core import Session
     from vlgp_b200.gp import make_cholesky
@@ -249,14 +307,15 @@ def run_ours(args):
     stdout = sys.stdout
     sys.stdout = quiet
     try:
+        sampler = ClockSampler(eng.device)
+        sampler.start()                          # before the warm-up: nvidia-smi / NVML are up when the timed region starts
         for _ in range(args.warmup):
             step()
         eng.profile_enable(0x1)                  # E-step launches only: they end with a sync anyway
         c0 = eng.counters()
-        sampler = ClockSampler(eng.device)
-        sampler.start()                          # spawn nvidia-smi BEFORE the barrier: its start-up time differs per rank
         eng.sync()
         dist.barrier()
+        sampler.arm()                            # only samples from here on are reported
         eng.timer_start()
         t0 = time.perf_counter()
         split = np.zeros(3)
@@ -385,7 +444,7 @@ def run_ours(args):
                                 "sample": "%d of %d trials (%d segments), %.2f s per EM iteration measured with the "
                                           "NumPy/SciPy oracle, scaled linearly in segments" % (
                                               args.cpu_sample_trials, c["n_trials"], nseg, sec)}
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
 
 
 def main():
