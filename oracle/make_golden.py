@@ -253,13 +253,43 @@ def golden_fit_fixed_omega(ref):
     print("fit_fixed_omega.npz", len(out))
 
 
+VEM_OPTION_CASES = {
+    # name: (likelihood list or None, config overrides) -- the option branches of vem that the default fit never takes
+    "latent_both": (None, dict(constrain_latent="both")),
+    "loading_svd": (None, dict(constrain_loading="svd")),
+    "loading_row2_latent_location": (None, dict(constrain_loading=2, constrain_latent="location")),
+    "latent_scale_no_loading": (None, dict(constrain_loading="none", constrain_latent="scale")),
+    "gradient_step": (None, dict(use_hessian=False, learning_rate=1e-4)),
+    "map_no_hstep": (None, dict(method="MAP", Hstep=False)),
+    "mixed_lik": (["poisson"] * 6 + ["gaussian"] * 4, dict()),
+    "short_steps_tight_bounds": (None, dict(Eniter=3, Mniter=2, dmu_bound=0.05, da_bound=0.01, db_bound=0.02)),
+}
+
+
+def golden_vem_options(ref):
+    """Two vem iterations of the reference under the option branches listed above (vlgp/core.py:191-235,366-416)."""
+    out = {}
+    for name, (lik, kw) in VEM_OPTION_CASES.items():
+        segs, params, config = build_problem(ref, seed=11, n_trials=4, T=100, N=10, L=2, lik=lik, window=50,
+                                             max_iter=2, min_iter=2, **kw)
+        p = name + "/"
+        out[p + "y"] = np.stack([s["y"] for s in segs])
+        out[p + "poisson"] = params["likelihood"] == "poisson"
+        out.update(pack_state(p + "in_", segs, params))
+        ref.core.vem(segs, params, config)
+        out.update(pack_state(p + "out_", segs, params))
+        out[p + "n_it"] = np.array(config["runtime"]["it"])
+    np.savez_compressed(os.path.join(OUT, "vem_options.npz"), **out)
+    print("vem_options.npz", len(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
     import vlgp.preprocess, vlgp.core, vlgp.gp, vlgp.math, vlgp.util  # noqa: F401,E401
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
-               golden_fit_fixed_omega):
+               golden_fit_fixed_omega, golden_vem_options):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
 

@@ -186,3 +186,37 @@ def test_fit_fixed_omega_pipeline():
         assert relerr(np.stack([t[k] for t in trials]), g[k]) < 1e-9, k
     for k in ("a", "b", "noise"):
         assert relerr(params[k], g[k]) < 1e-9, k
+
+
+VEM_OPTION_CASES = {
+    "latent_both": dict(constrain_latent="both"),
+    "loading_svd": dict(constrain_loading="svd"),
+    "loading_row2_latent_location": dict(constrain_loading=2, constrain_latent="location"),
+    "latent_scale_no_loading": dict(constrain_loading="none", constrain_latent="scale"),
+    "gradient_step": dict(use_hessian=False, learning_rate=1e-4),
+    "map_no_hstep": dict(method="MAP", Hstep=False),
+    "mixed_lik": dict(),
+    "short_steps_tight_bounds": dict(Eniter=3, Mniter=2, dmu_bound=0.05, da_bound=0.01, db_bound=0.02),
+}
+
+
+@pytest.mark.parametrize("case", sorted(VEM_OPTION_CASES))
+def test_vem_option_branches(case):
+    """Two vem iterations of the reference under the options the default fit never takes: latent / loading
+    constraints (vlgp/core.py:366-416), gradient-step M-step (:194-198), MAP (no variance update), Gaussian channels,
+    active clipping bounds.  Same configuration table as oracle/make_golden.py::VEM_OPTION_CASES."""
+    g = load_golden("vem_options")
+    p = case + "/"
+    segs = _segs(g, p)
+    params = _params(g, p)
+    params["cholesky"] = orc.make_cholesky([50], params["omega"], params["sigma"], 50)
+    cfg = orc.default_config(max_iter=2, min_iter=2, **VEM_OPTION_CASES[case])
+    orc.vem(segs, params, cfg)
+    assert cfg["runtime"]["it"] == int(g[p + "n_it"])
+    hstep = cfg["Hstep"]
+    assert relerr(params["omega"], g[p + "out_omega"]) < (1e-6 if hstep else 1e-15)
+    tol = 1e-6 if hstep else 1e-9        # with the H-step the new prior factor depends on omega's last digits
+    for k in ("a", "b", "noise"):
+        assert relerr(params[k], g[p + "out_" + k]) < tol, k
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
