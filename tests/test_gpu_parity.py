@@ -479,6 +479,44 @@ def test_vem_shapes_vs_oracle(vl, N, L, window, big_counts):
     assert relerr(np.stack([s["v"] for s in segs]), np.stack([s["v"] for s in s_ref])) < tol
 
 
+VEM_OPTION_CASES = {
+    "latent_both": dict(constrain_latent="both"),
+    "loading_svd": dict(constrain_loading="svd"),
+    "loading_row2_latent_location": dict(constrain_loading=2, constrain_latent="location"),
+    "latent_scale_no_loading": dict(constrain_loading="none", constrain_latent="scale"),
+    "gradient_step": dict(use_hessian=False, learning_rate=1e-4),
+    "map_no_hstep": dict(method="MAP", Hstep=False),
+    "mixed_lik": dict(),
+    "short_steps_tight_bounds": dict(Eniter=3, Mniter=2, dmu_bound=0.05, da_bound=0.01, db_bound=0.02),
+}
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("VLGP_UNVERIFIED_TESTS"),
+                    reason="written after this round's GPU minutes were spent: run once with VLGP_UNVERIFIED_TESTS=1, "
+                           "then drop the guard")
+@pytest.mark.parametrize("case", sorted(VEM_OPTION_CASES))
+def test_vem_option_branches_golden(vl, case):
+    """Two vem iterations against the reference's outputs (tests/golden/vem_options.npz) under the options the default
+    fit never takes; the CPU suite pins the oracle to the same vectors (tests/test_oracle_golden.py)."""
+    from vlgp_b200 import core
+    from vlgp_b200.gp import make_cholesky
+
+    g = load_golden("vem_options")
+    p = case + "/"
+    segs = _segs(g, p)
+    params = _params(g, p)
+    cfg = _cfg(max_iter=2, min_iter=2, **VEM_OPTION_CASES[case])
+    make_cholesky(segs, params, cfg)
+    core.vem(segs, params, cfg)
+    assert cfg["runtime"]["it"] == int(g[p + "n_it"])
+    tol = 5e-4 if cfg["Hstep"] else 1e-8      # with the H-step: L-BFGS-B end point + pivot ties of the new factor (DESIGN.md 5)
+    assert relerr(params["omega"], g[p + "out_omega"]) < 1e-4
+    for k in ("a", "b"):
+        assert relerr(params[k], g[p + "out_" + k]) < tol, k
+    for k in ("mu", "v"):
+        assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
+
+
 def test_reference_api_smoke(vl):
     """The reference's own API test (tests/test_api.py:4-38 there) with `import vlgp_b200 as vlgp`: integer counts from
     np.random.poisson, an extra user key per trial, fit with every default, then transform on the fitted trials."""
