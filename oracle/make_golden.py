@@ -253,6 +253,29 @@ def golden_fit_fixed_omega(ref):
     print("fit_fixed_omega.npz", len(out))
 
 
+def golden_api_extras(ref):
+    """After fit(Hstep=False) on the tutorial-shaped problem: sample_posterior of the first trial (vlgp/api.py:142-168)
+    and transform of three NEW trials with the fitted model (vlgp/api.py:171-184)."""
+    out = {}
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    np.random.seed(0)
+    res = ref.fit(trials, 3, max_iter=3, min_iter=3, Hstep=False)
+    params, config = res["params"], res["config"]
+    np.random.seed(5)
+    out["samples"] = ref.sample_posterior(res["trials"][0], params, 4)
+    out["trial0_mu"] = res["trials"][0]["mu"].copy()
+    out["trial0_w"] = res["trials"][0]["w"].copy()
+    for k in ("omega", "sigma"):
+        out[k] = np.array(params[k])
+    new = make_trials(3, 200, 30, 3, seed=77)
+    out["new_y"] = np.stack([t["y"] for t in new]).astype(np.uint8)
+    ref.transform(new, params, config)
+    for k in ("mu", "v", "w"):
+        out["new_" + k] = np.stack([t[k] for t in new])
+    np.savez_compressed(os.path.join(OUT, "api_extras.npz"), **out)
+    print("api_extras.npz", len(out))
+
+
 VEM_OPTION_CASES = {
     # name: (likelihood list or None, config overrides) -- the option branches of vem that the default fit never takes
     "latent_both": (None, dict(constrain_latent="both")),
@@ -289,7 +312,7 @@ def main():
     import vlgp.preprocess, vlgp.core, vlgp.gp, vlgp.math, vlgp.util  # noqa: F401,E401
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
-               golden_fit_fixed_omega, golden_vem_options):
+               golden_fit_fixed_omega, golden_vem_options, golden_api_extras):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
 

@@ -275,8 +275,15 @@ def mstep(trials, params, config):
     a, b, noise, da, db = mstep_arrays(y, x, mu, v, params["a"], params["b"], poisson, config["Mniter"],
                                        config["use_hessian"], config["eps"], config["learning_rate"],
                                        config["da_bound"], config["db_bound"])
-    params["a"], params["b"], params["noise"] = a, b, noise
-    params["da"], params["db"] = da, db
+    # the reference works on the arrays stored in params (a, b, da, db are updated IN PLACE, vlgp/core.py:148-156,201,
+    # 219; noise is rebound, :177,244) -- observable through FactorAnalysis.transform, whose components_ IS params["a"]
+    for key, val in (("a", a), ("b", b), ("da", da), ("db", db)):
+        cur = params.get(key)
+        if isinstance(cur, np.ndarray) and cur.shape == val.shape and cur.dtype == val.dtype and cur.flags.writeable:
+            cur[...] = val
+        else:
+            params[key] = val
+    params["noise"] = noise
 
 
 # --------------------------------------------------------------------------------------------------------------------

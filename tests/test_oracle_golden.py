@@ -220,3 +220,51 @@ def test_vem_option_branches(case):
         assert relerr(params[k], g[p + "out_" + k]) < tol, k
     for k in ("mu", "v", "w"):
         assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
+
+
+def test_sample_posterior_matches_reference():
+    """api.sample_posterior is host-side NumPy in the reference and here: same seed,
+    same inputs, same draws (vlgp/api.py:142-168)."""
+    from vlgp_b200 import api
+
+    g = load_golden("api_extras")
+    params = {"cholesky": orc.make_cholesky([200], g["omega"], g["sigma"], 50)}
+    trial = {"mu": g["trial0_mu"], "w": g["trial0_w"]}
+    np.random.seed(5)
+    samples = api.sample_posterior(trial, params, 4)
+    assert samples.shape == g["samples"].shape == (4, 200, 3)
+    assert relerr(samples, g["samples"]) < 1e-9
+
+
+def test_transform_new_trials_pipeline():
+    """transform() on trials the model has not seen (vlgp/api.py:171-184): initialise through the fitted
+    FactorAnalysis map, then max_iter E-step iterations on the uncut trials -- restated with the host set-up of
+    vlgp_b200.preprocess and the oracle's E-step, against the reference's output."""
+    from vlgp_b200 import preprocess
+    from vlgp_b200.synth import make_trials
+    from vlgp_b200.util import cut_trials
+
+    g = load_golden("api_extras")
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    config = preprocess.get_config(max_iter=3, min_iter=3, Hstep=False)
+    params = preprocess.get_params(trials, 3, omega_bound=config["omega_bound"])
+    np.random.seed(0)
+    preprocess.initialize(trials, params, config)
+    preprocess.fill_params(params)
+    preprocess.fill_trials(trials)
+    params["cholesky"] = orc.make_cholesky([200], params["omega"], params["sigma"], 50)
+    orc.update_w(trials, params)
+    orc.update_v(trials, params, config)
+    segs = list(cut_trials(trials, params, config))
+    preprocess.fill_trials(segs)
+    params["cholesky"] = orc.make_cholesky([50], params["omega"], params["sigma"], 50)
+    orc.vem(segs, params, config)
+    params["cholesky"] = orc.make_cholesky([200], params["omega"], params["sigma"], 50)
+    # -- transform(new, params, config)
+    new = make_trials(3, 200, 30, 3, seed=77)
+    assert np.array_equal(np.stack([t["y"] for t in new]), g["new_y"])
+    preprocess.initialize(new, params, config)
+    preprocess.fill_trials(new)
+    orc.estep(new, params, config, n_iter=config["max_iter"])
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([t[k] for t in new]), g["new_" + k]) < 1e-9, k

@@ -19,6 +19,7 @@ import weakref
 import numpy as np
 
 from .engine import Engine, TrialSet, get_engine, pack_y
+from .util import assign_inplace
 
 __all__ = ["vem", "estep", "mstep", "hstep", "infer", "update_w", "update_v", "constrain_loading", "constrain_latent",
            "Session"]
@@ -263,11 +264,11 @@ def _constrain_loading_dev(s: Session, params, config):
         params["a"] = vt
     elif kind == "fro":
         sc = np.linalg.norm(a) + config["eps"]
-        params["a"] = a / sc
+        assign_inplace(params, "a", a / sc)        # in place like the reference (the "svd" branch rebinds there too)
         M = np.eye(L) * sc
     else:
         sc = np.linalg.norm(a, ord=kind, axis=1, keepdims=True) + config["eps"]
-        params["a"] = a / sc
+        assign_inplace(params, "a", a / sc)
         M = np.diag(sc[:, 0])
     s.eng.push_params(params, which=("a",))
     s.ts.latent_affine(None, M)
@@ -283,11 +284,12 @@ def _constrain_latent_dev(s: Session, params, config):
     shift, M = None, None
     if kind in ("location", "both"):
         shift = mean
-        params["b"] = np.array(params["b"], dtype=float)
-        params["b"][0, :] += mean @ params["a"]
+        b = np.array(params["b"], dtype=float)
+        b[0, :] += mean @ params["a"]
+        assign_inplace(params, "b", b)
     if kind in ("scale", "both"):
         M = np.diag(1.0 / std)
-        params["a"] = np.asarray(params["a"], dtype=float) * std[:, None]
+        assign_inplace(params, "a", np.asarray(params["a"], dtype=float) * std[:, None])
     s.eng.push_params(params, which=("a", "b"))
     s.ts.latent_affine(shift, M)
 

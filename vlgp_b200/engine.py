@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import VlgpNativeError, as_f64, dptr
+from .util import assign_inplace
 
 try:  # optional C helper for the pointer tables (host plumbing only); pure-Python fallback below
     from . import _fastpack
@@ -172,7 +173,11 @@ class Engine:
         self._ck(self.lib.vlgp_get_params(self.ctx, dptr(g("a")), dptr(g("b")), dptr(g("noise")), dptr(g("da")),
                                           dptr(g("db")), None, None), "get_params")
         for k, val in out.items():
-            params[k] = val.reshape(1, N) if k in ("b", "db") else val
+            val = val.reshape(1, N) if k in ("b", "db") else val
+            if k == "noise":
+                params[k] = val              # the reference rebinds noise (vlgp/core.py:177,244) ...
+            else:
+                assign_inplace(params, k, val)   # ... and updates a, b, da, db in place (:148-149,155-156,201,219)
         return params
 
     def new_trials(self, lengths) -> "TrialSet":

@@ -20,6 +20,24 @@ def clip(a, lbound, ubound=None):
     np.clip(a, lbound, ubound, out=a)
 
 
+def assign_inplace(d, key, value):
+    """``d[key] <- value`` keeping the IDENTITY of the array already stored there whenever it can hold the value.
+
+    The reference updates ``params["a"]`` and ``params["b"]`` in place all through ``vem`` (vlgp/core.py:148-149,201,
+    219,384-389,406-408), and that is observable: ``initialize`` binds ``params["a"]`` to the very array
+    ``FactorAnalysis.components_`` (vlgp/preprocess.py:20,27) and keeps the estimator's bound ``transform`` in
+    ``params["transform"]`` (:21), so the map a later ``transform()`` call applies to new trials uses the FITTED loading.
+    Rebinding the key instead would silently freeze that map at the FactorAnalysis solution."""
+    value = np.asarray(value, dtype=float)
+    cur = d.get(key)
+    if (isinstance(cur, np.ndarray) and cur.dtype == np.float64 and cur.shape == value.shape and cur.flags.writeable):
+        if cur is not value:
+            cur[...] = value
+    else:
+        d[key] = np.array(value, dtype=float)
+    return d[key]
+
+
 def window_starts(length: int, window: int):
     """Start bins of the ceil(length/window) windows covering a trial.  When the length is not a multiple of the
     window, the surplus is spread over the window boundaries by ONE draw of ``np.random.multinomial`` from the global
