@@ -276,6 +276,48 @@ def golden_api_extras(ref):
     print("api_extras.npz", len(out))
 
 
+def fit_option_cases():
+    """kwargs of fit() beyond the defaults (vlgp/preprocess.py:59-74,85-106); shared with tests/test_host_orchestration.py."""
+    rng = np.random.default_rng(5)
+    N, L = 12, 2
+    return N, L, {
+        "mixed_lik": dict(max_iter=2, min_iter=2, lik=["poisson"] * 8 + ["gaussian"] * 4),
+        "user_a_b": dict(max_iter=2, min_iter=2, a=0.4 * rng.standard_normal((L, N)), b=np.full((1, N), -2.0)),
+        "user_omega_sigma": dict(max_iter=2, min_iter=2, omega=np.array([0.01, 0.02]), sigma=np.array([0.8, 1.0])),
+        "latent_both_map": dict(max_iter=2, min_iter=2, constrain_latent="both", method="MAP"),
+        "loading_svd": dict(max_iter=2, min_iter=2, constrain_loading="svd"),
+        "tol_early_stop": dict(max_iter=6, min_iter=1, tol=1e-1),
+        "window25": dict(max_iter=2, min_iter=2, window=25),
+    }
+
+
+def fit_option_trials(N, L, kw):
+    trials = make_trials(4, 100, N, L, seed=9)
+    if "lik" in kw:
+        rng = np.random.default_rng(1)
+        for t in trials:
+            t["y"][:, 8:] = t["y"][:, 8:] + 0.3 * rng.standard_normal((100, 4))
+    return trials
+
+
+def golden_fit_options(ref):
+    """Whole fit() runs of the reference under non-default keyword arguments (small problem, T % window == 0)."""
+    out = {}
+    N, L, cases = fit_option_cases()
+    for name, kw in cases.items():
+        trials = fit_option_trials(N, L, kw)
+        np.random.seed(0)
+        res = ref.fit(trials, L, **copy.deepcopy(kw))
+        p = name + "/"
+        for k in ("mu", "v", "w"):
+            out[p + k] = np.stack([t[k] for t in res["trials"]])
+        for k in ("a", "b", "noise", "omega", "sigma"):
+            out[p + k] = np.array(res["params"][k])
+        out[p + "n_it"] = np.array(res["config"]["runtime"]["it"])
+    np.savez_compressed(os.path.join(OUT, "fit_options.npz"), **out)
+    print("fit_options.npz", len(out))
+
+
 VEM_OPTION_CASES = {
     # name: (likelihood list or None, config overrides) -- the option branches of vem that the default fit never takes
     "latent_both": (None, dict(constrain_latent="both")),
@@ -312,7 +354,8 @@ def main():
     import vlgp.preprocess, vlgp.core, vlgp.gp, vlgp.math, vlgp.util  # noqa: F401,E401
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
-               golden_fit_fixed_omega, golden_vem_options, golden_api_extras):
+               golden_fit_fixed_omega, golden_vem_options, golden_api_extras,
+               golden_fit_options):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
 

@@ -124,3 +124,39 @@ def test_vem_three_iterations_through_the_host_code(monkeypatch):
     for k in ("a", "b"):
         assert relerr(params[k], g["out_" + k]) < 1e-7, k
     assert relerr(np.stack([s["mu"] for s in segs]), g["out_mu"]) < 1e-6
+
+
+def _fit_option_cases():
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)            # defines the case table; touches the reference only inside main()
+    return mod
+
+
+@pytest.mark.parametrize("case", ["mixed_lik", "user_a_b", "user_omega_sigma", "latent_both_map", "loading_svd",
+                                  "tol_early_stop", "window25"])
+def test_fit_keyword_arguments_match_the_reference(monkeypatch, case):
+    """fit() under non-default keyword arguments -- mixed likelihoods, user-supplied loading / bias / GP
+    hyperparameters, latent constraint + MAP, the 'svd' loading constraint (which REBINDS every segment's mu in the
+    reference, so the trials keep their initial mu until the final infer), early stop on tol, another window -- through
+    the package's host code over the oracle stand-in, against whole-fit outputs of the reference."""
+    import vlgp_b200 as vlgp
+
+    mg = _fit_option_cases()
+    install(monkeypatch)
+    g = load_golden("fit_options")
+    N, L, cases = mg.fit_option_cases()
+    kw = cases[case]
+    trials = mg.fit_option_trials(N, L, kw)
+    np.random.seed(0)
+    res = vlgp.fit(trials, L, **copy.deepcopy(kw))
+    p = case + "/"
+    assert res["config"]["runtime"]["it"] == int(g[p + "n_it"])
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([t[k] for t in trials]), g[p + k]) < 1e-8, k
+    for k in ("a", "b", "noise", "omega", "sigma"):
+        assert relerr(res["params"][k], g[p + k]) < 1e-8, k

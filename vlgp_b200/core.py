@@ -122,14 +122,16 @@ class Session:
         params["cholesky"] = {int(t): self.ts.get_cholesky(int(t)) for t in sorted(set(self.ts.lengths.tolist()))}
         self.have_factors = True
 
-    def pull(self, trials, which=("mu", "v", "w", "dmu")):
+    def pull(self, trials, which=("mu", "v", "w", "dmu"), rebind=()):
         """Device state -> trial dicts with the reference's aliasing: mu and v are written IN PLACE (segment arrays are
-        views of their trial), w and dmu are rebound to fresh arrays (views of one new block per key)."""
+        views of their trial), w and dmu are rebound to fresh arrays (views of one new block per key).  Keys listed in
+        ``rebind`` are rebound as well: constrain_loading="svd" REPLACES every trial["mu"] (vlgp/core.py:404-405), so
+        from then on the segments' posterior means no longer reach the trials they were cut from."""
         L = self.eng.L
         fresh = {}
         for k in which:
             done = False
-            if k in ("mu", "v"):
+            if k in ("mu", "v") and k not in rebind:
                 try:      # in place when every trial already holds a writable C-contiguous float64 block of its shape
                     self.ts.get_state_parts(**{k: [tr[k] for tr in trials]})
                     done = True
@@ -142,7 +144,7 @@ class Session:
             cuts = [int(x) for x in self.ts.starts[1:]]
             for k, a in fresh.items():
                 views = np.split(a, cuts) if cuts else [a]
-                if k in ("mu", "v"):
+                if k in ("mu", "v") and k not in rebind:
                     for tr, val in zip(trials, views):
                         if isinstance(tr.get(k), np.ndarray) and tr[k].shape == val.shape:
                             tr[k][...] = val
@@ -294,6 +296,10 @@ def _constrain_latent_dev(s: Session, params, config):
     s.ts.latent_affine(shift, M)
 
 
+def _rebound_keys(config):
+    return ("mu",) if config["constrain_loading"] == "svd" else ()
+
+
 def constrain_loading(trials, params, config):
     """Normalise the loading matrix and rescale the latents accordingly."""
     kind = config["constrain_loading"]
@@ -301,7 +307,7 @@ def constrain_loading(trials, params, config):
         return
     with Session(trials, params, upload_factors=False) as s:
         _constrain_loading_dev(s, params, config)
-        s.pull(trials, ("mu",))
+        s.pull(trials, ("mu",), rebind=_rebound_keys(config))
 
 
 def constrain_latent(trials, params, config):
@@ -382,7 +388,7 @@ def vem(trials, params, config, session: Session = None):
             _echo("Iteration {:4d}, E-step {:.2f}s, M-step {:.2f}s".format(runtime["it"], te, tm))
 
             if callbacks:
-                s.pull(trials)              # callbacks see coherent host dicts
+                s.pull(trials, rebind=_rebound_keys(config))      # callbacks see coherent host dicts
                 for cb in callbacks:
                     try:
                         cb(trials, params, config)
@@ -394,7 +400,7 @@ def vem(trials, params, config, session: Session = None):
                          and np.linalg.norm(params["db"]) < tol * norm_b)
             if converged and it + 1 >= config["min_iter"]:
                 break
-        s.pull(trials)
+        s.pull(trials, rebind=_rebound_keys(config))
     finally:
         if own:
             s.close()
