@@ -318,6 +318,38 @@ def golden_fit_options(ref):
     print("fit_options.npz", len(out))
 
 
+def fit_overlap_trials():
+    """Unequal trial lengths that are not multiples of the window: overlapping, ALIASED segments (vlgp/util.py:482-498)."""
+    out = []
+    for i, T in enumerate((130, 175, 100, 262)):
+        out += make_trials(1, T, 14, 2, seed=40 + i)
+    return out
+
+
+FIT_OVERLAP_CASES = {
+    "default": dict(max_iter=3, min_iter=3),
+    "latent_both_no_hstep": dict(max_iter=3, min_iter=3, constrain_latent="both", Hstep=False),
+    "row_norm_loading": dict(max_iter=2, min_iter=2, constrain_loading=2),
+}
+
+
+def golden_fit_overlap(ref):
+    """Whole fit() of the reference on trials whose windows overlap, i.e. with its sequential, in-place updates of the
+    bins two segments share."""
+    out = {}
+    for name, kw in FIT_OVERLAP_CASES.items():
+        trials = fit_overlap_trials()
+        np.random.seed(0)
+        res = ref.fit(trials, 2, **copy.deepcopy(kw))
+        p = name + "/"
+        for k in ("mu", "v", "w"):
+            out[p + k] = np.concatenate([t[k] for t in res["trials"]])
+        for k in ("a", "b", "noise", "omega", "sigma"):
+            out[p + k] = np.array(res["params"][k])
+    np.savez_compressed(os.path.join(OUT, "fit_overlap.npz"), **out)
+    print("fit_overlap.npz", len(out))
+
+
 VEM_OPTION_CASES = {
     # name: (likelihood list or None, config overrides) -- the option branches of vem that the default fit never takes
     "latent_both": (None, dict(constrain_latent="both")),
@@ -355,7 +387,7 @@ def main():
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
                golden_fit_fixed_omega, golden_vem_options, golden_api_extras,
-               golden_fit_options):
+               golden_fit_options, golden_fit_overlap):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
 

@@ -168,14 +168,25 @@ class OracleTrialSet:
         return p
 
     # -- steps -----------------------------------------------------------------------------------------------------------
-    def estep(self, n_iter, dmu_bound=5.0, method="VB"):
-        self.eng.log.append(("estep", n_iter))
+    row_ops = True      # E-step over a subset of segments, row copies, affine map on selected rows (see core.py)
+
+    def estep(self, n_iter, dmu_bound=5.0, method="VB", subset=None):
+        self.eng.log.append(("estep", n_iter if subset is None else (n_iter, len(subset))))
         trials = self._trials()
-        trials = [dict(tr, **{k: tr[k].copy() for k in ("mu", "v", "w", "dmu")}) for tr in trials]
+        sel = range(len(trials)) if subset is None else [int(i) for i in subset]
+        work = [dict(trials[i], **{k: trials[i][k].copy() for k in ("mu", "v", "w", "dmu")}) for i in sel]
         cfg = orc.default_config(dmu_bound=dmu_bound, method=method, Eniter=n_iter)
-        orc.estep(trials, self._params(), cfg, n_iter=n_iter)
-        self._store(trials, ("mu", "v", "w", "dmu"))
+        orc.estep(work, self._params(), cfg, n_iter=n_iter)
+        for i, tr in zip(sel, work):
+            s, n = self.starts[i], self.lengths[i]
+            for k in ("mu", "v", "w", "dmu"):
+                self.state[k][s:s + n] = tr[k]
         return 0
+
+    def copy_rows(self, src, dst, which=("mu", "v")):
+        src, dst = np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64)
+        for k in which:
+            self.state[k][dst] = self.state[k][src]
 
     def update_w(self):
         self.eng.log.append(("update_w", None))
@@ -251,12 +262,15 @@ class OracleTrialSet:
         out = [self.hstep_objective(int(l), h) for l, h in zip(latents, np.asarray(hypers, dtype=float))]
         return (np.array([o[0] for o in out]), np.array([o[1] for o in out]), np.array([o[2] for o in out], np.int32))
 
-    def latent_affine(self, shift=None, M=None):
+    def latent_affine(self, shift=None, M=None, rows=None):
         mu = self.state["mu"]
+        idx = slice(None) if rows is None else np.asarray(rows, dtype=np.int64)
+        x = mu[idx]
         if shift is not None:
-            mu -= np.asarray(shift, dtype=float).reshape(1, -1)
+            x = x - np.asarray(shift, dtype=float).reshape(1, -1)
         if M is not None:
-            mu[...] = mu @ np.asarray(M, dtype=float)
+            x = x @ np.asarray(M, dtype=float)
+        mu[idx] = x
 
     def norms(self):
         return float(np.sum(self.state["mu"] ** 2)), float(np.sum(self.state["dmu"] ** 2))

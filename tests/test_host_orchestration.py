@@ -160,3 +160,24 @@ def test_fit_keyword_arguments_match_the_reference(monkeypatch, case):
         assert relerr(np.stack([t[k] for t in trials]), g[p + k]) < 1e-8, k
     for k in ("a", "b", "noise", "omega", "sigma"):
         assert relerr(res["params"][k], g[p + k]) < 1e-8, k
+
+
+@pytest.mark.parametrize("case", ["default", "latent_both_no_hstep", "row_norm_loading"])
+def test_fit_on_overlapping_aliased_windows_matches_the_reference(monkeypatch, case):
+    """Trial lengths that are not multiples of the window: the reference's segments are overlapping VIEWS, processed
+    in order with in-place updates of the shared bins.  core.py reproduces that exactly when the engine offers the
+    three row-level operations (_Aliasing); the oracle stand-in does, and the whole fit equals the reference's."""
+    import vlgp_b200 as vlgp
+
+    mg = _fit_option_cases()
+    eng = install(monkeypatch)
+    g = load_golden("fit_overlap")
+    trials = mg.fit_overlap_trials()
+    np.random.seed(0)
+    res = vlgp.fit(trials, 2, **copy.deepcopy(mg.FIT_OVERLAP_CASES[case]))
+    p = case + "/"
+    for k in ("a", "b", "noise", "omega", "sigma"):
+        assert relerr(res["params"][k], g[p + k]) < 1e-9, k
+    for k in ("mu", "v", "w"):
+        assert relerr(np.concatenate([t[k] for t in trials]), g[p + k]) < 1e-9, k
+    assert any(n == "estep" and isinstance(d, tuple) for n, d in eng.log)          # the level-by-level E-step ran

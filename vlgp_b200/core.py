@@ -67,6 +67,61 @@ def _check_regressors(trials):
             raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
 
 
+def _shared_rows(trials):
+    """Junctions between consecutive segments that are overlapping views of one trial (windows cut from a trial whose
+    length is not a multiple of the window, vlgp/util.py:482-498): list of (k, n) -- the last n rows of segment k ARE
+    the first n rows of segment k + 1 in the reference (one block of memory).  Found from the addresses of the mu
+    arrays, so it needs nothing beyond what cut_trials returns."""
+    out = []
+    for k in range(len(trials) - 1):
+        a, b = trials[k].get("mu"), trials[k + 1].get("mu")
+        if not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.ndim == 2 and b.ndim == 2):
+            continue
+        if not (a.dtype == np.float64 == b.dtype and a.flags.c_contiguous and b.flags.c_contiguous
+                and a.shape[1] == b.shape[1] and np.may_share_memory(a, b)):
+            continue
+        row = a.strides[0]
+        d = b.__array_interface__["data"][0] - a.__array_interface__["data"][0]
+        if d <= 0 or d % row:
+            continue
+        n = a.shape[0] - d // row
+        if 0 < n < min(a.shape[0], b.shape[0]):
+            out.append((k, int(n)))
+    return out
+
+
+class _Aliasing:
+    """Row bookkeeping that reproduces what the reference computes when segments share bins.  Every segment has its
+    own copy of its rows on the device; the reference has ONE copy of a shared row, processes the segments in list order
+    and updates mu / v in place (vlgp/core.py:96-97,112,123-126).  Hence:
+      * E-step: a segment starts from the mu, v its predecessor left on the shared rows -> segments are run level by
+        level along each chain of overlapping junctions (level = position in the chain), the predecessor's tail rows
+        being copied to the successor's head rows before its level runs; afterwards the successor's values are copied
+        back, so both copies hold what the reference's single row holds (the M- and H-step read them);
+      * constrain_loading / constrain_latent (vlgp/core.py:384-389,414-416) go through the segment list and rescale /
+        shift every segment's mu in place: a shared row gets the operation once per segment that contains it."""
+
+    def __init__(self, junctions, starts, lengths):
+        n_seg = len(lengths)
+        level = np.zeros(n_seg, dtype=np.int64)
+        succ = {k for k, _ in junctions}
+        for k, _ in junctions:
+            level[k + 1] = level[k] + 1
+        self.levels = [np.flatnonzero(level == lv) for lv in range(int(level.max()) + 1)]
+        self.fwd = []                  # per level >= 1: (src rows in the predecessors, dst rows in this level's segments)
+        tail, head = {}, {}
+        for k, n in junctions:
+            tail[k] = np.arange(starts[k] + lengths[k] - n, starts[k] + lengths[k])
+            head[k + 1] = np.arange(starts[k + 1], starts[k + 1] + n)
+        for lv in range(1, len(self.levels)):
+            segs = [int(i) for i in self.levels[lv]]
+            self.fwd.append((np.concatenate([tail[i - 1] for i in segs]), np.concatenate([head[i] for i in segs])))
+        ks = sorted(succ)
+        self.back_src = np.concatenate([head[k + 1] for k in ks])
+        self.back_dst = np.concatenate([tail[k] for k in ks])
+        self.shared = np.concatenate([self.back_src, self.back_dst])
+
+
 class Session:
     """Device copy of a list of trials plus the current parameters."""
 
@@ -93,6 +148,13 @@ class Session:
                 return [tr[key] if tr.get(key) is not None else np.zeros((n, L)) for tr, n in zip(trials, lengths)]
 
             self.ts.set_state_parts(mu=blocks("mu"), v=blocks("v"), w=blocks("w"))
+            # overlapping windows: exact reference semantics need three row-level device operations; without them the
+            # segments are treated as independent copies
+            self.alias = None
+            if getattr(self.ts, "row_ops", False):
+                junctions = _shared_rows(trials)
+                if junctions:
+                    self.alias = _Aliasing(junctions, self.ts.starts, self.ts.lengths)
             chol = params.get("cholesky") if upload_factors else None
             self.have_factors = False
             if chol:
@@ -181,7 +243,10 @@ def estep(trials, params, config, session=None):
         return
     with _with_session(trials, params, session) as s:
         s.require_factors()
-        nfail = s.ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+        if s.alias is None:
+            nfail = s.ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+        else:
+            nfail = _estep_aliased(s, config)
         if nfail:
             logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
         s.pull(trials)
@@ -274,6 +339,8 @@ def _constrain_loading_dev(s: Session, params, config):
         M = np.diag(sc[:, 0])
     s.eng.push_params(params, which=("a",))
     s.ts.latent_affine(None, M)
+    if s.alias is not None and kind != "svd":
+        s.ts.latent_affine(None, M, rows=s.alias.shared)          # a shared bin is rescaled once per segment holding it
 
 
 def _constrain_latent_dev(s: Session, params, config):
@@ -293,7 +360,15 @@ def _constrain_latent_dev(s: Session, params, config):
         M = np.diag(1.0 / std)
         assign_inplace(params, "a", np.asarray(params["a"], dtype=float) * std[:, None])
     s.eng.push_params(params, which=("a", "b"))
-    s.ts.latent_affine(shift, M)
+    if s.alias is None:
+        s.ts.latent_affine(shift, M)
+    else:       # the reference shifts every segment, then scales every segment: shared bins get each step twice
+        if shift is not None:
+            s.ts.latent_affine(shift, None)
+            s.ts.latent_affine(shift, None, rows=s.alias.shared)
+        if M is not None:
+            s.ts.latent_affine(None, M)
+            s.ts.latent_affine(None, M, rows=s.alias.shared)
 
 
 def _rebound_keys(config):
@@ -323,6 +398,19 @@ def constrain_latent(trials, params, config):
 # ----------------------------------------------------------------------------------------------------------------------
 # outer loop
 # ----------------------------------------------------------------------------------------------------------------------
+def _estep_aliased(s: Session, config):
+    """E-step over segments that share bins, in the reference's order of dependence (see _Aliasing)."""
+    ts, al = s.ts, s.alias
+    nfail = 0
+    for lv, segs in enumerate(al.levels):
+        if lv > 0:
+            src, dst = al.fwd[lv - 1]
+            ts.copy_rows(src, dst, which=("mu", "v"))
+        nfail += ts.estep(config["Eniter"], config["dmu_bound"], config["method"], subset=segs)
+    ts.copy_rows(al.back_src, al.back_dst, which=("mu", "v"))
+    return nfail
+
+
 def _em_iteration(s: Session, trials, params, config):
     """One EM iteration on a device session: constrain + E-step, constrain + M-step, H-step (vlgp/core.py:307-326).
     Returns (e_elapsed, m_elapsed, h_elapsed) wall-clock seconds; every stage ends with a device synchronisation."""
@@ -330,7 +418,10 @@ def _em_iteration(s: Session, trials, params, config):
     t0 = time.perf_counter()
     _constrain_loading_dev(s, params, config)
     if config["Eniter"] >= 1:
-        nfail = ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+        if s.alias is None:
+            nfail = ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
+        else:
+            nfail = _estep_aliased(s, config)
         if nfail:
             logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
     t1 = time.perf_counter()
