@@ -49,6 +49,8 @@ class _FakeEngine:
 
 
 class _FakeSession:
+    alias = None                    # no overlapping windows
+
     def __init__(self, mom=None):
         self.eng = _FakeEngine()
         self.ts = _FakeSet(mom)
