@@ -59,6 +59,35 @@ class OracleEngine:
     def sync(self):
         pass
 
+    # -- measurement entry points (bench.py): fixed stand-in values, only the FLOW is under test -----------------------
+    def peak_fp64(self):
+        return {"dfma_tflops": 30.0, "dmma_tflops": 35.0}
+
+    def peak_hbm(self, nbytes=1 << 30):
+        return 6000.0
+
+    def flush_l2(self):
+        pass
+
+    def timer_start(self):
+        import time
+
+        self._t0 = time.perf_counter()
+
+    def timer_stop(self):
+        import time
+
+        return (time.perf_counter() - self._t0) * 1e3
+
+    def counters(self):
+        return {"launches": len(self.log), "estep_solves": 0, "hstep_evals": 0, "allreduces": 0}
+
+    def profile_enable(self, mask=0xF):
+        self._prof = mask
+
+    def profile_get(self, which):
+        return 1.0, 1
+
     def oracle_params(self):
         p = dict(self.params)
         p.update(zdim=self.L, ydim=self.N, xdim=1, rank=self.rank, gp_noise=self.gp_noise, dt=self.dt,

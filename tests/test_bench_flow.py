@@ -1,0 +1,54 @@
+"""bench.py's own arm needs a GPU; its FLOW does not.  With the oracle stand-in as the engine (tests/oracle_engine.py)
+the whole of run_ours -- problem set-up, warm-up, timed loop, clock sampler, the extra profiling iteration, the
+end-to-end arm, the JSON assembly -- runs on the CPU in a child process, and what arrives on the child's stdout must be
+exactly ONE line of JSON with the keys of the contract (numbers are meaningless here; only their presence is checked)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DRIVER = r"""
+import sys, types
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import oracle_engine, vlgp_b200.engine as engine_mod
+engine_mod._ENGINE = oracle_engine.OracleEngine()
+print("a library chatting on stdout before the benchmark starts is the caller's problem")   # before _claim_stdout
+import bench
+args = types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="ours", config="tiny", cpu_sample_trials=1, no_cpu=True)
+from vlgp_b200 import synth
+synth.CONFIGS["tiny"] = dict(n_trials=2, T=100, N=6, L=2, dtype="f64")
+import os as _os
+# a C-level write to fd 1 during the run (what NCCL does when it announces its version) must not reach stdout
+real_claim = bench._claim_stdout
+def claim_then_chat():
+    fd = real_claim()
+    _os.write(1, b"NCCL version 9.9.9+fake\n")
+    return fd
+bench._claim_stdout = claim_then_chat
+bench.run_ours(args)
+"""
+
+
+def test_run_ours_prints_exactly_one_json_line_with_the_contract_keys(tmp_path):
+    script = tmp_path / "drive_bench.py"
+    script.write_text(DRIVER.format(root=ROOT, tests=os.path.join(ROOT, "tests")))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    # the first line was printed by the driver before bench took stdout over; after that: the JSON line and nothing else
+    assert len(lines) == 2 and lines[0].startswith("a library chatting"), lines
+    assert "NCCL version 9.9.9+fake" in r.stderr and "NCCL version" not in r.stdout.split("\n", 1)[1]
+    d = json.loads(lines[1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "clocks", "gpu_launches", "split_ms"):
+        assert k in d, k
+    assert d["metric"] == "EM-iterations/sec" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["e2e"]["value"] > 0
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}        # no GPU here: the values are None
+    assert "workload" in d["config"] and "cpu_baseline" not in d            # --no-cpu
