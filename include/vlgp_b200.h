@@ -100,6 +100,16 @@ VLGP_API int vlgp_set_cholesky(vlgp_ctx *ctx, int set_id, int length, const doub
 /* n_failed: number of (trial, latent, iteration) r x r systems that were not positive definite (their update is
  * skipped exactly like the reference's except-branches, vlgp/core.py:92-94,112). */
 VLGP_API int vlgp_estep(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, int *n_failed);
+/* The same on n_segments listed members of the set only (each index once; the others are untouched).  With the two
+ * row operations below it reproduces the reference's E-step on OVERLAPPING windows, whose segments are views of one
+ * trial that are updated in place one after the other (vlgp/util.py:482-498, vlgp/core.py:96-97,112,123-126): the host
+ * runs the segments level by level along each chain of overlapping windows (vlgp_b200/core.py::_Aliasing). */
+VLGP_API int vlgp_estep_subset(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb,
+                               const int32_t *segments, int n_segments, int *n_failed);
+/* For i < n: bin dst[i] <- bin src[i] in the per-bin arrays selected by which_mask (bit 0 mu, 1 v, 2 w, 3 dmu); bins
+ * are indices into the set's concatenated bins.  No bin may be written twice or be both read and written. */
+VLGP_API int vlgp_trials_copy_rows(vlgp_ctx *ctx, int set_id, int which_mask, const int64_t *src, const int64_t *dst,
+                                   int64_t n);
 VLGP_API int vlgp_update_w(vlgp_ctx *ctx, int set_id);
 VLGP_API int vlgp_update_v(vlgp_ctx *ctx, int set_id, int *n_failed);
 
@@ -131,6 +141,11 @@ VLGP_API int vlgp_hstep_objective_batch(vlgp_ctx *ctx, int set_id, int n, const 
 /* ---- constraints and convergence bookkeeping (vlgp/core.py:300-305,350-354,366-416) ------------------------------ */
 /* mu <- (mu - shift) @ M for every bin; shift (L) and M (L x L, row-major) may be NULL (0 / identity). */
 VLGP_API int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M);
+/* The same map on the n_rows listed bins only (each once): the reference's constrain_loading / constrain_latent walk the
+ * segment list and rescale every segment's mu in place (vlgp/core.py:384-389,414-416), so a bin shared by two
+ * overlapping windows is mapped once per window holding it. */
+VLGP_API int vlgp_latent_affine_rows(vlgp_ctx *ctx, int set_id, const double *shift, const double *M,
+                                     const int64_t *rows, int64_t n_rows);
 /* out[0] = sum mu^2, out[1] = sum dmu^2 over all bins and latents (summed over ranks when a communicator is set). */
 VLGP_API int vlgp_norms(vlgp_ctx *ctx, int set_id, double out[2]);
 /* Per-latent sum(mu), sum(mu^2) and the bin count (summed over ranks when a communicator is set). */

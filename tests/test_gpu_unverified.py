@@ -1,0 +1,232 @@
+"""GPU tests of device code written AFTER this round's GPU minutes were spent.
+
+Everything here compiles and is exercised on the CPU as far as the host side goes, but has never run on a GPU, so it is
+kept off the default product path (opt-in environment switches) and off the default GPU suite:
+
+  * the tests below marked ``unverified`` run in-process only with VLGP_UNVERIFIED_TESTS=1;
+  * ``test_unverified_device_code_in_a_child_process`` (always part of ``-m gpu``) runs exactly those tests -- and the
+    guarded ones of tests/test_gpu_parity.py -- in a CHILD interpreter, so that a fault in unverified kernels cannot take
+    the CUDA context of the verified suite with it.  It passes when the child passes and reports an expected failure
+    (with the tail of the child's log; full log under gpurun_out/) when it does not: the verified suite stays green and
+    the outcome is still recorded.  Once they have passed on a B200: drop the guards, make the switches default.
+
+Covered: the three row-level operations behind the reference's in-place semantics of OVERLAPPING windows
+(vlgp_estep_subset, vlgp_trials_copy_rows, vlgp_latent_affine_rows; vlgp/util.py:482-498, vlgp/core.py:96-97,112,
+123-126,384-389,414-416) and whole fits through them against the reference's own outputs (tests/golden/fit_overlap.npz).
+"""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+unverified = pytest.mark.skipif(not os.environ.get("VLGP_UNVERIFIED_TESTS"),
+                                reason="not yet run on a GPU: VLGP_UNVERIFIED_TESTS=1 (run in a child process by "
+                                       "test_unverified_device_code_in_a_child_process)")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from vlgp_b200 import engine
+
+    return engine.get_engine()        # fails loudly if the native library / GPU is missing
+
+
+def _model(eng, N, L, rng, omega=None):
+    params = dict(a=0.4 * rng.standard_normal((L, N)), b=np.full((1, N), np.log(0.1)), noise=np.ones(N),
+                  omega=np.full(L, 5e-3) if omega is None else np.asarray(omega, dtype=float), sigma=np.ones(L),
+                  likelihood=np.array(["poisson"] * N), zdim=L, ydim=N, xdim=1, rank=50, gp_noise=1e-4, dt=1)
+    eng.ensure_model(params)
+    eng.push_params(params)
+    return params
+
+
+def _filled_set(eng, rng, lengths, N, L):
+    ts = eng.new_trials(lengths)
+    nbin = int(np.sum(lengths))
+    ts.set_y(rng.poisson(0.2, size=(nbin, N)).astype(float))
+    mu = 0.3 * rng.standard_normal((nbin, L))
+    ts.set_state(mu=mu, v=np.zeros((nbin, L)), w=np.zeros((nbin, L)))
+    ts.make_cholesky()
+    ts.update_w()
+    ts.update_v()
+    return ts
+
+
+@unverified
+@pytest.mark.parametrize("lengths", [[50] * 23, [50, 120, 64, 200, 50, 77]], ids=["segments", "ragged"])
+def test_estep_subset_touches_only_the_listed_members(eng, lengths):
+    """estep(subset=s) gives, on the listed members, bit for bit what the E-step over the whole set gives (members are
+    independent), and leaves every other member untouched -- both through the SMEM-resident segment kernel (equal
+    lengths <= 64) and through the any-length kernel."""
+    rng = np.random.default_rng(5)
+    N, L = 17, 3
+    _model(eng, N, L, rng, omega=[5e-3, 1e-2, 2e-3])
+    with _filled_set(eng, np.random.default_rng(6), lengths, N, L) as full, \
+            _filled_set(eng, np.random.default_rng(6), lengths, N, L) as part:
+        before = part.get_state()
+        full.estep(4, 5.0, "VB")
+        ref = full.get_state()
+        subset = np.array([len(lengths) - 1, 0, 3], dtype=np.int32)     # unordered on purpose
+        assert part.estep(4, 5.0, "VB", subset=subset) == 0
+        got = part.get_state()
+        listed = np.zeros(part.nbin, dtype=bool)
+        for i in subset:
+            listed[part.starts[i]:part.starts[i] + part.lengths[i]] = True
+        for k in ("mu", "v", "w", "dmu"):
+            assert np.array_equal(got[k][listed], ref[k][listed]), k
+            assert np.array_equal(got[k][~listed], before[k][~listed]), k
+        assert not np.array_equal(got["mu"][listed], before["mu"][listed])
+        # the rest in a second call: together the two calls equal the full E-step
+        rest = np.setdiff1d(np.arange(len(lengths)), subset).astype(np.int32)
+        part.estep(4, 5.0, "VB", subset=rest)
+        got = part.get_state()
+        for k in ("mu", "v", "w", "dmu"):
+            assert np.array_equal(got[k], ref[k]), k
+
+
+@unverified
+def test_row_operations_argument_errors(eng):
+    from vlgp_b200._lib import VlgpNativeError
+
+    rng = np.random.default_rng(1)
+    _model(eng, 6, 2, rng)
+    with _filled_set(eng, rng, [50, 50, 50], 6, 2) as ts:
+        for bad in ([0, 0], [3], [-1]):
+            with pytest.raises(VlgpNativeError):
+                ts.estep(1, 5.0, "VB", subset=bad)
+        assert ts.estep(1, 5.0, "VB", subset=[]) == 0
+        for src, dst in (([0, 1], [5, 5]), ([0, 1], [1, 7]), ([0], [150]), ([150], [0])):
+            with pytest.raises(VlgpNativeError):
+                ts.copy_rows(src, dst)
+        with pytest.raises(VlgpNativeError):
+            ts.latent_affine(np.ones(2), None, rows=[4, 4])
+        with pytest.raises(VlgpNativeError):
+            ts.latent_affine(np.ones(2), None, rows=[150])
+        ts.copy_rows([], [])
+        ts.latent_affine(np.ones(2), None, rows=[])
+
+
+@unverified
+def test_copy_rows_and_affine_rows_against_numpy(eng):
+    rng = np.random.default_rng(2)
+    N, L = 9, 4
+    _model(eng, N, L, rng)
+    with _filled_set(eng, rng, [50] * 7, N, L) as ts:
+        st = ts.get_state()
+        src = np.array([45, 46, 47, 48, 49, 149, 148], dtype=np.int64)
+        dst = np.array([50, 51, 52, 53, 54, 150, 151], dtype=np.int64)
+        ts.copy_rows(src, dst, which=("mu", "v"))
+        got = ts.get_state()
+        for k in ("mu", "v"):
+            exp = st[k].copy()
+            exp[dst] = st[k][src]
+            assert np.array_equal(got[k], exp), k
+        for k in ("w", "dmu"):
+            assert np.array_equal(got[k], st[k]), k
+        ts.copy_rows(src, dst, which=("w", "dmu"))
+        got2 = ts.get_state()
+        for k in ("w", "dmu"):
+            exp = st[k].copy()
+            exp[dst] = st[k][src]
+            assert np.array_equal(got2[k], exp), k
+        # affine map on listed bins: shift then matrix, exactly the full-set kernel's arithmetic
+        rows = np.array([3, 349, 120, 121], dtype=np.int64)
+        shift = rng.standard_normal(L)
+        M = np.diag(rng.uniform(0.5, 2.0, L))
+        mu0 = got2["mu"].copy()
+        ts.latent_affine(shift, M, rows=rows)
+        mu1 = ts.get_state(("mu",))["mu"]
+        exp = mu0.copy()
+        exp[rows] = (mu0[rows] - shift) * np.diag(M)          # diagonal M: one rounding per entry on both sides
+        assert np.array_equal(mu1, exp)
+        Mfull = rng.standard_normal((L, L))
+        ts.latent_affine(None, Mfull, rows=rows)
+        mu2 = ts.get_state(("mu",))["mu"]
+        exp2 = exp.copy()
+        exp2[rows] = exp[rows] @ Mfull
+        assert relerr(mu2, exp2) < 1e-14
+        other = np.setdiff1d(np.arange(ts.nbin), rows)
+        assert np.array_equal(mu2[other], mu0[other])
+
+
+def _make_golden_module():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "oracle", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)            # the case tables; the reference is only touched inside its main()
+    return mod
+
+
+@unverified
+@pytest.mark.parametrize("case", ["latent_both_no_hstep", "row_norm_loading", "default"])
+def test_fit_on_overlapping_aliased_windows_matches_the_reference(eng, monkeypatch, case):
+    """Whole fit() on trial lengths 130 / 175 / 100 / 262 (windows overlap) against the REFERENCE's own outputs, with the
+    device row operations switched on.  CPU twin: tests/test_host_orchestration.py (same host code over the oracle)."""
+    import vlgp_b200 as vlgp
+
+    monkeypatch.setenv("VLGP_ALIASED_WINDOWS", "1")
+    mg = _make_golden_module()
+    g = load_golden("fit_overlap")
+    trials = mg.fit_overlap_trials()
+    np.random.seed(0)
+    kw = copy.deepcopy(mg.FIT_OVERLAP_CASES[case])
+    res = vlgp.fit(trials, 2, **kw)
+    p = case + "/"
+    # without the H-step omega is fixed and so are the prior factors; with it: L-BFGS-B end point + pivot ties
+    # (DESIGN.md section 5), the same allowance as the other whole-fit tests with the H-step on
+    tol = 1e-7 if kw.get("Hstep", True) is False else 5e-4
+    assert relerr(res["params"]["omega"], g[p + "omega"]) < (1e-12 if tol == 1e-7 else 1e-4)
+    for k in ("a", "b", "noise", "sigma"):
+        assert relerr(res["params"][k], g[p + k]) < tol, k
+    for k in ("mu", "v", "w"):
+        assert relerr(np.concatenate([t[k] for t in trials]), g[p + k]) < tol, k
+
+
+@unverified
+def test_dealiased_run_differs_from_the_reference(eng, monkeypatch):
+    """The switch matters: with independent copies of the shared bins the same fit is percent-level off the reference
+     -- guards against the aliased path silently not being taken in the test above."""
+    import vlgp_b200 as vlgp
+
+    monkeypatch.delenv("VLGP_ALIASED_WINDOWS", raising=False)
+    mg = _make_golden_module()
+    g = load_golden("fit_overlap")
+    trials = mg.fit_overlap_trials()
+    np.random.seed(0)
+    vlgp.fit(trials, 2, **copy.deepcopy(mg.FIT_OVERLAP_CASES["latent_both_no_hstep"]))
+    assert relerr(np.concatenate([t["mu"] for t in trials]), g["latent_both_no_hstep/mu"]) > 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def test_unverified_device_code_in_a_child_process():
+    if os.environ.get("VLGP_UNVERIFIED_TESTS"):
+        pytest.skip("already running the guarded tests in this process")
+    env = dict(os.environ, VLGP_UNVERIFIED_TESTS="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_unverified.py"),
+           os.path.join(ROOT, "tests", "test_gpu_parity.py"),
+           "-k", "subset or row_operations or copy_rows or aliased or dealiased or option_branches_golden or "
+                 "transform_new_trials_golden"]
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        out, code = r.stdout + "\n" + r.stderr, r.returncode
+    except subprocess.TimeoutExpired as e:
+        out, code = "TIMEOUT after 900 s\n%s" % (e.stdout or ""), -1
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "unverified_tests.log"), "w") as f:
+            f.write(out)
+    except OSError:
+        pass
+    print(out[-4000:])
+    if code != 0:
+        pytest.xfail("guarded tests of not-yet-verified device code failed in the child (exit %d): %s"
+                     % (code, out.strip().splitlines()[-1] if out.strip() else ""))

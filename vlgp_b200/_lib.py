@@ -48,6 +48,8 @@ EXPORTS = {
     "vlgp_get_cholesky": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p, c_i32_p, c_i32_p]),
     "vlgp_set_cholesky": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p]),
     "vlgp_estep": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_double, C.c_int, c_int_p]),
+    "vlgp_estep_subset": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_double, C.c_int, c_i32_p, C.c_int, c_int_p]),
+    "vlgp_trials_copy_rows": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i64_p, c_i64_p, C.c_int64]),
     "vlgp_update_w": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_update_v": (C.c_int, [ctx_p, C.c_int, c_int_p]),
     "vlgp_mstep": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -59,6 +61,7 @@ EXPORTS = {
     "vlgp_hstep_objective_batch": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i32_p, c_double_p, c_double_p, c_double_p,
                                              c_i32_p]),
     "vlgp_latent_affine": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p]),
+    "vlgp_latent_affine_rows": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_i64_p, C.c_int64]),
     "vlgp_norms": (C.c_int, [ctx_p, C.c_int, c_double_p]),
     "vlgp_latent_moments": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_i64_p]),
     "vlgp_comm_unique_id": (C.c_int, [ctx_p, C.c_char_p, C.c_char_p]),

@@ -27,8 +27,10 @@ static int settle_mstep(vlgp_ctx *ctx) {
 
 // kernels.cu files
 int vlgp_launch_ichol(vlgp_ctx *ctx, PriorFactor &pf, const double *d_omega, const double *d_sigma, double *d_work);
-int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter, double dmu_bound, int method_vb);
-int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled);
+int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter, double dmu_bound, int method_vb,
+                              const int32_t *d_subset = nullptr, int n_subset = 0);
+int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled,
+                               const int32_t *d_subset = nullptr, int n_subset = 0);
 int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
                       double da_bound, double db_bound);
 int vlgp_mstep_job_setup(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
@@ -55,11 +57,14 @@ int vlgp_fail(vlgp_ctx *ctx, int code, const char *fmt, ...) {
 
 namespace {
 
+// rows != null: the map is applied to the n listed bins, one application per LIST ENTRY (a bin listed twice is mapped
+// twice -- by different threads, so a list must not repeat a bin; the host's lists of shared bins never do).
 __global__ void latent_affine_kernel(int64_t nbin, int L, double *mu, const double *__restrict__ shiftM, int has_shift,
-                                     int has_M) {
+                                     int has_M, const int64_t *__restrict__ rows) {
     // shiftM: [0,L) shift, [L, L+L*L) M row-major
-    const int64_t bin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t bin = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (bin >= nbin) return;
+    if (rows) bin = rows[bin];
     double x[VLGP_MAX_L], o[VLGP_MAX_L];
     for (int l = 0; l < L; ++l) x[l] = mu[bin * L + l] - (has_shift ? shiftM[l] : 0.0);
     if (has_M) {
@@ -72,6 +77,22 @@ __global__ void latent_affine_kernel(int64_t nbin, int L, double *mu, const doub
     } else {
         for (int l = 0; l < L; ++l) mu[bin * L + l] = x[l];
     }
+}
+
+// dst row <- src row for n (src, dst) pairs of bins, in each of the listed per-bin arrays (L doubles per bin).  All reads
+// of a pair's source happen in the same thread as its write; the host never lists a bin both as a source and as a
+// destination in one call (tail rows of one segment -> head rows of the next), so the pairs are independent.
+__global__ void copy_rows_kernel(int64_t n, int L, const int64_t *__restrict__ src, const int64_t *__restrict__ dst,
+                                 double *a0, double *a1, double *a2, double *a3) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * L) return;
+    const int64_t pair = i / L;
+    const int l = (int)(i - pair * L);
+    const int64_t s = src[pair] * L + l, d = dst[pair] * L + l;
+    if (a0) a0[d] = a0[s];
+    if (a1) a1[d] = a1[s];
+    if (a2) a2[d] = a2[s];
+    if (a3) a3[d] = a3[s];
 }
 
 // part[b][0..2L+2): per-latent sum mu, per-latent sum mu^2, sum dmu^2 total, (unused)
@@ -837,25 +858,113 @@ static int check_ready(vlgp_ctx *ctx, TrialSet *ts, const char *who) {
     return VLGP_OK;
 }
 
-int vlgp_estep(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, int *n_failed) {
+}   // extern "C"
+
+// Host index lists (segments, bins) travel through a stream-ordered scratch allocation: validated here, so that a kernel
+// never sees an index outside the set.
+template <typename T>
+static int upload_indices(vlgp_ctx *ctx, const T *h, int64_t n, int64_t bound, const char *who, T **d_out) {
+    REQUIRE(h && n >= 1, "%s: empty index list", who);
+    for (int64_t i = 0; i < n; ++i)
+        REQUIRE(h[i] >= 0 && (int64_t)h[i] < bound, "%s: index %lld at position %lld outside [0, %lld)", who,
+                (long long)h[i], (long long)i, (long long)bound);
+    T *d = nullptr;
+    CK(vlgp_dalloc(ctx, &d, (size_t)n * sizeof(T)));
+    cudaError_t e = cudaMemcpyAsync(d, h, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        vlgp_dfree(ctx, d);
+        CK(e);
+    }
+    *d_out = d;
+    return VLGP_OK;
+}
+
+extern "C" {
+
+static int estep_impl(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, const int32_t *segs,
+                      int n_segs, bool subset, int *n_failed) {
     TrialSet *ts = get_set(ctx, set_id);
     int rc = check_ready(ctx, ts, "estep");
     if (rc) return rc;
     if (n_failed) *n_failed = 0;
     if (n_iter < 1) return VLGP_OK;
+    if (subset && n_segs == 0) return VLGP_OK;
     CK(cudaSetDevice(ctx->device));
     SETTLE();
+    int32_t *d_sub = nullptr;
+    if (subset) {
+        REQUIRE(n_segs > 0 && n_segs <= ts->n_trials, "estep_subset: %d segments listed, the set has %d", n_segs,
+                ts->n_trials);
+        // a segment listed twice would be processed by two CTAs at once
+        std::vector<uint8_t> seen((size_t)ts->n_trials, 0);
+        for (int i = 0; i < n_segs && segs; ++i) {
+            if (segs[i] < 0 || segs[i] >= ts->n_trials) break;      // reported by upload_indices
+            REQUIRE(!seen[segs[i]], "estep_subset: segment %d listed twice", segs[i]);
+            seen[segs[i]] = 1;
+        }
+        rc = upload_indices<int32_t>(ctx, segs, n_segs, ts->n_trials, "estep_subset", &d_sub);
+        if (rc) return rc;
+    }
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     {
         ProfScope ps(ctx, 0);
         bool handled = false;
-        rc = vlgp_launch_estep_segments(ctx, ts, n_iter, dmu_bound, method_vb, &handled);
-        if (rc) return rc;
-        if (!handled) rc = vlgp_launch_estep_generic(ctx, ts, 0, n_iter, dmu_bound, method_vb);
-        if (rc) return rc;
+        rc = vlgp_launch_estep_segments(ctx, ts, n_iter, dmu_bound, method_vb, &handled, d_sub, n_segs);
+        if (!rc && !handled) rc = vlgp_launch_estep_generic(ctx, ts, 0, n_iter, dmu_bound, method_vb, d_sub, n_segs);
     }
-    ctx->counters[1] += (int64_t)ts->n_trials * ctx->L * n_iter * 2;
+    if (d_sub) vlgp_dfree(ctx, d_sub);
+    if (rc) return rc;
+    ctx->counters[1] += (int64_t)(subset ? n_segs : ts->n_trials) * ctx->L * n_iter * 2;
     return read_flag(ctx, 0, n_failed);
+}
+
+int vlgp_estep(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, int *n_failed) {
+    return estep_impl(ctx, set_id, n_iter, dmu_bound, method_vb, nullptr, 0, false, n_failed);
+}
+
+int vlgp_estep_subset(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, int method_vb, const int32_t *segments,
+                      int n_segments, int *n_failed) {
+    REQUIRE(ctx && n_segments >= 0 && (segments || n_segments == 0), "estep_subset: bad arguments");
+    return estep_impl(ctx, set_id, n_iter, dmu_bound, method_vb, segments, n_segments, true, n_failed);
+}
+
+int vlgp_trials_copy_rows(vlgp_ctx *ctx, int set_id, int which_mask, const int64_t *src, const int64_t *dst, int64_t n) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "trials_copy_rows: bad set %d", set_id);
+    REQUIRE(which_mask > 0 && which_mask < 16, "trials_copy_rows: which_mask %d (bit 0 mu, 1 v, 2 w, 3 dmu)", which_mask);
+    REQUIRE(n >= 0 && (n == 0 || (src && dst)), "trials_copy_rows: bad arguments");
+    if (n == 0) return VLGP_OK;
+    {   // the pairs must be independent: no bin both read and written, no bin written twice
+        std::vector<uint8_t> mark((size_t)ts->nbin, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            REQUIRE(src[i] >= 0 && src[i] < ts->nbin && dst[i] >= 0 && dst[i] < ts->nbin,
+                    "trials_copy_rows: pair %lld (%lld -> %lld) outside [0, %lld)", (long long)i, (long long)src[i],
+                    (long long)dst[i], (long long)ts->nbin);
+            REQUIRE(!(mark[dst[i]] & 2), "trials_copy_rows: bin %lld is written twice", (long long)dst[i]);
+            mark[dst[i]] |= 2;
+        }
+        for (int64_t i = 0; i < n; ++i)
+            REQUIRE(!(mark[src[i]] & 2), "trials_copy_rows: bin %lld is both a source and a destination",
+                    (long long)src[i]);
+    }
+    CK(cudaSetDevice(ctx->device));
+    SETTLE();
+    int64_t *d_idx = nullptr;
+    std::vector<int64_t> both((size_t)2 * n);
+    std::copy(src, src + n, both.begin());
+    std::copy(dst, dst + n, both.begin() + n);
+    int rc = upload_indices<int64_t>(ctx, both.data(), 2 * n, ts->nbin, "trials_copy_rows", &d_idx);
+    if (rc) return rc;
+    const int L = ctx->L, nt = 256;
+    copy_rows_kernel<<<(unsigned)((n * L + nt - 1) / nt), nt, 0, ctx->stream>>>(
+        n, L, d_idx, d_idx + n, (which_mask & 1) ? ts->d_mu : nullptr, (which_mask & 2) ? ts->d_v : nullptr,
+        (which_mask & 4) ? ts->d_w : nullptr, (which_mask & 8) ? ts->d_dmu : nullptr);
+    cudaError_t e = cudaGetLastError();
+    vlgp_dfree(ctx, d_idx);
+    CK(e);
+    ctx->counters[0]++;
+    CK(cudaStreamSynchronize(ctx->stream));      // `both` is pageable host memory read by the asynchronous copy
+    return VLGP_OK;
 }
 
 int vlgp_update_w(vlgp_ctx *ctx, int set_id) {
@@ -1011,22 +1120,52 @@ int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyp
 }
 
 // ---- constraints / bookkeeping ---------------------------------------------------------------------------------------
-int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M) {
+static int latent_affine_impl(vlgp_ctx *ctx, int set_id, const double *shift, const double *M, const int64_t *rows,
+                              int64_t n_rows, bool listed) {
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts, "latent_affine: bad set %d", set_id);
     if (!shift && !M) return VLGP_OK;
+    if (listed && n_rows == 0) return VLGP_OK;
+    if (listed) {
+        REQUIRE(rows && n_rows > 0, "latent_affine_rows: bad arguments");
+        std::vector<uint8_t> seen((size_t)ts->nbin, 0);
+        for (int64_t i = 0; i < n_rows; ++i) {
+            if (rows[i] < 0 || rows[i] >= ts->nbin) break;          // reported by upload_indices
+            REQUIRE(!seen[rows[i]], "latent_affine_rows: bin %lld listed twice", (long long)rows[i]);
+            seen[rows[i]] = 1;
+        }
+    }
     CK(cudaSetDevice(ctx->device));
     SETTLE();
     const int L = ctx->L;
+    int64_t *d_rows = nullptr;
+    if (listed) {
+        int rc = upload_indices<int64_t>(ctx, rows, n_rows, ts->nbin, "latent_affine_rows", &d_rows);
+        if (rc) return rc;
+    }
     for (int l = 0; l < L; ++l) ctx->h_pin[l] = shift ? shift[l] : 0.0;
     for (int i = 0; i < L * L; ++i) ctx->h_pin[L + i] = M ? M[i] : 0.0;
     CK(cudaMemcpyAsync(ctx->d_small, ctx->h_pin, (L + L * L) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const int nt = 256;
-    latent_affine_kernel<<<(unsigned)((ts->nbin + nt - 1) / nt), nt, 0, ctx->stream>>>(ts->nbin, L, ts->d_mu, ctx->d_small,
-                                                                                     shift != nullptr, M != nullptr);
-    CKL();
+    const int64_t n = listed ? n_rows : ts->nbin;
+    latent_affine_kernel<<<(unsigned)((n + nt - 1) / nt), nt, 0, ctx->stream>>>(n, L, ts->d_mu, ctx->d_small,
+                                                                               shift != nullptr, M != nullptr, d_rows);
+    cudaError_t e = cudaGetLastError();
+    if (d_rows) vlgp_dfree(ctx, d_rows);
+    CK(e);
+    ctx->counters[0]++;
     CK(cudaStreamSynchronize(ctx->stream));
     return VLGP_OK;
+}
+
+int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M) {
+    return latent_affine_impl(ctx, set_id, shift, M, nullptr, 0, false);
+}
+
+int vlgp_latent_affine_rows(vlgp_ctx *ctx, int set_id, const double *shift, const double *M, const int64_t *rows,
+                            int64_t n_rows) {
+    REQUIRE(ctx && n_rows >= 0, "latent_affine_rows: bad arguments");
+    return latent_affine_impl(ctx, set_id, shift, M, rows, n_rows, true);
 }
 
 static int moments(vlgp_ctx *ctx, TrialSet *ts, std::vector<double> &out) {

@@ -19,6 +19,7 @@ namespace {
 
 struct EstepArgs {
     int n_trials, N, L, rank;
+    const int32_t *subset;       // n_trials trial indices to process (vlgp_estep_subset), or null: trials 0..n_trials-1
     const int *len;
     const int64_t *start;
     const int *fidx;
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(NT) estep_generic_kernel(EstepArgs p) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *minv_cta = p.minv + (size_t)blockIdx.x * LT * rank * rank;
 
-    for (int trial = blockIdx.x; trial < p.n_trials; trial += gridDim.x) {
+    for (int item = blockIdx.x; item < p.n_trials; item += gridDim.x) {
+        const int trial = p.subset ? p.subset[item] : item;
         const int T = p.len[trial];
         const int64_t s0 = p.start[trial];
         const double *G = p.Gptr[p.fidx[trial]];
@@ -311,9 +313,11 @@ int launch_estep_t(vlgp_ctx *ctx, TrialSet *ts, EstepArgs &p) {
     }
 
 // mode: 0 = estep, 1 = update_w, 2 = update_v
-int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter, double dmu_bound, int method_vb) {
+int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter, double dmu_bound, int method_vb,
+                              const int32_t *d_subset, int n_subset) {
     EstepArgs p{};
-    p.n_trials = ts->n_trials;
+    p.n_trials = d_subset ? n_subset : ts->n_trials;
+    p.subset = d_subset;
     p.N = ctx->N;
     p.L = ctx->L;
     p.rank = ctx->rank;

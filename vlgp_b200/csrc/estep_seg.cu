@@ -9,13 +9,14 @@ template <> int launch_seg_variant<2, false>(vlgp_ctx *, TrialSet *, SegArgs &, 
 template <> int launch_seg_variant<4, false>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
 }
 
-int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled) {
+int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled,
+                               const int32_t *d_subset, int n_subset) {
     *handled = false;
     if (getenv("VLGP_FORCE_GENERIC_ESTEP")) return VLGP_OK;
     if (ts->min_len != ts->max_len || ts->max_len > VLGP_MAX_W || ts->factors.size() != 1) return VLGP_OK;
     const int W = ts->max_len, L = ctx->L, N = ctx->N;
     SegArgs p{};
-    p.n_seg = ts->n_trials; p.W = W; p.N = N; p.rank = ctx->rank;
+    p.n_seg = d_subset ? n_subset : ts->n_trials; p.subset = d_subset; p.W = W; p.N = N; p.rank = ctx->rank;
     p.G = ts->factors[0].d_G;
     int goff = 0, moff = 0, po = 0, co = 0;
     p.use_dmma = getenv("VLGP_NO_DMMA_ESTEP") ? 0 : 1;

@@ -24,6 +24,7 @@ constexpr int NWARP = NT / 32;
 
 struct SegArgs {
     int n_seg, W, N, rank;
+    const int32_t *subset;        // n_seg segment indices to process (vlgp_estep_subset), or null: segments 0..n_seg-1
     const double *G;              // L x W x rank
     int nc[VLGP_MAX_L];           // leading non-zero columns per latent
     int goff[VLGP_MAX_L];         // offsets (doubles) of the compact factor / Minv of latent l inside their regions
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
     __syncthreads();
 
     for (int seg = blockIdx.x; seg < p.n_seg; seg += gridDim.x) {
-        const int64_t bin0 = (int64_t)seg * W;
+        const int64_t bin0 = (int64_t)(p.subset ? p.subset[seg] : seg) * W;
         for (int i = tid; i < W * LT; i += NT) {
             s.mu[i] = p.mu[bin0 * LT + i];
             s.v[i] = p.v[bin0 * LT + i];

@@ -374,12 +374,40 @@ class TrialSet:
         self.h2d_bytes += G.nbytes
 
     # -- steps -----------------------------------------------------------------------------------------------------------
-    def estep(self, n_iter, dmu_bound=5.0, method="VB"):
+    @property
+    def row_ops(self):
+        """True when the host may drive the reference's in-place semantics of OVERLAPPING windows through
+        ``estep(subset=)``, ``copy_rows`` and ``latent_affine(rows=)`` (vlgp_b200/core.py::_Aliasing).  The three device
+        operations have not yet run on a GPU (written after this round's GPU minutes were spent), so they are opt-in:
+        VLGP_ALIASED_WINDOWS=1.  Without it overlapping windows are independent copies."""
+        return os.environ.get("VLGP_ALIASED_WINDOWS", "0") not in ("", "0")
+
+    def estep(self, n_iter, dmu_bound=5.0, method="VB", subset=None):
+        """E-step on every member of the set, or on the listed members only (``subset``: indices, each once)."""
         lib, ctx = self._lib()
         nf = C.c_int()
-        self.eng._ck(lib.vlgp_estep(ctx, self.id, int(n_iter), float(dmu_bound), int(method == "VB"), C.byref(nf)),
-                     "estep")
+        if subset is None:
+            self.eng._ck(lib.vlgp_estep(ctx, self.id, int(n_iter), float(dmu_bound), int(method == "VB"),
+                                        C.byref(nf)), "estep")
+        else:
+            sub = np.ascontiguousarray(subset, dtype=np.int32).reshape(-1)
+            self.eng._ck(lib.vlgp_estep_subset(ctx, self.id, int(n_iter), float(dmu_bound), int(method == "VB"),
+                                               sub.ctypes.data_as(_lib.c_i32_p), int(sub.size), C.byref(nf)),
+                         "estep_subset")
         return nf.value
+
+    def copy_rows(self, src, dst, which=("mu", "v")):
+        """bin dst[i] <- bin src[i] (indices into the set's concatenated bins) in the listed per-bin arrays."""
+        lib, ctx = self._lib()
+        src = np.ascontiguousarray(src, dtype=np.int64).reshape(-1)
+        dst = np.ascontiguousarray(dst, dtype=np.int64).reshape(-1)
+        if src.size != dst.size:
+            raise ValueError("copy_rows: %d sources, %d destinations" % (src.size, dst.size))
+        mask = 0
+        for k in which:
+            mask |= 1 << self._WHICH[k]
+        self.eng._ck(lib.vlgp_trials_copy_rows(ctx, self.id, mask, src.ctypes.data_as(_lib.c_i64_p),
+                                               dst.ctypes.data_as(_lib.c_i64_p), int(src.size)), "trials_copy_rows")
 
     def update_w(self):
         lib, ctx = self._lib()
@@ -435,12 +463,18 @@ class TrialSet:
                      "hstep_objective_batch")
         return ll, dll, info
 
-    def latent_affine(self, shift=None, M=None):
+    def latent_affine(self, shift=None, M=None, rows=None):
+        """mu <- (mu - shift) @ M on every bin, or on the listed bins only (``rows``: bin indices, each once)."""
         lib, ctx = self._lib()
         L = self.eng.L
         s = None if shift is None else as_f64(np.asarray(shift).reshape(-1), (L,))
         m = None if M is None else as_f64(M, (L, L))
-        self.eng._ck(lib.vlgp_latent_affine(ctx, self.id, dptr(s), dptr(m)), "latent_affine")
+        if rows is None:
+            self.eng._ck(lib.vlgp_latent_affine(ctx, self.id, dptr(s), dptr(m)), "latent_affine")
+        else:
+            r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
+            self.eng._ck(lib.vlgp_latent_affine_rows(ctx, self.id, dptr(s), dptr(m), r.ctypes.data_as(_lib.c_i64_p),
+                                                     int(r.size)), "latent_affine_rows")
 
     def norms(self):
         """(sum mu^2, sum dmu^2) over all bins (all ranks)."""
