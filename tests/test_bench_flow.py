@@ -49,6 +49,8 @@ def test_run_ours_prints_exactly_one_json_line_with_the_contract_keys(tmp_path):
     assert d["metric"] == "EM-iterations/sec" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["e2e"]["value"] > 0
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    # the dominant kernel is FP64-bound; the same launch against the HBM roofline (MEASURED_PEAKS.json when present)
+    assert set(d["roofline"]["hbm"]) >= {"algorithmic_bytes_per_launch", "achieved_gbs", "peak_gbs", "peak_source", "frac"}
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}        # no GPU here: the values are None
     assert "workload" in d["config"] and "cpu_baseline" not in d            # --no-cpu

@@ -266,6 +266,7 @@ class TrialSet:
         self.id = sid.value
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.y_stored = None          # dtype code of y in HBM once uploaded (1 = uint8 counts, 0 = float64)
 
     def free(self):
         if self.id is not None and self.eng.ctx:
@@ -292,6 +293,7 @@ class TrialSet:
             raise ValueError("y must be (%d, %d), got %s" % (self.nbin, self.eng.N, y.shape))
         self.eng._ck(lib.vlgp_trials_set_y(ctx, self.id, y.ctypes.data_as(C.c_void_p), int(ydtype)), "trials_set_y")
         self.h2d_bytes += y.nbytes
+        self.y_stored = int(ydtype)
 
     def set_y_parts(self, ys):
         """Upload per-trial observation blocks without concatenating them on the host (native pinned pipeline).
@@ -309,6 +311,7 @@ class TrialSet:
         self.eng._ck(lib.vlgp_trials_set_y_parts(ctx, self.id, len(keep), ptrs, rows, 1 if src_u8 else 0,
                                                  C.byref(stored)), "trials_set_y_parts")
         self.h2d_bytes += self.nbin * N * (1 if stored.value == 1 else 8)
+        self.y_stored = stored.value
         return stored.value
 
     _WHICH = {"mu": 0, "v": 1, "w": 2, "dmu": 3}
