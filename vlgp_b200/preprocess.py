@@ -65,8 +65,38 @@ def get_params(trials, zdim, **kwargs):
     }
 
 
+def _blas_thread_cap():
+    """Context manager that caps the BLAS thread pool while the factor analysis runs.
+
+    FactorAnalysis.fit is a handful of randomized SVDs of a tall, skinny matrix (bins/10 x neurons): every product is a
+    few Mflop, and OpenBLAS with one thread per core spends its time waking and spinning threads -- measured on the
+    256 x 1000 x 100 workload: 2.0 s with 8 threads, 0.19 s with 4, 0.32 s with 1 (1.49 of fit()'s 1.75 s wall time on
+    the GPU box went here).  The arithmetic is sklearn's own either way; the summation order inside GEMM depends on the
+    thread count, as it does for the reference between two machines (loading agrees to 1e-14, latents to 1e-12).
+    VLGP_INIT_BLAS_THREADS overrides the cap of 4; 0 leaves the pool alone."""
+    import contextlib
+    import os
+
+    try:
+        cap = int(os.environ.get("VLGP_INIT_BLAS_THREADS", "4"))
+    except ValueError:
+        cap = 4
+    if cap <= 0:
+        return contextlib.nullcontext()
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:  # pragma: no cover
+        return contextlib.nullcontext()
+    return threadpool_limits(limits=cap, user_api="blas")
+
+
 def initialize(trials, params, config):
     """Factor-analysis initialisation of loading / bias / noise and of every trial's posterior mean."""
+    with _blas_thread_cap():
+        _initialize(trials, params, config)
+
+
+def _initialize(trials, params, config):
     from sklearn.decomposition import FactorAnalysis
 
     zdim, xdim = params["zdim"], params["xdim"]
