@@ -5,6 +5,7 @@ transform() on new trials maps them with the fitted loading.  The host code of t
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from vlgp_b200 import core, preprocess
 from vlgp_b200.engine import Engine
@@ -124,3 +125,61 @@ def test_fitted_loading_reaches_the_factor_analysis_map():
     assign_inplace(params, "a", params["a"] * 0.5)
     z1 = params["transform"](y)
     assert not np.allclose(z0, z1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# host packing helpers of core.Session (pure host code, no engine)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_c_helper", [True, False])
+def test_regressor_check_scans_owners_not_segments(monkeypatch, use_c_helper):
+    """Only the all-ones bias regressor is supported (xdim == 1).  Segments are views of their trial's x: the check
+    must accept them, scan each owning array once, and still catch every way a regressor can be something else."""
+    from vlgp_b200 import core
+
+    if not use_c_helper:
+        monkeypatch.setattr(core, "_fastpack", None)
+    elif core._fastpack is None:
+        pytest.skip("_fastpack not built")
+    T, N = 120, 7
+    x = np.ones((T, 1, N))
+    segs = [dict(x=x[s:s + 40]) for s in range(0, T, 40)] + [dict(), dict(x=None), dict(x=np.ones((30, 1, N)))]
+    scans = []
+    real = core._all_ones
+    monkeypatch.setattr(core, "_all_ones", lambda a: scans.append(a.shape) or real(a))
+    core._check_regressors(segs)
+    if use_c_helper:
+        assert sorted(scans) == [(30, 1, N), (T, 1, N)]          # one scan per owner, not per segment
+    bad = np.ones((T, 1, N))
+    bad[77, 0, 3] = 0.5
+    with pytest.raises(NotImplementedError):
+        core._check_regressors(segs + [dict(x=bad[40:80])])
+    core._check_regressors(segs + [dict(x=bad[:40])])            # the view itself is all ones even if its owner is not
+    with pytest.raises(NotImplementedError):
+        core._check_regressors([dict(x=np.ones((T, 2, N)))])
+    with pytest.raises(NotImplementedError):
+        core._check_regressors([dict(x=np.ones((T, N)))])
+    # (an array verified once is remembered as all ones for as long as it lives, hence fresh arrays per case)
+    wide = np.ones((T, 2, N))
+    core._check_regressors([dict(x=wide[:, :1, :])])             # a (T, 1, N) view of a wider array of ones
+    wide = np.ones((T, 2, N))
+    wide[5, 1, 0] = 3.0
+    core._check_regressors([dict(x=wide[:, :1, :])])             # ... judged by its own entries
+    wide = np.ones((T, 2, N))
+    wide[5, 0, 0] = 3.0
+    with pytest.raises(NotImplementedError):
+        core._check_regressors([dict(x=wide[:, :1, :])])
+
+
+def test_row_views_equal_np_split():
+    from vlgp_b200 import core
+
+    for lengths in ([50] * 6, [50, 120, 64, 1, 200], [7]):
+        lengths = np.asarray(lengths, dtype=np.int32)
+        starts = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
+        a = np.arange(int(lengths.sum()) * 3, dtype=float).reshape(-1, 3)
+        views = core._row_views(a, starts, lengths)
+        ref = np.split(a, [int(s) for s in starts[1:]])
+        assert len(views) == len(ref)
+        for v, r in zip(views, ref):
+            assert v.shape == r.shape and np.shares_memory(v, a) and np.array_equal(v, r)
+            assert v.flags.c_contiguous and v.flags.writeable

@@ -18,7 +18,7 @@ import weakref
 
 import numpy as np
 
-from .engine import Engine, TrialSet, get_engine, pack_y
+from .engine import Engine, TrialSet, get_engine, pack_y, _fastpack
 from .util import assign_inplace
 
 __all__ = ["vem", "estep", "mstep", "hstep", "infer", "update_w", "update_v", "constrain_loading", "constrain_latent",
@@ -59,12 +59,37 @@ def _all_ones(x):
 
 
 def _check_regressors(trials):
-    for tr in trials:
-        x = tr.get("x")
-        if x is None:
-            continue
-        if x.ndim != 3 or x.shape[1] != 1 or not _all_ones(x):
+    """Only the all-ones bias regressor is supported.  Segments made by cut_trials are views of their trial's x, so
+    the scan runs once per underlying array (and at most once per process per array, see _all_ones), not once per
+    segment: 5120 segments of 256 trials cost 256 scans, and finding those 256 is one pass in C (_fastpack)."""
+    xs = [tr.get("x") for tr in trials]
+    owners = None
+    if _fastpack is not None:
+        try:
+            owners = _fastpack.block_owners(xs, 3, 1, 1)
+        except ValueError:
+            raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)") from None
+        except (TypeError, BufferError, AttributeError):
+            owners = None
+    if owners is None:
+        owners = [x for x in xs if x is not None]
+        if any(x.ndim != 3 or x.shape[1] != 1 for x in owners):
             raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
+    else:
+        if not any(o.ndim != 3 or o.shape[1] != 1 for o in owners) and all(_all_ones(o) for o in owners):
+            return
+        # views that cover only part of an owner which is not all ones as a whole: judge every view by its own entries
+        owners = [x for x in xs if x is not None]
+    for x in owners:
+        if not _all_ones(x):
+            raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
+
+
+def _row_views(a, starts, lengths):
+    """Per-trial views of the rows of one (bins, L) block (what np.split returns, without its per-piece overhead)."""
+    if lengths.size and (lengths == lengths[0]).all():
+        return list(a.reshape(lengths.size, int(lengths[0]), a.shape[1]))
+    return [a[s:s + n] for s, n in zip(starts.tolist(), lengths.tolist())]
 
 
 def _shared_rows(trials):
@@ -141,7 +166,7 @@ class Session:
             def blocks(key):
                 try:
                     out = [tr[key] for tr in trials]
-                    if not any(b is None for b in out):
+                    if not [1 for b in out if b is None]:
                         return out
                 except KeyError:
                     pass
@@ -203,9 +228,8 @@ class Session:
                 fresh[k] = np.empty((self.ts.nbin, L))
         if fresh:
             self.ts.get_state_parts(**{k: [a] for k, a in fresh.items()})
-            cuts = [int(x) for x in self.ts.starts[1:]]
             for k, a in fresh.items():
-                views = np.split(a, cuts) if cuts else [a]
+                views = _row_views(a, self.ts.starts, self.ts.lengths)
                 if k in ("mu", "v") and k not in rebind:
                     for tr, val in zip(trials, views):
                         if isinstance(tr.get(k), np.ndarray) and tr[k].shape == val.shape:

@@ -68,7 +68,76 @@ static PyObject *fp_format_char(PyObject *self, PyObject *obj) {
     return r;
 }
 
+/* block_owners(seq, ndim, axis, extent) -> list of the DISTINCT arrays owning the memory of the blocks in seq (None
+ * items are skipped): item.base when that is an object of the item's own type (a view), else the item itself.
+ * Every block must have `ndim` dimensions and shape[axis] == extent, else ValueError.  Used for the regressor check:
+ * thousands of segments are views of a few hundred trial-level arrays, and only those need to be scanned. */
+static PyObject *fp_block_owners(PyObject *self, PyObject *args) {
+    PyObject *seq;
+    int ndim, axis;
+    Py_ssize_t extent;
+    if (!PyArg_ParseTuple(args, "Oiin", &seq, &ndim, &axis, &extent)) return NULL;
+    if (axis < 0 || axis >= ndim) {
+        PyErr_SetString(PyExc_ValueError, "axis out of range");
+        return NULL;
+    }
+    PyObject *fast = PySequence_Fast(seq, "expected a sequence of arrays");
+    if (!fast) return NULL;
+    PyObject *seen = PyDict_New();
+    PyObject *out = NULL;
+    static PyObject *base_name = NULL;
+    if (!base_name) base_name = PyUnicode_InternFromString("base");
+    if (!seen || !base_name) goto fail;
+    {
+        const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+        PyObject *last = NULL;      /* borrowed: kept alive by `seen`; consecutive blocks usually share their owner */
+        for (Py_ssize_t i = 0; i < n; ++i) {
+            PyObject *item = PySequence_Fast_GET_ITEM(fast, i);
+            if (item == Py_None) continue;
+            Py_buffer view;
+            if (PyObject_GetBuffer(item, &view, PyBUF_STRIDES) != 0) goto fail;
+            const int ok = view.ndim == ndim && view.shape[axis] == extent;
+            PyBuffer_Release(&view);
+            if (!ok) {
+                PyErr_Format(PyExc_ValueError, "item %zd: expected %d dimensions with shape[%d] == %zd", i, ndim, axis,
+                             extent);
+                goto fail;
+            }
+            PyObject *owner = PyObject_GetAttr(item, base_name);
+            if (!owner) {
+                PyErr_Clear();
+                owner = item;
+                Py_INCREF(owner);
+            } else if (Py_TYPE(owner) != Py_TYPE(item)) {
+                Py_DECREF(owner);
+                owner = item;
+                Py_INCREF(owner);
+            }
+            if (owner == last) {
+                Py_DECREF(owner);
+                continue;
+            }
+            PyObject *key = PyLong_FromVoidPtr((void *)owner);
+            if (!key) {
+                Py_DECREF(owner);
+                goto fail;
+            }
+            const int rc = PyDict_SetItem(seen, key, owner);      /* the dict holds its own references */
+            Py_DECREF(key);
+            Py_DECREF(owner);
+            if (rc != 0) goto fail;
+            last = owner;
+        }
+    }
+    out = PyDict_Values(seen);
+fail:
+    Py_XDECREF(seen);
+    Py_DECREF(fast);
+    return out;
+}
+
 static PyMethodDef methods[] = {
+    {"block_owners", fp_block_owners, METH_VARARGS, "block_owners(seq, ndim, axis, extent) -> distinct owning arrays"},
     {"pointers", fp_pointers, METH_VARARGS, "pointers(seq, itemsize, ncols, writable=False) -> (ptr bytes, row bytes)"},
     {"format_char", fp_format_char, METH_O, "struct format character of a buffer"},
     {NULL, NULL, 0, NULL}};
