@@ -247,6 +247,14 @@ def optimze1d(ts, latent, initial, bounds, mask, evaluate=None):
 
 
 def _optimize_dev(s, params, config):
+    from .util import blas_threads
+
+    # scipy's L-BFGS-B routine solves 10 x 10 systems through LAPACK at every call: one BLAS thread (util.blas_threads)
+    with blas_threads(0 if os.environ.get("VLGP_HSTEP_BLAS_THREADS") == "0" else 1):
+        _optimize_dev_impl(s, params, config)
+
+
+def _optimize_dev_impl(s, params, config):
     ts = s.ts
     zdim = params["zdim"]
     sigma = np.array(params["sigma"], dtype=float)

@@ -66,7 +66,7 @@ def get_params(trials, zdim, **kwargs):
 
 
 def _blas_thread_cap():
-    """Context manager that caps the BLAS thread pool while the factor analysis runs.
+    """Cap of the BLAS thread pool while the factor analysis runs.
 
     FactorAnalysis.fit is a handful of randomized SVDs of a tall, skinny matrix (bins/10 x neurons): every product is a
     few Mflop, and OpenBLAS with one thread per core spends its time waking and spinning threads -- measured on the
@@ -74,20 +74,15 @@ def _blas_thread_cap():
     the GPU box went here).  The arithmetic is sklearn's own either way; the summation order inside GEMM depends on the
     thread count, as it does for the reference between two machines (loading agrees to 1e-14, latents to 1e-12).
     VLGP_INIT_BLAS_THREADS overrides the cap of 4; 0 leaves the pool alone."""
-    import contextlib
     import os
+
+    from .util import blas_threads
 
     try:
         cap = int(os.environ.get("VLGP_INIT_BLAS_THREADS", "4"))
     except ValueError:
         cap = 4
-    if cap <= 0:
-        return contextlib.nullcontext()
-    try:
-        from threadpoolctl import threadpool_limits
-    except ImportError:  # pragma: no cover
-        return contextlib.nullcontext()
-    return threadpool_limits(limits=cap, user_api="blas")
+    return blas_threads(max(cap, 0))
 
 
 def initialize(trials, params, config):
