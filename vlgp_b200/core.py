@@ -50,12 +50,17 @@ def _all_ones(x):
         return True
     if base.min() != 1 or base.max() != 1:
         return base is not x and x.min() == 1 and x.max() == 1
+    _remember_ones(base)
+    return True
+
+
+def _remember_ones(base):
+    """Record (weakly) that ``base`` -- an array that owns its memory -- is all ones."""
     try:
         key = id(base)
         _ONES_VERIFIED[key] = weakref.ref(base, lambda _r, k=key: _ONES_VERIFIED.pop(k, None))
     except TypeError:  # pragma: no cover
         pass
-    return True
 
 
 def _check_regressors(trials):

@@ -117,16 +117,45 @@ def _initialize(trials, params, config):
             tr["mu"] = to_latent(tr["y"])
         if tr.get("x") is None:
             tr["x"] = np.ones((nt, xdim, ydim))
+            _mark_ones(tr["x"])
         tr["w"] = np.zeros((nt, zdim))
         tr["v"] = np.zeros((nt, zdim))
 
 
+def _mark_ones(x):
+    """Tell the engine's regressor check (core._all_ones) that this freshly made array is the all-ones bias column, so
+    that it is not scanned again (205 MB at 256 trials x 1000 bins x 100 neurons)."""
+    try:
+        from .core import _remember_ones
+
+        _remember_ones(x)
+    except Exception:  # pragma: no cover - bookkeeping only
+        pass
+
+
 def fill_trials(trials):
+    """``cut`` index and zero ``w`` / ``v`` / ``dmu`` where missing (vlgp/preprocess.py:115-120).  The missing arrays of
+    one key are handed out as row blocks of ONE zero array when every ``mu`` is a 2-D float64 array of the same width
+    (thousands of segments: one allocation instead of one ``zeros_like`` each)."""
     for i, tr in enumerate(trials):
         tr["cut"] = i
-        for key in ("w", "v", "dmu"):
-            if key not in tr:
-                tr[key] = np.zeros_like(tr["mu"])
+    for key in ("w", "v", "dmu"):
+        need = [tr for tr in trials if key not in tr]
+        if not need:
+            continue
+        mus = [tr["mu"] for tr in need]
+        width = {(m.shape[1] if isinstance(m, np.ndarray) and m.ndim == 2 and m.dtype == np.float64 else None)
+                 for m in mus}
+        if len(need) > 1 and len(width) == 1 and None not in width:
+            rows = [m.shape[0] for m in mus]
+            block = np.zeros((sum(rows), width.pop()))
+            r0 = 0
+            for tr, n in zip(need, rows):
+                tr[key] = block[r0:r0 + n]
+                r0 += n
+        else:
+            for tr, m in zip(need, mus):
+                tr[key] = np.zeros_like(m)
 
 
 def fill_params(params):

@@ -40,6 +40,11 @@ def blas_threads(n):
         if _BLAS_CONTROLLER is None:
             from threadpoolctl import ThreadpoolController
 
+            # the controller only knows the libraries loaded when it is created: pull in the ones the host path calls
+            # into (SciPy ships its own OpenBLAS, loaded with scipy.linalg / scipy.optimize) before taking the snapshot
+            import scipy.linalg  # noqa: F401
+            import scipy.optimize  # noqa: F401
+
             _BLAS_CONTROLLER = ThreadpoolController()
         return _BLAS_CONTROLLER.limit(limits=int(n), user_api="blas")
     except Exception:  # pragma: no cover - threadpoolctl missing or an unknown BLAS: run unthrottled
