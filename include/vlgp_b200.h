@@ -151,6 +151,14 @@ VLGP_API int vlgp_norms(vlgp_ctx *ctx, int set_id, double out[2]);
 /* Per-latent sum(mu), sum(mu^2) and the bin count (summed over ranks when a communicator is set). */
 VLGP_API int vlgp_latent_moments(vlgp_ctx *ctx, int set_id, double *sum, double *sumsq, int64_t *count);
 
+/* ---- host packing (context-free, no device needed) ------------------------------------------------------------------
+ * The reference hands y over as float64 (it promotes whatever arrives, vlgp/core.py:60); spike counts are stored in HBM
+ * as uint8 when every entry is an integer in [0, 255].  This is the conversion + exactness check that the host threads of
+ * vlgp_trials_set_y_parts run on disjoint ranges: dst[k] = (uint8) src[k]; returns 1 when every entry was such a count
+ * (dst is then exact), 0 otherwise (dst is then unspecified).  vlgp_host_pack_isa: 1 when the AVX2 body is in use. */
+VLGP_API int vlgp_host_f64_to_u8(const double *src, unsigned char *dst, int64_t cnt);
+VLGP_API int vlgp_host_pack_isa(void);
+
 /* ---- multi-GPU: one process per GPU, NCCL sum-allreduce of the M-/H-step sufficient statistics ------------------- */
 VLGP_API int vlgp_comm_unique_id(vlgp_ctx *ctx, const char *libnccl_path, char id[128]);
 VLGP_API int vlgp_comm_init(vlgp_ctx *ctx, const char *libnccl_path, int rank, int n_ranks, const char id[128]);

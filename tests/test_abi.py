@@ -139,3 +139,36 @@ def test_pointer_tables_and_fastpack():
         _pointer_table([np.zeros((4, 6))[:, ::2]], np.float64, 3, writable=True)
     with pytest.raises(ValueError):
         _pointer_table([np.zeros((4, 2))], np.float64, 3)
+
+
+def test_host_count_conversion_is_exact_or_refused(libpath):
+    """vlgp_host_f64_to_u8 (the float64 -> uint8 spike-count conversion of the upload path, context-free): exact for
+    integer counts in [0, 255] at every length around the vector width, refused (return 0) for anything else at any
+    position -- fractions, negatives, 256, NaN, inf, huge values."""
+    import ctypes as C
+
+    import numpy as np
+
+    from vlgp_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.vlgp_host_pack_isa() in (0, 1)
+    u8p = C.POINTER(C.c_ubyte)
+    rng = np.random.default_rng(0)
+    for n in (1, 3, 15, 16, 17, 31, 32, 33, 1000, 100003):
+        y = rng.poisson(0.4, n).astype(float)
+        y[rng.integers(n)] = 255.0
+        y[rng.integers(n)] = -0.0
+        out = np.full(n, 7, np.uint8)
+        assert lib.vlgp_host_f64_to_u8(_lib.dptr(y), out.ctypes.data_as(u8p), n) == 1
+        assert np.array_equal(out, y.astype(np.uint8)), n
+        for bad in (0.5, -1.0, 256.0, 254.99999999, np.nan, np.inf, -np.inf, 1e300, -1e-300, 2.0 ** 31, 2.0 ** 32 + 3):
+            for pos in {0, n - 1, n // 2}:
+                z = y.copy()
+                z[pos] = bad
+                assert lib.vlgp_host_f64_to_u8(_lib.dptr(z), out.ctypes.data_as(u8p), n) == 0, (n, bad, pos)
+    # unaligned source / destination
+    y = rng.poisson(1.0, 1001).astype(float)
+    buf = np.zeros(1100, np.uint8)
+    assert lib.vlgp_host_f64_to_u8(_lib.dptr(y[1:]), buf[3:].ctypes.data_as(u8p), 1000) == 1
+    assert np.array_equal(buf[3:1003], y[1:].astype(np.uint8)) and not buf[:3].any() and not buf[1003:].any()

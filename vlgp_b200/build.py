@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libvlgp_b200.so")
-SOURCES = ["capi.cu", "comm.cu", "shmcomm.cu", "ichol.cu", "estep.cu", "estep_seg.cu", "estep_seg_v_fast.cu", "estep_seg_v_gen.cu", "estep_seg_v_big.cu", "mstep.cu", "hstep.cu", "hstep_dmma.cu"]
+SOURCES = ["capi.cu", "hostpack.cpp", "comm.cu", "shmcomm.cu", "ichol.cu", "estep.cu", "estep_seg.cu", "estep_seg_v_fast.cu", "estep_seg_v_gen.cu", "estep_seg_v_big.cu", "mstep.cu", "hstep.cu", "hstep_dmma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]

@@ -532,8 +532,9 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
         CK(cudaEventCreateWithFlags(&ctx->stage_ev[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->stage_ev[1], cudaEventDisableTiming));
     }
+    // the float64 -> uint8 conversion streams 8 bytes per entry at ~6 GB/s per thread (hostpack.cpp): up to 16 threads
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+    const int nthreads = (int)std::min<unsigned>(hw ? hw : 4, src_dtype == VLGP_Y_F64 ? 16 : 8);
 
     // Flatten the parts into one virtual element range [0, total * N) so that chunks need not align with parts.
     std::vector<int64_t> part_off(n_parts + 1, 0);
@@ -576,16 +577,8 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
                     } else if (src_dtype == VLGP_Y_U8) {
                         memcpy(dst, (const unsigned char *)parts[p] + loc, (size_t)cnt);
                     } else {
-                        const double *src = (const double *)parts[p] + loc;
-                        bool ok = true;
-                        for (int64_t k = 0; k < cnt; ++k) {
-                            const double v = src[k];
-                            const bool in = (v >= 0.0) & (v <= 255.0);         // also false for NaN
-                            const unsigned char c = in ? (unsigned char)(int)v : (unsigned char)0;
-                            dst[k] = c;
-                            ok &= in & ((double)c == v);                       // exact only for integer counts
-                        }
-                        if (!ok) exact.store(false);
+                        // exact only for integer counts in [0, 255] (hostpack.cpp: AVX2 body chosen at run time)
+                        if (!vlgp_host_f64_to_u8((const double *)parts[p] + loc, dst, cnt)) exact.store(false);
                     }
                     a = stop;
                     ++p;
