@@ -73,7 +73,7 @@ def cut(trials, params, config):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: NumPy/SciPy oracle port of the reference, bounded sample
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_em_iteration_time(cfgname, sample_trials, steps, warmup):
+def cpu_em_iteration_time(cfgname, sample_trials, steps, warmup, all_threads_probe=None):
     """Seconds per EM iteration of the oracle on ``sample_trials`` trials of the workload, and the segment counts."""
     from oracle import vlgp_oracle as orc
 
@@ -94,6 +94,19 @@ def cpu_em_iteration_time(cfgname, sample_trials, steps, warmup):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+    if all_threads_probe is not None:
+        # the reference at one BLAS thread and at one per core, the better one is the baseline.
+        # One more iteration with the pool opened up (the operands are 50 x 50: more threads have never helped).
+        try:
+            from threadpoolctl import threadpool_limits
+
+            ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            with threadpool_limits(limits=ncpu, user_api="blas"):
+                t0 = time.perf_counter()
+                orc.vem(segs, params, config)
+                all_threads_probe.update(threads=ncpu, sec=time.perf_counter() - t0)
+        except Exception as e:  # pragma: no cover - diagnostics only
+            all_threads_probe.update(error=repr(e))
     return float(np.mean(times)), len(segs), c
 
 
@@ -107,10 +120,14 @@ def run_reference(args):
     c = CONFIGS[args.config]
     full_trials = c["n_trials"]
     sample = max(1, min(args.cpu_sample_trials, full_trials))
-    sec, nseg, _ = cpu_em_iteration_time(args.config, sample, args.steps, args.warmup)
+    probe = {}
+    sec, nseg, _ = cpu_em_iteration_time(args.config, sample, args.steps, args.warmup, all_threads_probe=probe)
+    threads = int(os.environ.get("OPENBLAS_NUM_THREADS", os.environ.get("OMP_NUM_THREADS", "0")) or 0) or os.cpu_count()
+    sec_one = sec
+    if probe.get("sec") and probe["sec"] < sec:     # the opened-up pool won: that is the baseline then
+        sec, threads = probe["sec"], probe["threads"]
     full_sec = sec * full_trials / sample          # E-, M- and H-step cost are all linear in the number of segments
     value = 1.0 / full_sec
-    threads = int(os.environ.get("OPENBLAS_NUM_THREADS", os.environ.get("OMP_NUM_THREADS", "0")) or 0) or os.cpu_count()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": full_sec * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -119,7 +136,10 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d of %d trials (%d of %d segments), %.2f s per EM iteration measured, scaled "
                                    "linearly in segments" % (sample, full_trials, nseg, nseg * full_trials // sample,
-                                                             sec)},
+                                                             sec),
+                         "blas_threads_tried": {"1": sec_one, str(probe.get("threads", "all")): probe.get("sec")},
+                         "note": "seconds per EM iteration of the sample at each BLAS pool size; the reference is a "
+                                 "single Python process, the faster setting is reported"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
