@@ -86,6 +86,21 @@ __host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_tot
     return bytes;
 }
 
+// (a, a^2) of one (latent, neuron) entry of the packed loading in shared memory.  The rate passes are bound by
+// shared-memory wavefronts, not by the FP64 pipe (ncu, config 2: 1.68e9 LSU wavefronts in a 9.4 ms launch = 61 % of the
+// SM-cycles, FP64 pipe 35 %): every lane of a warp needs the pair of ITS neuron, a 128-bit load costs four wavefronts
+// however few distinct addresses the warp touches, and there are L of them per (bin, neuron).  Reading only a (64-bit,
+// two wavefronts) and squaring it in registers halves that traffic for one DMUL; a * a is the very value
+// pack_params_kernel stored, so results are unchanged bit for bit.  -DVLGP_ESTEP_A2_FROM_SMEM restores the 128-bit load.
+__device__ __forceinline__ double2 load_a(const double2 *aa, int idx) {
+#ifdef VLGP_ESTEP_A2_FROM_SMEM
+    return aa[idx];
+#else
+    const double x = reinterpret_cast<const double *>(aa)[2 * idx];
+    return make_double2(x, x * x);
+#endif
+}
+
 // One rate pass over the segment.  STAGE 1: part <- partial sums of resid * a_l ; STAGE 2: of U * a_l^2.
 template <int LT, int STAGE, bool FAST>
 __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, int64_t bin0) {
@@ -114,7 +129,7 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
                 double eta0 = bb[n].x, eta1 = bb[n2].x, h0 = 0.0, h1 = 0.0;
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
-                    const double2 p0 = aa[l * N + n], p1 = aa[l * N + n2];
+                    const double2 p0 = load_a(aa, l * N + n), p1 = load_a(aa, l * N + n2);
                     eta0 = fma(mu_t[l], p0.x, eta0);
                     eta1 = fma(mu_t[l], p1.x, eta1);
                     h0 = fma(v_t[l], p0.y, h0);
@@ -134,7 +149,7 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
                 double eta0 = bb[n].x, h0 = 0.0;
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
-                    const double2 p0 = aa[l * N + n];
+                    const double2 p0 = load_a(aa, l * N + n);
                     eta0 = fma(mu_t[l], p0.x, eta0);
                     h0 = fma(v_t[l], p0.y, h0);
                     al0[l] = (STAGE == 1) ? p0.x : p0.y;
@@ -151,7 +166,7 @@ __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, i
                 double al[LT], eta = bn.x, h = 0.0;
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
-                    const double2 p2 = aa[l * N + n];          // (a, a^2)
+                    const double2 p2 = load_a(aa, l * N + n);  // (a, a^2)
                     eta = fma(mu_t[l], p2.x, eta);
                     h = fma(v_t[l], p2.y, h);
                     al[l] = (STAGE == 1) ? p2.x : p2.y;
