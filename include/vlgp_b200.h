@@ -158,6 +158,9 @@ VLGP_API int vlgp_latent_moments(vlgp_ctx *ctx, int set_id, double *sum, double 
  * (dst is then exact), 0 otherwise (dst is then unspecified).  vlgp_host_pack_isa: 1 when the AVX2 body is in use. */
 VLGP_API int vlgp_host_f64_to_u8(const double *src, unsigned char *dst, int64_t cnt);
 VLGP_API int vlgp_host_pack_isa(void);
+/* Self-test of the persistent host thread pool those threads come from (hostpack.cpp): `rounds` parallel calls of
+ * n_tasks tasks; returns 0 when every task of every call ran exactly once before its call returned. */
+VLGP_API int vlgp_host_pool_selftest(int n_tasks, int rounds, int *workers);
 
 /* ---- multi-GPU: one process per GPU, NCCL sum-allreduce of the M-/H-step sufficient statistics ------------------- */
 VLGP_API int vlgp_comm_unique_id(vlgp_ctx *ctx, const char *libnccl_path, char id[128]);

@@ -172,3 +172,50 @@ def test_host_count_conversion_is_exact_or_refused(libpath):
     buf = np.zeros(1100, np.uint8)
     assert lib.vlgp_host_f64_to_u8(_lib.dptr(y[1:]), buf[3:].ctypes.data_as(u8p), 1000) == 1
     assert np.array_equal(buf[3:1003], y[1:].astype(np.uint8)) and not buf[:3].any() and not buf[1003:].any()
+
+
+def test_host_thread_pool_runs_every_task_exactly_once(libpath):
+    """The persistent host pool behind the upload / download pipeline (hostpack.cpp): thousands of parallel calls with
+    0 .. 64 tasks, from one thread and from several at once, and in a forked child (threads do not survive a fork: the
+    pool must notice and rebuild itself instead of waiting for workers that no longer exist)."""
+    import ctypes as C
+    import os
+    import threading
+
+    from vlgp_b200 import _lib
+
+    lib = _lib.load()
+    w = C.c_int()
+    for n in (0, 1, 2, 3, 7, 8, 16, 17, 64):
+        assert lib.vlgp_host_pool_selftest(n, 1500, C.byref(w)) == 0, n
+        assert w.value <= 15
+    assert lib.vlgp_host_pool_selftest(-1, 1, None) == -1
+    out = []
+    threads = [threading.Thread(target=lambda k=k: out.append(lib.vlgp_host_pool_selftest(k, 2000, None)))
+               for k in (5, 16, 9, 12)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert out == [0, 0, 0, 0]
+    pid = os.fork()
+    if pid == 0:                                   # child: must not hang on the parent's vanished workers
+        rc = 1
+        try:
+            rc = 0 if lib.vlgp_host_pool_selftest(8, 300, None) == 0 else 1
+        finally:
+            os._exit(rc)
+    import time
+
+    t0 = time.time()
+    while True:
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        if time.time() - t0 > 60:
+            os.kill(pid, 9)
+            os.waitpid(pid, 0)
+            raise AssertionError("the forked child hung in the host pool")
+        time.sleep(0.05)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    assert lib.vlgp_host_pool_selftest(8, 300, None) == 0

@@ -74,6 +74,7 @@ EXPORTS = {
     "vlgp_comm_attach_shm": (C.c_int, [ctx_p, C.c_void_p]),
     "vlgp_host_f64_to_u8": (C.c_int, [c_double_p, C.POINTER(C.c_ubyte), C.c_int64]),
     "vlgp_host_pack_isa": (C.c_int, []),
+    "vlgp_host_pool_selftest": (C.c_int, [C.c_int, C.c_int, c_int_p]),
     "vlgp_peak_fp64": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "vlgp_peak_hbm": (C.c_int, [ctx_p, C.c_uint64, c_double_p]),
     "vlgp_flush_l2": (C.c_int, [ctx_p]),

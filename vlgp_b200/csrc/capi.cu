@@ -8,6 +8,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "hostpack.h"
 #include "linalg.cuh"
 
 // An M-step begun with vlgp_mstep_begin may still be running on stream_m: calls that read or overwrite what it writes
@@ -584,10 +585,7 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
                     ++p;
                 }
             };
-            std::vector<std::thread> pool;
-            for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
-            work(0);
-            for (auto &th : pool) th.join();
+            vlgp_host_parallel_for(nthreads, work);          // persistent pool (hostpack.cpp)
             if (!exact.load()) break;
             CK(cudaMemcpyAsync((unsigned char *)ts->d_y + (size_t)e0 * esz, ctx->h_stage[buf], (size_t)(e1 - e0) * esz,
                                cudaMemcpyHostToDevice, ctx->stream));
@@ -660,10 +658,7 @@ static int pipeline_copy(vlgp_ctx *ctx, void *dev, size_t esz, int n_parts, void
         if (e1 - e0 < (int64_t)(1 << 16)) {
             for (int t = 0; t < nthreads; ++t) work(t);
         } else {
-            std::vector<std::thread> pool;
-            for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
-            work(0);
-            for (auto &th : pool) th.join();
+            vlgp_host_parallel_for(nthreads, work);
         }
     };
     if (to_device) {

@@ -5,8 +5,16 @@
 // vem() call with host buffers (204 MB of float64 per call at 256 trials x 1000 bins x 100 neurons), so it gets an AVX2
 // body chosen at run time: 2.8 -> 5.8 GB/s of float64 per thread.
 #include <stdint.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/vlgp_b200.h"
+#include "hostpack.h"
 
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
@@ -75,4 +83,138 @@ int vlgp_host_pack_isa(void) {
 #else
     return 0;
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent host thread pool of the packing pipeline.  The gather / scatter / convert steps of one upload or download
+// are split over a few host threads per 8 MB staging chunk; creating those threads anew for every chunk cost ~100
+// thread creations per vem() call with host buffers.  The workers are created once (grown on demand up to 15), sleep on
+// a condition variable between calls and are never joined (the pool object is leaked on purpose: no destructor runs at
+// process exit).  run() executes fn(0..n-1), each index exactly once, on the workers and on the calling thread, and
+// returns when all have finished.  Calls are serialised; a forked child (no threads survive a fork) rebuilds the pool.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+class HostPool {
+  public:
+    static HostPool &instance() {
+        static HostPool *p = new HostPool();
+        return *p;
+    }
+
+    void run(int n, vlgp_host_task fn, void *arg) {
+        if (n <= 1) {
+            if (n == 1) fn(0, arg);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mutex_);
+        if (pid_ != getpid()) reset_after_fork();
+        const int want = n - 1 < kMaxWorkers ? n - 1 : kMaxWorkers;
+        while ((int)workers_.size() < want) workers_.emplace_back(&HostPool::worker, this);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = fn;
+            arg_ = arg;
+            n_tasks_ = n;
+            next_ = 0;
+            pending_ = n;
+            ++generation_;
+        }
+        cv_work_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        drain(lk);                                             // the caller works too
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+        n_tasks_ = 0;
+    }
+
+    int n_workers() {
+        std::lock_guard<std::mutex> serial(run_mutex_);
+        return (int)workers_.size();
+    }
+
+  private:
+    static constexpr int kMaxWorkers = 15;
+    HostPool() : pid_(getpid()) {}
+
+    // takes task indices until none is left; called and returns with the lock held
+    void drain(std::unique_lock<std::mutex> &lk) {
+        while (next_ < n_tasks_) {
+            const int t = next_++;
+            vlgp_host_task fn = fn_;
+            void *arg = arg_;
+            lk.unlock();
+            fn(t, arg);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+
+    void worker() {
+        std::unique_lock<std::mutex> lk(m_);
+        uint64_t seen = 0;
+        for (;;) {
+            cv_work_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            drain(lk);
+        }
+    }
+
+    void reset_after_fork() {
+        // the parent's worker threads do not exist in this process: forget them (their std::thread objects must not be
+        // destroyed while joinable, so the vector is leaked) and start with fresh synchronisation state
+        new (&workers_) std::vector<std::thread>();
+        new (&m_) std::mutex();
+        new (&cv_work_) std::condition_variable();
+        new (&cv_done_) std::condition_variable();
+        fn_ = nullptr;
+        n_tasks_ = next_ = pending_ = 0;
+        pid_ = getpid();
+    }
+
+    std::mutex run_mutex_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    vlgp_host_task fn_ = nullptr;
+    void *arg_ = nullptr;
+    int n_tasks_ = 0, next_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    pid_t pid_;
+};
+
+}   // namespace
+
+void vlgp_host_parallel(int n, vlgp_host_task fn, void *arg) { HostPool::instance().run(n, fn, arg); }
+
+// Self-test of the pool (tests/test_abi.py): `rounds` calls with n_tasks tasks each; every task index of every call
+// must run exactly once and run() must not return before all of them have.  Returns 0 when that held, else the number
+// of violations; *workers (may be NULL) receives the number of pool threads afterwards.
+int vlgp_host_pool_selftest(int n_tasks, int rounds, int *workers) {
+    if (n_tasks < 0 || rounds < 0) return -1;
+    struct Ctx {
+        std::vector<std::atomic<int>> hits;
+        std::atomic<int64_t> sum{0};
+        explicit Ctx(int n) : hits(n) {}
+    };
+    int bad = 0;
+    for (int r = 0; r < rounds; ++r) {
+        Ctx c(n_tasks);
+        for (auto &h : c.hits) h.store(0);
+        vlgp_host_parallel(
+            n_tasks,
+            [](int t, void *a) {
+                Ctx *cx = static_cast<Ctx *>(a);
+                cx->hits[t].fetch_add(1);
+                volatile double x = 1.0;                      // a little work so that the tasks overlap in time
+                for (int i = 0; i < 200 * (1 + t % 3); ++i) x = x * 1.0000001 + 1e-9;
+                cx->sum.fetch_add(t + 1);
+            },
+            &c);
+        for (int t = 0; t < n_tasks; ++t)
+            if (c.hits[t].load() != 1) ++bad;
+        if (c.sum.load() != (int64_t)n_tasks * (n_tasks + 1) / 2) ++bad;
+    }
+    if (workers) *workers = HostPool::instance().n_workers();
+    return bad;
 }
