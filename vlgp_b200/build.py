@@ -36,9 +36,22 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(h) for h in hdrs)
 
 
+def _extra_flags():
+    """Extra compiler flags from VLGP_NVCC_DEFINES (e.g. "-DVLGP_ESTEP_TWO_BINS -DVLGP_ESTEP_A2_FROM_SMEM": the A/B
+    build options described in DESIGN.md section 8).  A change of flags rebuilds every object."""
+    return [f for f in os.environ.get("VLGP_NVCC_DEFINES", "").split() if f.startswith("-D")]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = nvcc_path()
     os.makedirs(OBJ, exist_ok=True)
+    extra = _extra_flags()
+    stamp = os.path.join(OBJ, "flags.txt")
+    prev = open(stamp).read() if os.path.exists(stamp) else ""
+    if prev != " ".join(extra):
+        force = True
+        with open(stamp, "w") as f:
+            f.write(" ".join(extra))
     hdr_m = _deps_mtime()
     jobs = []
     objs = []
@@ -47,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

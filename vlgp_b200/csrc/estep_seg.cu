@@ -45,7 +45,11 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     p.a = ctx->d_a; p.b = ctx->d_b; p.noise = ctx->d_noise; p.poisson = ctx->d_poisson;
     p.n_iter = n_iter; p.dmu_bound = dmu_bound; p.method_vb = method_vb; p.flags = ctx->d_flags;
     p.skip = getenv("VLGP_DEBUG_SKIP") ? atoi(getenv("VLGP_DEBUG_SKIP")) : 0;
+#ifdef VLGP_ESTEP_TWO_BINS
+    p.tpb = NT / ((W + 1) / 2);          // threads per PAIR of bins (estep_seg_impl.cuh: rate_pass_two_bins)
+#else
     p.tpb = NT / W;
+#endif
     if (p.tpb < 1) return VLGP_OK;
     if (p.tpb > N) p.tpb = N;
     p.chunk = (N + p.tpb - 1) / p.tpb;

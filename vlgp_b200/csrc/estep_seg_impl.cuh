@@ -102,11 +102,80 @@ __device__ __forceinline__ double2 load_a(const double2 *aa, int idx) {
 }
 
 // One rate pass over the segment.  STAGE 1: part <- partial sums of resid * a_l ; STAGE 2: of U * a_l^2.
+#ifdef VLGP_ESTEP_TWO_BINS
+// Build option (not the default; never run on a GPU yet): every thread works on TWO consecutive bins, so that each
+// fetch of the loading from shared memory is used twice and the two bins give the scheduler two independent Horner
+// chains.  Static facts (ptxas, L = 5): at the 128-register budget this needs no spills and the chains stay
+// interleaved (longest run of dependent DFMA: 5 / 2 in the two passes, against 13 in the one-bin form at 80 registers),
+// 8 LDS + 77 FP64-pipe instructions per two (bin, neuron) items instead of 14 + 82 -- at 2 CTAs per SM instead of 3.
+// Here p.tpb is the number of threads per bin PAIR (estep_seg.cu).
+template <int LT, int STAGE>
+__device__ __forceinline__ void rate_pass_two_bins(const SegArgs &p, const Smem<LT> &s) {
+    const int tid = threadIdx.x;
+    const int tp = tid / p.tpb, k = tid - tp * p.tpb;
+    const int t = 2 * tp;
+    if (t < p.W) {
+        const int N = p.N;
+        const bool two = t + 1 < p.W;
+        const int t1 = two ? t + 1 : t;            // an odd last bin is computed twice and stored once
+        double muA[LT], vA[LT], accA[LT], muB[LT], vB[LT], accB[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            muA[l] = s.mu[t * LT + l];
+            vA[l] = s.v[t * LT + l];
+            muB[l] = s.mu[t1 * LT + l];
+            vB[l] = s.v[t1 * LT + l];
+            accA[l] = accB[l] = 0.0;
+        }
+        const double2 *aa = (const double2 *)s.a;
+        const double2 *bb = (const double2 *)s.b;
+        const uint8_t *yA = s.ys + t * N, *yB = s.ys + t1 * N;
+        for (int n = k; n < N; n += p.tpb) {
+            double al[LT], sq[LT];
+            const double bn = bb[n].x;
+            double etaA = bn, etaB = bn, hA = 0.0, hB = 0.0;
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                const double2 pp = load_a(aa, l * N + n);
+                al[l] = pp.x;
+                sq[l] = pp.y;
+                etaA = fma(muA[l], pp.x, etaA);
+                etaB = fma(muB[l], pp.x, etaB);
+                hA = fma(vA[l], pp.y, hA);
+                hB = fma(vB[l], pp.y, hB);
+            }
+            double rA, rB;
+            trunc_exp2(fma(0.5, hA, etaA), fma(0.5, hB, etaB), rA, rB);
+            const double cA = (STAGE == 1) ? (double)yA[n] - rA : rA;
+            const double cB = (STAGE == 1) ? (double)yB[n] - rB : rB;
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                const double x = (STAGE == 1) ? al[l] : sq[l];
+                accA[l] = fma(cA, x, accA[l]);
+                accB[l] = fma(cB, x, accB[l]);
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            s.part[(k * p.W + t) * LT + l] = accA[l];
+            if (two) s.part[(k * p.W + t + 1) * LT + l] = accB[l];
+        }
+    }
+}
+#endif
+
 template <int LT, int STAGE, bool FAST>
 __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, int64_t bin0) {
     const int tid = threadIdx.x;
+#ifdef VLGP_ESTEP_TWO_BINS
+    if (FAST) {
+        rate_pass_two_bins<LT, STAGE>(p, s);
+    } else
+    for (int t = 2 * (tid / p.tpb), k = tid % p.tpb, tend = min(t + 2, p.W); t < tend; ++t) {
+#else
     const int t = tid / p.tpb, k = tid - t * p.tpb;
     if (t < p.W) {
+#endif
         const int N = p.N;
         double mu_t[LT], v_t[LT], acc[LT];
 #pragma unroll
@@ -545,7 +614,11 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
 }
 
 template <int LT, int NBMAX, bool FAST>
+#ifdef VLGP_ESTEP_TWO_BINS
+__global__ void __launch_bounds__(NT, 2) estep_seg_kernel(SegArgs p) {
+#else
 __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(SegArgs p) {
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<LT> s(smem_raw, p);
     __shared__ int bad[VLGP_MAX_L];
