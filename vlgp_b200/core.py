@@ -18,7 +18,7 @@ import weakref
 
 import numpy as np
 
-from .engine import Engine, TrialSet, get_engine, pack_y, _fastpack
+from .engine import Engine, TrialSet, get_engine, _fastpack
 from .util import assign_inplace
 
 __all__ = ["vem", "estep", "mstep", "hstep", "infer", "update_w", "update_v", "constrain_loading", "constrain_latent",
