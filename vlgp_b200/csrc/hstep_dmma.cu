@@ -18,7 +18,7 @@ namespace {
 constexpr int WARPS = 4;
 
 
-template <int NB>
+template <int NB, bool HALF_LAST>
 __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBatch eb, int nseg, int W, int L, double dt,
                                                                         const double *__restrict__ w,
                                                                         double *__restrict__ partall) {
@@ -78,23 +78,33 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
             }
         }
         // ---- blocked symmetric sweep -> tiles hold -B^-1 ----------------------------------------------------------
+        // When at most four rows of the LAST block are real (W = 50: rows 48, 49), columns 4..7 of that pivot block are
+        // identity padding: the off-diagonal tiles of its block column are exactly zero there, so the second k4 half of
+        // every product of the last sweep step adds exact zeros and is left out (27 of 378 DMMA and their operand
+        // shuffles at NB = 7; results unchanged bit for bit).  HALF_LAST = (W - 8 (NB - 1) <= 4), chosen by the launcher.
         bool ok = true;
 #pragma unroll
         for (int kb = 0; kb < NB; ++kb) {
+            const bool hi = !(kb == NB - 1 && HALF_LAST);       // compile-time: kb is unrolled
             Tile P = A[tix(kb, kb)];
             ok = tile_spd_inverse(P, lane) && ok;
-            const double Pt0 = tform(P, 0, lane), Pt1 = tform(P, 1, lane);
-            const double Pn0 = nform(P, 0, lane), Pn1 = nform(P, 1, lane);
+            const double Pt0 = tform(P, 0, lane), Pn0 = nform(P, 0, lane);
+            double Pt1 = 0.0, Pn1 = 0.0;
+            if (hi) {
+                Pt1 = tform(P, 1, lane);
+                Pn1 = nform(P, 1, lane);
+            }
             double V0[NB], V1[NB];            // operand form of the OLD block column A_{m,kb} (rows = block m)
 #pragma unroll
             for (int m = 0; m < NB; ++m) {
                 if (m == kb) continue;
+                V1[m] = 0.0;
                 if (m > kb) {
                     V0[m] = nform(A[tix(m, kb)], 0, lane);
-                    V1[m] = nform(A[tix(m, kb)], 1, lane);
+                    if (hi) V1[m] = nform(A[tix(m, kb)], 1, lane);
                 } else {
                     V0[m] = tform(A[tix(kb, m)], 0, lane);
-                    V1[m] = tform(A[tix(kb, m)], 1, lane);
+                    if (hi) V1[m] = tform(A[tix(kb, m)], 1, lane);
                 }
             }
 #pragma unroll
@@ -103,30 +113,30 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
                 Tile T{0.0, 0.0};
                 if (m > kb) {
                     dmma(T, V0[m], Pt0);
-                    dmma(T, V1[m], Pt1);
+                    if (hi) dmma(T, V1[m], Pt1);
                     A[tix(m, kb)] = T;
                 } else {
                     dmma(T, Pn0, V0[m]);
-                    dmma(T, Pn1, V1[m]);
+                    if (hi) dmma(T, Pn1, V1[m]);
                     A[tix(kb, m)] = T;
                 }
             }
 #pragma unroll
             for (int i = 0; i < NB; ++i) {    // A_ij -= (A_ik P) A_kj
                 if (i == kb) continue;
-                double T0, T1;
+                double T0, T1 = 0.0;
                 if (i > kb) {
                     T0 = -nform(A[tix(i, kb)], 0, lane);
-                    T1 = -nform(A[tix(i, kb)], 1, lane);
+                    if (hi) T1 = -nform(A[tix(i, kb)], 1, lane);
                 } else {
                     T0 = -tform(A[tix(kb, i)], 0, lane);
-                    T1 = -tform(A[tix(kb, i)], 1, lane);
+                    if (hi) T1 = -tform(A[tix(kb, i)], 1, lane);
                 }
 #pragma unroll
                 for (int j = 0; j <= i; ++j) {
                     if (j == kb) continue;
                     dmma(A[tix(i, j)], T0, V0[j]);
-                    dmma(A[tix(i, j)], T1, V1[j]);
+                    if (hi) dmma(A[tix(i, j)], T1, V1[j]);
                 }
             }
             A[tix(kb, kb)].x = -P.x;
@@ -164,26 +174,32 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
     }
 }
 
-template <int NB>
-int launch_t(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
+template <int NB, bool HALF_LAST>
+int launch_th(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
     constexpr int NT = NB * (NB + 1) / 2;
     const size_t smem = (size_t)2 * NT * 32 * sizeof(double2) + WARPS * 64 * sizeof(double);
     const int S = ts->n_trials;
     if (ts->dmma_grid == 0) {
         if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(hstep_segment_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CK(cudaFuncSetAttribute(hstep_segment_dmma_kernel<NB, HALF_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
         int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_dmma_kernel<NB>, WARPS * 32, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_dmma_kernel<NB, HALF_LAST>, WARPS * 32, smem));
         if (per_sm < 1) per_sm = 1;
         ts->dmma_grid = per_sm * ctx->prop.multiProcessorCount;
         if (ts->dmma_grid > (S + WARPS - 1) / WARPS) ts->dmma_grid = (S + WARPS - 1) / WARPS;
     }
     const int grid = ts->dmma_grid;
-    hstep_segment_dmma_kernel<NB><<<dim3(grid, eb.n), WARPS * 32, smem, ctx->stream>>>(eb, S, ts->max_len, ctx->L, ctx->dt,
+    hstep_segment_dmma_kernel<NB, HALF_LAST><<<dim3(grid, eb.n), WARPS * 32, smem, ctx->stream>>>(eb, S, ts->max_len, ctx->L, ctx->dt,
                                                                                       ts->d_w, ts->d_hpart);
     CKL();
     return VLGP_OK;
+}
+
+template <int NB>
+int launch_t(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
+    // at most four real rows in the last 8-row block: the second half of the last sweep step is all padding
+    return ts->max_len - 8 * (NB - 1) <= 4 ? launch_th<NB, true>(ctx, ts, eb) : launch_th<NB, false>(ctx, ts, eb);
 }
 
 }   // namespace
