@@ -54,3 +54,37 @@ def test_run_ours_prints_exactly_one_json_line_with_the_contract_keys(tmp_path):
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}        # no GPU here: the values are None
     assert "workload" in d["config"] and "cpu_baseline" not in d            # --no-cpu
+
+
+REF_DRIVER = r"""
+import sys, types
+sys.path.insert(0, {root!r})
+import bench
+from vlgp_b200 import synth
+synth.CONFIGS["tiny"] = dict(n_trials=3, T=100, N=6, L=2, dtype="f64")
+args = types.SimpleNamespace(gpus=1, steps=1, warmup=0, impl="reference", config="tiny", cpu_sample_trials=2, no_cpu=False)
+bench.run_reference(args)
+"""
+
+
+def test_reference_arm_prints_one_json_line_with_its_keys(tmp_path):
+    """`bench.py --impl reference` needs no GPU at all: the oracle port on a bounded sample, scaled to the workload; the
+    line carries impl / cpu_baseline (kind, cores, sample, both BLAS pool sizes tried) / e2e with zero copy bytes."""
+    script = tmp_path / "drive_ref.py"
+    script.write_text(REF_DRIVER.format(root=ROOT))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", RANK="0")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "EM-iterations/sec" and d["gpu_launches"] == 0
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "2 of 3 trials" in cb["sample"] and cb["value"] == d["value"]
+    assert set(cb["blas_threads_tried"]) >= {"1"} and len(cb["blas_threads_tried"]) == 2
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 print nothing and exit 0
+    r2 = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120, cwd=str(tmp_path),
+                        env=dict(env, RANK="1"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
