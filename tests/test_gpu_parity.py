@@ -510,6 +510,12 @@ def test_vem_option_branches_golden(vl, case):
     core.vem(segs, params, cfg)
     assert cfg["runtime"]["it"] == int(g[p + "n_it"])
     tol = 5e-4 if cfg["Hstep"] else 1e-8      # with the H-step: L-BFGS-B end point + pivot ties of the new factor
+    if cfg["method"] == "MAP":
+        # without the variance term the Newton iteration on the posterior mean amplifies rounding differences by about
+        # 1e3 per EM iteration on this kind of data (CPU against CPU: reference vs NumPy port 4e-14 / 5e-11 / 6e-8 after
+        # 1 / 2 / 3 iterations, scripts/fuzz_options_vs_reference.py), so last-digit differences of the device arithmetic
+        # do not stay at 1e-13
+        tol = max(tol, 1e-6)
     assert relerr(params["omega"], g[p + "out_omega"]) < 1e-4
     for k in ("a", "b"):
         assert relerr(params[k], g[p + "out_" + k]) < tol, k
