@@ -181,3 +181,22 @@ def test_fit_on_overlapping_aliased_windows_matches_the_reference(monkeypatch, c
     for k in ("mu", "v", "w"):
         assert relerr(np.concatenate([t[k] for t in trials]), g[p + k]) < 1e-9, k
     assert any(n == "estep" and isinstance(d, tuple) for n, d in eng.log)          # the level-by-level E-step ran
+
+
+def test_hstep_on_unequal_lengths_raises_like_the_reference(monkeypatch):
+    """window=None keeps the trials uncut; with the H-step on the reference stacks their mu / w (vlgp/gp.py:77-80) and
+    numpy raises ValueError for unequal lengths.  Same exception type here, before anything is launched; with
+    Hstep=False the same call goes through (the E- and M-step take any lengths)."""
+    import vlgp_b200 as vlgp
+    from vlgp_b200.synth import make_trials
+
+    install(monkeypatch)
+    trials = make_trials(1, 80, 6, 2, seed=1) + make_trials(1, 120, 6, 2, seed=2)
+    np.random.seed(0)
+    with pytest.raises(ValueError, match="same shape"):
+        vlgp.fit(trials, 2, max_iter=1, min_iter=1, window=None)
+    install(monkeypatch)
+    trials = make_trials(1, 80, 6, 2, seed=1) + make_trials(1, 120, 6, 2, seed=2)
+    np.random.seed(0)
+    res = vlgp.fit(trials, 2, max_iter=1, min_iter=1, window=None, Hstep=False)
+    assert res["config"]["runtime"]["it"] == 1 and [t["mu"].shape for t in trials] == [(80, 2), (120, 2)]
