@@ -46,6 +46,10 @@ def blas_threads(n):
             import scipy.optimize  # noqa: F401
 
             _BLAS_CONTROLLER = ThreadpoolController()
+        # a cap only ever LOWERS the pool: a process started with OPENBLAS_NUM_THREADS=1 stays at one thread
+        current = [lib.num_threads for lib in _BLAS_CONTROLLER.lib_controllers if lib.user_api == "blas"]
+        if not current or max(current) <= int(n):
+            return contextlib.nullcontext()
         return _BLAS_CONTROLLER.limit(limits=int(n), user_api="blas")
     except Exception:  # pragma: no cover - threadpoolctl missing or an unknown BLAS: run unthrottled
         return contextlib.nullcontext()
