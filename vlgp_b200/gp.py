@@ -260,7 +260,8 @@ def _optimize_dev_impl(s, params, config):
     sigma = np.array(params["sigma"], dtype=float)
     omega = np.array(params["omega"], dtype=float)
     gp_noise = params["gp_noise"]
-    if len(set(np.asarray(ts.lengths).tolist())) > 1:
+    lengths = getattr(ts, "lengths", None)
+    if lengths is not None and len(set(np.asarray(lengths).tolist())) > 1:
         # the reference stacks the segments' mu / w (vlgp/gp.py:77-80): unequal lengths end in numpy's ValueError there
         raise ValueError("all input arrays must have the same shape")
     ts.hstep_prepare()
