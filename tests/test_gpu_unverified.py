@@ -216,10 +216,10 @@ def test_unverified_device_code_in_a_child_process():
            "-k", "estep_subset_touches or row_operations or copy_rows or aliased or dealiased or option_branches_golden or "
                  "transform_new_trials_golden"]
     try:
-        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
         out, code = r.stdout + "\n" + r.stderr, r.returncode
     except subprocess.TimeoutExpired as e:
-        out, code = "TIMEOUT after 600 s\n%s" % (e.stdout or ""), -1
+        out, code = "TIMEOUT after 420 s\n%s" % (e.stdout or ""), -1
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "unverified_tests.log"), "w") as f:
