@@ -201,6 +201,16 @@ __device__ __forceinline__ double warp_sum(double x) {
 // degree-13 Taylor polynomial in Horner form (truncation 4e-18), scaling by 2^t through the exponent field.
 // Maximum error 1 ulp on [-708, 10] (checked against numpy.exp on 4e6 points, scripts/check_exp.py).  Arguments
 // below -708 are clamped: the result is then 3e-308 instead of a denormal/0, an absolute difference of 3e-308.
+//
+// The Taylor coefficients 1/13! .. 1/2!, 1 live in constant memory: written as literals, ptxas re-materialised every one
+// of them with two UMOV per loop iteration (24 of the 156 instructions of the E-step's two-neuron rate-pass body, as
+// many in the M-step kernel); from the constant bank they are loaded into uniform registers once, outside the loops
+// (136 instructions; same FP64 instructions in the same order, so results are unchanged bit for bit).
+static __constant__ double VLGP_EXP_C[13] = {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08,
+                                             2.755731922398589e-07,  2.7557319223985893e-06, 2.48015873015873e-05,
+                                             1.984126984126984e-04,  1.388888888888889e-03,  8.333333333333333e-03,
+                                             4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0};
+
 __device__ __forceinline__ double trunc_exp(double x) {
     x = x > 10.0 ? 10.0 : x;                                       // plain compare-select: no NaN-propagating min/max
     x = x < -708.0 ? -708.0 : x;
@@ -210,26 +220,17 @@ __device__ __forceinline__ double trunc_exp(double x) {
     const double t = tmp - shift;
     double r = fma(t, -6.93147180369123816490e-01, x);             // ln2 high part
     r = fma(t, -1.90821492927058770002e-10, r);                    // ln2 low part
-    double p = 1.6059043836821613e-10;                             // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                           // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                          // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                          // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                         // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                           // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                          // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                          // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                          // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                         // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                         // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
+    double p = VLGP_EXP_C[0];                                      // 1/13!
+#pragma unroll
+    for (int k = 1; k < 13; ++k) p = fma(p, r, VLGP_EXP_C[k]);     // 1/12! ... 1/2!, 1
     p = fma(p, r, 1.0);
     return p * __hiloint2double((ti + 1023) << 20, 0);             // 2^t, t in [-1022, 15]
 }
 
 // Two independent evaluations with their Horner chains interleaved statement by statement (the polynomial is a chain
-// of 14 dependent DFMAs; two chains in flight double the FP64-pipe utilisation of a warp).  Bitwise identical to two
-// calls of trunc_exp.
+// of 14 dependent DFMAs; two chains in flight double the FP64-pipe utilisation of a warp -- when ptxas keeps them
+// interleaved, which it does not under an 80-register cap).  Bitwise identical to two calls of
+// trunc_exp.
 __device__ __forceinline__ void trunc_exp2(double x0, double x1, double &e0, double &e1) {
     x0 = x0 > 10.0 ? 10.0 : x0;
     x1 = x1 > 10.0 ? 10.0 : x1;
@@ -242,24 +243,14 @@ __device__ __forceinline__ void trunc_exp2(double x0, double x1, double &e0, dou
     double r0 = fma(t0, -6.93147180369123816490e-01, x0), r1 = fma(t1, -6.93147180369123816490e-01, x1);
     r0 = fma(t0, -1.90821492927058770002e-10, r0);
     r1 = fma(t1, -1.90821492927058770002e-10, r1);
-    double p0 = 1.6059043836821613e-10, p1 = 1.6059043836821613e-10;
-#define VLGP_EXP_STEP(c)  \
-    p0 = fma(p0, r0, c);  \
-    p1 = fma(p1, r1, c);
-    VLGP_EXP_STEP(2.08767569878681e-09)
-    VLGP_EXP_STEP(2.505210838544172e-08)
-    VLGP_EXP_STEP(2.755731922398589e-07)
-    VLGP_EXP_STEP(2.7557319223985893e-06)
-    VLGP_EXP_STEP(2.48015873015873e-05)
-    VLGP_EXP_STEP(1.984126984126984e-04)
-    VLGP_EXP_STEP(1.388888888888889e-03)
-    VLGP_EXP_STEP(8.333333333333333e-03)
-    VLGP_EXP_STEP(4.1666666666666664e-02)
-    VLGP_EXP_STEP(1.6666666666666666e-01)
-    VLGP_EXP_STEP(0.5)
-    VLGP_EXP_STEP(1.0)
-    VLGP_EXP_STEP(1.0)
-#undef VLGP_EXP_STEP
+    double p0 = VLGP_EXP_C[0], p1 = VLGP_EXP_C[0];
+#pragma unroll
+    for (int k = 1; k < 13; ++k) {
+        p0 = fma(p0, r0, VLGP_EXP_C[k]);
+        p1 = fma(p1, r1, VLGP_EXP_C[k]);
+    }
+    p0 = fma(p0, r0, 1.0);
+    p1 = fma(p1, r1, 1.0);
     e0 = p0 * __hiloint2double((i0 + 1023) << 20, 0);
     e1 = p1 * __hiloint2double((i1 + 1023) << 20, 0);
 }
