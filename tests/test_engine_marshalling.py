@@ -121,7 +121,7 @@ def test_latent_affine_rows_arguments(ts):
 
 def test_row_ops_switch(ts, monkeypatch):
     monkeypatch.delenv("VLGP_ALIASED_WINDOWS", raising=False)
-    assert ts.row_ops is False
+    assert ts.row_ops is True                                        # the reference's aliased semantics are the default
     monkeypatch.setenv("VLGP_ALIASED_WINDOWS", "0")
     assert ts.row_ops is False
     monkeypatch.setenv("VLGP_ALIASED_WINDOWS", "1")

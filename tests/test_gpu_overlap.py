@@ -1,23 +1,10 @@
-"""GPU tests of device code written AFTER this round's GPU minutes were spent.
-
-Everything here compiles and is exercised on the CPU as far as the host side goes, but has never run on a GPU, so it is
-kept off the default product path (opt-in environment switches) and off the default GPU suite:
-
-  * the tests below marked ``unverified`` run in-process only with VLGP_UNVERIFIED_TESTS=1;
-  * ``test_unverified_device_code_in_a_child_process`` (always part of ``-m gpu``) runs exactly those tests -- and the
-    guarded ones of tests/test_gpu_parity.py -- in a CHILD interpreter, so that a fault in unverified kernels cannot take
-    the CUDA context of the verified suite with it.  It passes when the child passes and reports an expected failure
-    (with the tail of the child's log; full log under gpurun_out/) when it does not: the verified suite stays green and
-    the outcome is still recorded.  Once they have passed on a B200: drop the guards, make the switches default.
-
-Covered: the three row-level operations behind the reference's in-place semantics of OVERLAPPING windows
+"""GPU tests of the row-level device operations behind the reference's in-place semantics of OVERLAPPING windows
 (vlgp_estep_subset, vlgp_trials_copy_rows, vlgp_latent_affine_rows; vlgp/util.py:482-498, vlgp/core.py:96-97,112,
 123-126,384-389,414-416) and whole fits through them against the reference's own outputs (tests/golden/fit_overlap.npz).
+The aliased path is the default; VLGP_ALIASED_WINDOWS=0 switches it off (independent copies of the shared bins).
 """
 import copy
 import os
-import subprocess
-import sys
 
 import numpy as np
 import pytest
@@ -25,10 +12,6 @@ import pytest
 from conftest import ROOT, load_golden, relerr
 
 pytestmark = pytest.mark.gpu
-
-unverified = pytest.mark.skipif(not os.environ.get("VLGP_UNVERIFIED_TESTS"),
-                                reason="not yet run on a GPU: VLGP_UNVERIFIED_TESTS=1 (run in a child process by "
-                                       "test_unverified_device_code_in_a_child_process)")
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +42,6 @@ def _filled_set(eng, rng, lengths, N, L):
     return ts
 
 
-@unverified
 @pytest.mark.parametrize("lengths", [[50] * 23, [50, 120, 64, 200, 50, 77]], ids=["segments", "ragged"])
 def test_estep_subset_touches_only_the_listed_members(eng, lengths):
     """estep(subset=s) gives, on the listed members, bit for bit what the E-step over the whole set gives (members are
@@ -91,7 +73,6 @@ def test_estep_subset_touches_only_the_listed_members(eng, lengths):
             assert np.array_equal(got[k], ref[k]), k
 
 
-@unverified
 def test_row_operations_argument_errors(eng):
     from vlgp_b200._lib import VlgpNativeError
 
@@ -113,7 +94,6 @@ def test_row_operations_argument_errors(eng):
         ts.latent_affine(np.ones(2), None, rows=[])
 
 
-@unverified
 def test_copy_rows_and_affine_rows_against_numpy(eng):
     rng = np.random.default_rng(2)
     N, L = 9, 4
@@ -165,14 +145,13 @@ def _make_golden_module():
     return mod
 
 
-@unverified
 @pytest.mark.parametrize("case", ["latent_both_no_hstep", "row_norm_loading", "default"])
 def test_fit_on_overlapping_aliased_windows_matches_the_reference(eng, monkeypatch, case):
     """Whole fit() on trial lengths 130 / 175 / 100 / 262 (windows overlap) against the REFERENCE's own outputs, with the
     device row operations switched on.  CPU twin: tests/test_host_orchestration.py (same host code over the oracle)."""
     import vlgp_b200 as vlgp
 
-    monkeypatch.setenv("VLGP_ALIASED_WINDOWS", "1")
+    monkeypatch.delenv("VLGP_ALIASED_WINDOWS", raising=False)
     mg = _make_golden_module()
     g = load_golden("fit_overlap")
     trials = mg.fit_overlap_trials()
@@ -190,43 +169,15 @@ def test_fit_on_overlapping_aliased_windows_matches_the_reference(eng, monkeypat
         assert relerr(np.concatenate([t[k] for t in trials]), g[p + k]) < tol, k
 
 
-@unverified
 def test_dealiased_run_differs_from_the_reference(eng, monkeypatch):
     """The switch matters: with independent copies of the shared bins the same fit is percent-level off the reference
      -- guards against the aliased path silently not being taken in the test above."""
     import vlgp_b200 as vlgp
 
-    monkeypatch.delenv("VLGP_ALIASED_WINDOWS", raising=False)
+    monkeypatch.setenv("VLGP_ALIASED_WINDOWS", "0")
     mg = _make_golden_module()
     g = load_golden("fit_overlap")
     trials = mg.fit_overlap_trials()
     np.random.seed(0)
     vlgp.fit(trials, 2, **copy.deepcopy(mg.FIT_OVERLAP_CASES["latent_both_no_hstep"]))
     assert relerr(np.concatenate([t["mu"] for t in trials]), g["latent_both_no_hstep/mu"]) > 1e-4
-
-
-# ----------------------------------------------------------------------------------------------------------------------
-def test_unverified_device_code_in_a_child_process():
-    if os.environ.get("VLGP_UNVERIFIED_TESTS"):
-        pytest.skip("already running the guarded tests in this process")
-    env = dict(os.environ, VLGP_UNVERIFIED_TESTS="1")
-    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider",
-           os.path.join(ROOT, "tests", "test_gpu_unverified.py"),
-           os.path.join(ROOT, "tests", "test_gpu_parity.py"),
-           "-k", "estep_subset_touches or row_operations or copy_rows or aliased or dealiased or option_branches_golden or "
-                 "transform_new_trials_golden"]
-    try:
-        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=420)
-        out, code = r.stdout + "\n" + r.stderr, r.returncode
-    except subprocess.TimeoutExpired as e:
-        out, code = "TIMEOUT after 420 s\n%s" % (e.stdout or ""), -1
-    try:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "unverified_tests.log"), "w") as f:
-            f.write(out)
-    except OSError:
-        pass
-    print(out[-4000:])
-    if code != 0:
-        pytest.xfail("guarded tests of not-yet-verified device code failed in the child (exit %d): %s"
-                     % (code, out.strip().splitlines()[-1] if out.strip() else ""))

@@ -491,9 +491,6 @@ VEM_OPTION_CASES = {
 }
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("VLGP_UNVERIFIED_TESTS"),
-                    reason="written after this round's GPU minutes were spent: run once with VLGP_UNVERIFIED_TESTS=1, "
-                           "then drop the guard")
 @pytest.mark.parametrize("case", sorted(VEM_OPTION_CASES))
 def test_vem_option_branches_golden(vl, case):
     """Two vem iterations against the reference's outputs (tests/golden/vem_options.npz) under the options the default
@@ -523,9 +520,6 @@ def test_vem_option_branches_golden(vl, case):
         assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("VLGP_UNVERIFIED_TESTS"),
-                    reason="written after this round's GPU minutes were spent: run once with VLGP_UNVERIFIED_TESTS=1, "
-                           "then drop the guard")
 def test_transform_new_trials_golden(vl):
     """fit(Hstep=False) then transform() of three trials the model has not seen, against the reference
     (tests/golden/api_extras.npz).  transform() starts from FactorAnalysis.transform evaluated with the FITTED loading

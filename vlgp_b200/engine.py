@@ -379,11 +379,11 @@ class TrialSet:
     # -- steps -----------------------------------------------------------------------------------------------------------
     @property
     def row_ops(self):
-        """True when the host may drive the reference's in-place semantics of OVERLAPPING windows through
-        ``estep(subset=)``, ``copy_rows`` and ``latent_affine(rows=)`` (vlgp_b200/core.py::_Aliasing).  The three device
-        operations have not yet run on a GPU (written after this round's GPU minutes were spent), so they are opt-in:
-        VLGP_ALIASED_WINDOWS=1.  Without it overlapping windows are independent copies."""
-        return os.environ.get("VLGP_ALIASED_WINDOWS", "0") not in ("", "0")
+        """True when the host drives the reference's in-place semantics of OVERLAPPING windows through
+        ``estep(subset=)``, ``copy_rows`` and ``latent_affine(rows=)`` (vlgp_b200/core.py::_Aliasing): the default.
+        VLGP_ALIASED_WINDOWS=0 treats overlapping windows as independent copies instead (one batched E-step, last
+        writer wins on the shared bins -- NOT what the reference computes)."""
+        return os.environ.get("VLGP_ALIASED_WINDOWS", "1") not in ("", "0")
 
     def estep(self, n_iter, dmu_bound=5.0, method="VB", subset=None):
         """E-step on every member of the set, or on the listed members only (``subset``: indices, each once)."""
