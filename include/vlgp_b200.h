@@ -138,6 +138,26 @@ VLGP_API int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const d
 VLGP_API int vlgp_hstep_objective_batch(vlgp_ctx *ctx, int set_id, int n, const int32_t *latents, const double *hypers,
                                double *ll, double *dll, int32_t *info);
 
+/* The whole H-step optimisation of n_lat latents in one call: replaces the per-latent scipy L-BFGS-B runs of
+ * gp.optimize / gp.optimze1d (vlgp/gp.py:82-92,100-123).  Runs vlgp_hstep_prepare, then the restated L-BFGS-B
+ * (csrc/lbfgsb.cuh; scipy's defaults m = 10, factr = 1e7, pgtol = 1e-5, maxls = 20) of every latent in lockstep, one
+ * batched objective pass per round.  All vectors are in the optimiser's variables x = log(sigma^2, omega, eps):
+ * log_initial n_lat x 3, log_bounds 3 x 2 (lower, upper), mask 3 (gradient mask, the reference uses [0,1,0]),
+ * log_result n_lat x 3.  collapse_tol > 0 ends a line search whose whole bracket lies within that distance of its
+ * starting point (lbfgsb.cuh; 0 = the full scipy sequence).  Optional outputs: fval (minus ELBO at the result), nfev
+ * (evaluations the optimiser asked for), task (lbfgsb::Task termination code), n_rounds (batched device passes). */
+VLGP_API int vlgp_hstep_optimize(vlgp_ctx *ctx, int set_id, int n_lat, const int32_t *latents, const double *log_initial,
+                                 const double *log_bounds, const int32_t *mask, double collapse_tol, double *log_result,
+                                 double *fval, int32_t *nfev, int32_t *task, int32_t *n_rounds);
+/* The restated L-BFGS-B in reverse communication, context-free (no device): tests drive it next to scipy's setulb on
+ * identical objectives.  _advance: pass f, g at the x returned by the previous call (ignored on the first call); returns
+ * 1 when f, g are needed at x, 0 when finished (*task = termination code), < 0 on bad arguments. */
+VLGP_API int vlgp_lbfgsb_new(int n, const double *x0, const double *lower, const double *upper, double factr, double pgtol,
+                             int maxls, double collapse_tol, void **handle);
+VLGP_API int vlgp_lbfgsb_advance(void *handle, double f, const double *g, double *x, int *task);
+VLGP_API int vlgp_lbfgsb_info(void *handle, double *f, int *nfev, int *nit, int *n_collapsed);
+VLGP_API int vlgp_lbfgsb_free(void *handle);
+
 /* ---- constraints and convergence bookkeeping (vlgp/core.py:300-305,350-354,366-416) ------------------------------ */
 /* mu <- (mu - shift) @ M for every bin; shift (L) and M (L x L, row-major) may be NULL (0 / identity). */
 VLGP_API int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M);

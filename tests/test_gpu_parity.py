@@ -168,6 +168,39 @@ def test_hstep_whole_golden(vl):
     assert relerr(Gd @ Gd.transpose(0, 2, 1), g["G_after"] @ g["G_after"].transpose(0, 2, 1)) < 1e-5
 
 
+def test_hstep_native_optimizer_against_scipy_on_the_device_objective(vl, monkeypatch):
+    """vlgp_hstep_optimize (all L-BFGS-B rounds inside one native call, csrc/hstep_opt.cu) against scipy's own setulb
+    driven from Python (VLGP_HSTEP_SCIPY=1) on the SAME device objective: without the collapse rule the two must ask
+    for the same number of evaluations and end at the same point; with it (default, 1e-9) the end point stays within
+    1e-6 of scipy's (vlgp/gp.py:100-123) while the device rounds drop."""
+    from vlgp_b200 import core
+
+    g = load_golden("hstep")
+    n = g["mu"].shape[0]
+
+    def run(**cfg_kw):
+        segs = [dict(y=np.zeros((50, 2)), mu=g["mu"][i].copy(), w=g["w"][i].copy(), v=np.zeros((50, 2)))
+                for i in range(n)]
+        params = dict(a=np.zeros((2, 2)), b=np.zeros((1, 2)), noise=np.ones(2), omega=g["omega0"].copy(),
+                      sigma=np.ones(2), likelihood=np.array(["poisson"] * 2), zdim=2, ydim=2, xdim=1, rank=50,
+                      gp_noise=1e-4, dt=1)
+        cfg = _cfg()
+        cfg.update(cfg_kw)
+        core.hstep(segs, params, cfg)
+        return params["omega"].copy(), cfg["hstep_nfev"][-1], cfg.get("hstep_rounds", [None])[-1]
+
+    monkeypatch.setenv("VLGP_HSTEP_SCIPY", "1")
+    om_scipy, nf_scipy, _ = run()
+    monkeypatch.delenv("VLGP_HSTEP_SCIPY")
+    om_full, nf_full, rounds_full = run(hstep_collapse_tol=0.0)
+    om_def, nf_def, rounds_def = run()
+    assert list(nf_full) == list(nf_scipy)
+    assert relerr(np.log(om_full), np.log(om_scipy)) < 1e-12
+    assert np.max(np.abs(np.log(om_def) - np.log(om_scipy))) < 1e-6
+    assert rounds_def <= rounds_full <= max(nf_scipy)
+    assert relerr(om_def, g["omega_after"]) < 1e-6
+
+
 def test_update_w_v_and_long_trial_estep_golden(vl):
     from vlgp_b200 import core
     from vlgp_b200.gp import make_cholesky

@@ -466,6 +466,28 @@ class TrialSet:
                      "hstep_objective_batch")
         return ll, dll, info
 
+    def hstep_optimize(self, latents, initials, bounds, mask=(0, 1, 0), collapse_tol=1e-9):
+        """L-BFGS-B over log(sigma^2, omega, eps) of the listed latents, all rounds inside ONE native call
+        (vlgp_hstep_optimize; includes hstep_prepare).  ``initials``: (n, 3) and ``bounds``: (3, 2) in natural units, like
+        the reference passes them to optimze1d (vlgp/gp.py:83-90).  Returns (hyper (n, 3) natural units, fval (n,),
+        nfev (n,), task (n,), device rounds)."""
+        lib, ctx = self._lib()
+        lat = np.ascontiguousarray(latents, dtype=np.int32)
+        n = lat.size
+        x0 = as_f64(np.log(np.asarray(initials, dtype=np.float64)), (n, 3))
+        lb = as_f64(np.log(np.asarray(bounds, dtype=np.float64)), (3, 2))
+        mk = np.ascontiguousarray(mask, dtype=np.int32)
+        if mk.shape != (3,):
+            raise ValueError("mask must have 3 entries")
+        res, fval = np.empty((n, 3)), np.empty(n)
+        nfev, task = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        rounds = C.c_int32()
+        self.eng._ck(lib.vlgp_hstep_optimize(ctx, self.id, int(n), lat.ctypes.data_as(_lib.c_i32_p), dptr(x0), dptr(lb),
+                                             mk.ctypes.data_as(_lib.c_i32_p), float(collapse_tol), dptr(res), dptr(fval),
+                                             nfev.ctypes.data_as(_lib.c_i32_p), task.ctypes.data_as(_lib.c_i32_p),
+                                             C.byref(rounds)), "hstep_optimize")
+        return np.exp(res), fval, nfev, task, rounds.value
+
     def latent_affine(self, shift=None, M=None, rows=None):
         """mu <- (mu - shift) @ M on every bin, or on the listed bins only (``rows``: bin indices, each once)."""
         lib, ctx = self._lib()

@@ -246,6 +246,41 @@ def optimze1d(ts, latent, initial, bounds, mask, evaluate=None):
     return np.exp(x), fval, nfev
 
 
+def _optimize_scipy(ts, zdim, initials, bounds, mask):
+    """The H-step driven by scipy's own L-BFGS-B from Python (VLGP_HSTEP_SCIPY=1; also what an engine stand-in without
+    ``hstep_optimize`` gets): lockstep reverse communication, or threads / sequential ``minimize`` calls."""
+    ts.hstep_prepare()
+    results = [None] * zdim
+    lock = None
+    if not os.environ.get("VLGP_SEQUENTIAL_HSTEP") and not os.environ.get("VLGP_THREADED_HSTEP"):
+        lock = _lockstep_lbfgsb(ts, list(range(zdim)), initials, bounds, mask)
+    if lock is not None:
+        results = [(np.exp(x), f, nf) for x, f, nf in lock]
+    elif zdim > 1 and not os.environ.get("VLGP_SEQUENTIAL_HSTEP"):
+        ev = _LockstepEvaluator(ts, zdim)
+        errors = []
+
+        def run(l):
+            try:
+                results[l] = optimze1d(ts, l, initials[l], bounds, mask, evaluate=ev.evaluate)
+            except BaseException as e:  # noqa: BLE001
+                errors.append(e)
+            finally:
+                ev.retire()
+
+        threads = [threading.Thread(target=run, args=(l,), daemon=True) for l in range(zdim)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+    else:
+        for l in range(zdim):
+            results[l] = optimze1d(ts, l, initials[l], bounds, mask)
+    return results
+
+
 def _optimize_dev(s, params, config):
     from .util import blas_threads
 
@@ -264,38 +299,18 @@ def _optimize_dev_impl(s, params, config):
     if lengths is not None and len(set(np.asarray(lengths).tolist())) > 1:
         # the reference stacks the segments' mu / w (vlgp/gp.py:77-80): unequal lengths end in numpy's ValueError there
         raise ValueError("all input arrays must have the same shape")
-    ts.hstep_prepare()
     mask = np.array([0, 1, 0])
     bounds = ((1e-3, 1), config["omega_bound"], (gp_noise / 2, gp_noise * 2))
-    results = [None] * zdim
-    lock = None
-    if not os.environ.get("VLGP_SEQUENTIAL_HSTEP") and not os.environ.get("VLGP_THREADED_HSTEP"):
-        lock = _lockstep_lbfgsb(ts, list(range(zdim)), [(sigma[l] ** 2, omega[l], gp_noise) for l in range(zdim)],
-                                bounds, mask)
-    if lock is not None:
-        results = [(np.exp(x), f, nf) for x, f, nf in lock]
-    elif zdim > 1 and not os.environ.get("VLGP_SEQUENTIAL_HSTEP"):
-        ev = _LockstepEvaluator(ts, zdim)
-        errors = []
-
-        def run(l):
-            try:
-                results[l] = optimze1d(ts, l, (sigma[l] ** 2, omega[l], gp_noise), bounds, mask, evaluate=ev.evaluate)
-            except BaseException as e:  # noqa: BLE001
-                errors.append(e)
-            finally:
-                ev.retire()
-
-        threads = [threading.Thread(target=run, args=(l,), daemon=True) for l in range(zdim)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
+    initials = [(sigma[l] ** 2, omega[l], gp_noise) for l in range(zdim)]
+    if hasattr(ts, "hstep_optimize") and not any(os.environ.get(k) for k in (
+            "VLGP_HSTEP_SCIPY", "VLGP_SEQUENTIAL_HSTEP", "VLGP_THREADED_HSTEP")):
+        # default: every round of every latent's L-BFGS-B inside one native call (csrc/hstep_opt.cu, csrc/lbfgsb.cuh)
+        tol = config.get("hstep_collapse_tol", 1e-9)
+        hyper, fval, nf, _, rounds = ts.hstep_optimize(list(range(zdim)), initials, bounds, mask, tol if tol else 0.0)
+        results = [(hyper[l], float(fval[l]), int(nf[l])) for l in range(zdim)]
+        config.setdefault("hstep_rounds", []).append(int(rounds))
     else:
-        for l in range(zdim):
-            results[l] = optimze1d(ts, l, (sigma[l] ** 2, omega[l], gp_noise), bounds, mask)
+        results = _optimize_scipy(ts, zdim, initials, bounds, mask)
     nfev = []
     for l in range(zdim):
         (sigmasq, omega_new, _), _, nf = results[l]
