@@ -151,7 +151,8 @@ def workload_config(name, c, gpus):
     return {"workload": "%s: %d trials x T=%s x %d neurons x %d latents, Poisson, window=50 rank=50 Eniter=25 Mniter=25 "
                         "Hstep=True" % (name, c["n_trials"], T, c["N"], c["L"]),
             "segments": c["n_trials"] * (T // 50) if isinstance(T, int) else None,
-            "sharding": "trials over %d rank(s), NCCL allreduce of M-/H-step statistics" % gpus,
+            "sharding": "trials over %d rank(s), sum-allreduce of M-/H-step statistics (in-kernel over NVLink peer memory; "
+                        "NCCL when peers cannot be mapped)" % gpus,
             "l2": "256 MiB write between steps evicts the 126 MB L2 (inside the timed region, <0.1 ms/step)"}
 
 
@@ -283,6 +284,47 @@ def _emit(fd, line):
     os.write(fd, (json.dumps(line) + "\n").encode())
 
 
+def solo_parity(args, traj, n_iter):
+    """Correctness witness of a multi-rank run: rank 0 repeats the same n_iter EM iterations on ALL trials with a
+    private single-rank context (no communicator) and reports the relative differences of the loading, bias, omega and
+    the norm of the posterior means against what the N ranks arrived at after the timed steps."""
+    from vlgp_b200 import core, engine
+    from vlgp_b200.core import Session
+    from vlgp_b200.gp import make_cholesky
+
+    shared = engine._ENGINE
+    solo = engine.Engine(shared.device)
+    engine._ENGINE = solo
+    quiet, stdout = open(os.devnull, "w"), sys.stdout
+    sys.stdout = quiet
+    try:
+        trials, params, config, c = build_problem(args.config)
+        make_cholesky(trials, params, config)
+        core.update_w(trials, params, config)
+        core.update_v(trials, params, config)
+        segs = cut(trials, params, config)
+        make_cholesky(segs, params, config)
+        config["max_iter"] = config["min_iter"] = 1
+        with Session(segs, params) as s:
+            for _ in range(n_iter):
+                solo.flush_l2()
+                core._em_iteration(s, segs, params, config)
+                s.ts.norms()
+            mu_sq = float(s.ts.norms()[0])
+    finally:
+        sys.stdout = stdout
+        engine._ENGINE = shared
+        solo.close()
+
+    def rel(x, ref):
+        return float(np.max(np.abs(np.asarray(x) - np.asarray(ref))) / max(np.max(np.abs(ref)), 1e-300))
+
+    return {"vs": "single-rank run of the same %d EM iterations on rank 0 (private context, no communicator)" % n_iter,
+            "rel_diff_a": rel(traj["a"], params["a"]), "rel_diff_b": rel(traj["b"], params["b"]),
+            "rel_diff_omega": rel(traj["omega"], params["omega"]),
+            "rel_diff_mu_norm": abs(np.sqrt(traj["mu_sq"]) - np.sqrt(mu_sq)) / np.sqrt(mu_sq)}
+
+
 def run_ours(args):
     out_fd = _claim_stdout()
     from vlgp_b200 import core, dist
@@ -355,6 +397,9 @@ def run_ours(args):
         sys.stdout = stdout
     ms = float(eng.allreduce(np.array([ms]), op="max")[0])
     launches = c1["launches"] - c0["launches"]
+    # state after the timed steps, for the multi-rank correctness witness below
+    traj = {"a": np.array(params["a"], copy=True), "b": np.array(params["b"], copy=True),
+            "omega": np.array(params["omega"], copy=True), "mu_sq": float(s.ts.norms()[0])}
     # one more EM iteration outside the timed region with the H-step segment kernel and the M-step statistics kernel
     # timed individually (each timed launch adds a synchronisation, so this is kept out of `value`)
     sys.stdout = quiet
@@ -401,6 +446,9 @@ def run_ours(args):
 
     if rank != 0:
         return
+    parity = None
+    if world > 1:
+        parity = solo_parity(args, traj, args.warmup + args.steps)
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
     f_full, f_eff = estep_flops(S_local, W, N, L, ncols, config["Eniter"], params["rank"])
@@ -467,6 +515,8 @@ def run_ours(args):
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "api": "vlgp_b200.core.vem(splits, params, config) with host ndarrays"},
     }
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_cpu and args.gpus == 1:
         sec, nseg, _ = cpu_em_iteration_time(args.config, args.cpu_sample_trials, 1, 0)
         full_sec = sec * c["n_trials"] / args.cpu_sample_trials

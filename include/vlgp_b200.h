@@ -203,6 +203,13 @@ VLGP_API int vlgp_shm_allreduce(void *handle, double *buf, int n, int op);
 VLGP_API int vlgp_shm_close(void *handle, int unlink_name);
 VLGP_API int vlgp_comm_attach_shm(vlgp_ctx *ctx, void *handle);
 
+/* ---- in-kernel allreduce through peer memory (NVLink / NVSwitch; csrc/p2p.cuh) --------------------------------------
+ * Collective over the ranks (all on this node; needs the shared-memory handle attached): every rank allocates a mailbox,
+ * exports it with cudaIpcGetMemHandle and maps the peers'.  From then on the small device-side reductions (M-step
+ * statistics, H-step partial sums and moments) are exchanged by remote stores from inside the kernels that produce them
+ * instead of an NCCL launch in between.  *enabled = 0 (and nothing changes) when some rank cannot map some peer. */
+VLGP_API int vlgp_comm_enable_p2p(vlgp_ctx *ctx, int *enabled);
+
 /* ---- measurement helpers (used by bench.py only) ------------------------------------------------------------------ */
 /* Measured FP64 FMA peak (TFLOP/s) of this GPU with a register-resident DFMA loop, and with mma.sync.m8n8k4.f64. */
 VLGP_API int vlgp_peak_fp64(vlgp_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

@@ -79,6 +79,7 @@ EXPORTS = {
     "vlgp_shm_allreduce": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int]),
     "vlgp_shm_close": (C.c_int, [C.c_void_p, C.c_int]),
     "vlgp_comm_attach_shm": (C.c_int, [ctx_p, C.c_void_p]),
+    "vlgp_comm_enable_p2p": (C.c_int, [ctx_p, c_int_p]),
     "vlgp_host_f64_to_u8": (C.c_int, [c_double_p, C.POINTER(C.c_ubyte), C.c_int64]),
     "vlgp_host_pack_isa": (C.c_int, []),
     "vlgp_host_pool_selftest": (C.c_int, [C.c_int, C.c_int, c_int_p]),

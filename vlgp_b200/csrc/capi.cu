@@ -8,6 +8,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "p2p.cuh"
 #include "hostpack.h"
 #include "linalg.cuh"
 
@@ -1009,10 +1010,12 @@ struct StreamSwap {      // run a piece of host code with ctx->stream / ctx->com
     explicit StreamSwap(vlgp_ctx *x) : ctx(x), s(x->stream), c(x->comm) {
         ctx->stream = ctx->stream_m;
         if (ctx->comm_m) ctx->comm = ctx->comm_m;
+        ctx->p2p_chan = 1;
     }
     ~StreamSwap() {
         ctx->stream = s;
         ctx->comm = c;
+        ctx->p2p_chan = 0;
     }
 };
 
@@ -1024,7 +1027,7 @@ int vlgp_mstep_begin(vlgp_ctx *ctx, int set_id, int n_iter, int use_hessian, dou
     REQUIRE(!ctx->mstep_pending, "mstep_begin: the previous M-step has not been ended");
     if (n_iter < 1) return VLGP_OK;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->n_ranks > 1 && !ctx->comm_m) {        // no second communicator: run it here, in order, on the main stream
+    if (ctx->n_ranks > 1 && !ctx->comm_m && !ctx->p2p) {   // no second communicator / channel: in order, on the main stream
         CK(cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), ctx->stream));
         rc = vlgp_launch_mstep(ctx, ts, n_iter, use_hessian, eps, lr, da_bound, db_bound);
         if (rc) return rc;
@@ -1062,6 +1065,8 @@ int vlgp_mstep_end(vlgp_ctx *ctx, int *n_fallback) {
     CK(cudaSetDevice(ctx->device));
     int rc = settle_mstep(ctx);      // enqueue what is left, wait: whatever the host enqueues from here on sees a, b, noise
     ctx->mstep_pending = false;
+    if (rc) return rc;
+    rc = vlgp_p2p_check(ctx);
     if (rc) return rc;
     return read_flag(ctx, 1, n_fallback);
 }

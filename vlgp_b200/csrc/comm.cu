@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 struct NcclId {
     char internal[128];      // NCCL_UNIQUE_ID_BYTES
@@ -57,6 +58,9 @@ static int load_nccl(vlgp_ctx *ctx, const char *path) {
 
 int vlgp_allreduce_dev(vlgp_ctx *ctx, double *d_buf, size_t n, int op) {
     if (ctx->n_ranks <= 1 || n == 0) return VLGP_OK;
+    // peer-memory mailboxes when enabled (same node): lower latency than an NCCL launch for these small buffers and a
+    // fixed summation order; larger buffers go through it in pieces of the payload size
+    if (op == 0 && vlgp_p2p_enabled(ctx)) return vlgp_p2p_allreduce(ctx, d_buf, n);
     if (!ctx->comm) return vlgp_fail(ctx, VLGP_ERR_NCCL, "allreduce without a communicator");
     NCK(ctx->nccl->AllReduce(d_buf, d_buf, n, kNcclFloat64, op == 1 ? kNcclMax : kNcclSum, ctx->comm, ctx->stream));
     ctx->counters[3]++;
@@ -64,6 +68,7 @@ int vlgp_allreduce_dev(vlgp_ctx *ctx, double *d_buf, size_t n, int op) {
 }
 
 void vlgp_comm_destroy(vlgp_ctx *ctx) {
+    vlgp_p2p_destroy(ctx);
     if (ctx->shm) vlgp_shm_close(ctx->shm, 0);
     ctx->shm = nullptr;
     if (ctx->comm_m && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm_m);
@@ -96,6 +101,14 @@ int vlgp_comm_init(vlgp_ctx *ctx, const char *libnccl_path, int rank, int n_rank
     REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "comm_init: bad rank %d / %d", rank, n_ranks);
     REQUIRE(ctx->comm == nullptr, "comm_init: communicator already initialised");
     if (n_ranks == 1) return VLGP_OK;
+    if (getenv("VLGP_COMM_NO_NCCL")) {
+        // ranks of one node that will talk through peer memory and shared memory only (vlgp_comm_enable_p2p must
+        // succeed): also lets several ranks share ONE GPU, which NCCL refuses -- the multi-rank path is then testable
+        // on a single-GPU box
+        ctx->rank_id = rank;
+        ctx->n_ranks = n_ranks;
+        return VLGP_OK;
+    }
     int rc = load_nccl(ctx, libnccl_path);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));

@@ -107,6 +107,8 @@ struct vlgp_ctx {
     void *comm = nullptr;
     void *comm_m = nullptr;      // ncclCommSplit duplicate of comm for the overlapped M-step (null: no overlap when n_ranks > 1)
     void *shm = nullptr;         // host-side allreduce handle (shmcomm.cu) for the scalars the host consumes
+    void *p2p = nullptr;         // P2PState (p2p.cu): peer-memory mailboxes for in-kernel allreduces, or null
+    int p2p_chan = 0;            // channel of the current stream: 0 main, 1 overlapped M-step
     int rank_id = 0, n_ranks = 1;
     // measurement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -14,6 +14,7 @@
 // the FP64 tensor path with one warp per segment, the CTA-wide register sweep below is the fallback for W > 56.
 #include "common.cuh"
 #include "linalg.cuh"
+#include "p2p.cuh"
 
 int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, bool *handled);   // hstep_dmma.cu
 
@@ -192,10 +193,12 @@ __global__ void __launch_bounds__(NT, 2) hstep_segment_kernel(HEvalBatch eb, int
     }
 }
 
-// red[e][0] = sum_i tr(B_i^-1), red[e][1] = sum_i (d B_i^-1 d):dK   (deterministic, one CTA per evaluation)
+// red[e][0] = sum_i tr(B_i^-1), red[e][1] = sum_i (d B_i^-1 d):dK   (deterministic, one CTA per evaluation); with peer
+// memory the two sums are exchanged with the other ranks here (p2p.cuh, chunk = evaluation) instead of on the host
 __global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double *__restrict__ partall,
-                                                         double *__restrict__ redall) {
+                                                         double *__restrict__ redall, P2PDev pd) {
     __shared__ double red[32];
+    __shared__ double pair[2];
     const double *part = partall + (size_t)blockIdx.x * 2 * nseg;
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < nseg; i += NT) {
@@ -205,8 +208,14 @@ __global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double 
     a = block_sum(a, red);
     b = block_sum(b, red);
     if (threadIdx.x == 0) {
-        redall[blockIdx.x * 2] = a;
-        redall[blockIdx.x * 2 + 1] = b;
+        pair[0] = a;
+        pair[1] = b;
+    }
+    __syncthreads();
+    p2p_allreduce_cta(pd, blockIdx.x, (size_t)blockIdx.x * 2, pair, 2);
+    if (threadIdx.x == 0) {
+        redall[blockIdx.x * 2] = pair[0];
+        redall[blockIdx.x * 2 + 1] = pair[1];
     }
 }
 
@@ -291,17 +300,22 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
         }
     }
     if (dmma_ok) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    hstep_final_kernel<<<n, NT, 0, ctx->stream>>>(S, ts->d_hpart, red);
+    // (tr, pd) sums over ranks: inside the final kernel through peer memory when enabled; else on the host through
+    // shared memory when attached (they are consumed there), else NCCL
+    const bool p2p = ctx->n_ranks > 1 && vlgp_p2p_enabled(ctx);
+    P2PDev pd{};
+    pd.n_ranks = 1;
+    if (p2p) pd = vlgp_p2p_next(ctx);
+    hstep_final_kernel<<<n, NT, 0, ctx->stream>>>(S, ts->d_hpart, red, pd);
     CKL();
-    // (tr, pd) sums over ranks: on the host through shared memory when attached (they are consumed there), else NCCL
-    int rc = ctx->shm ? VLGP_OK : vlgp_allreduce_dev(ctx, red, 2 * n, 0);
+    int rc = (ctx->shm || p2p) ? VLGP_OK : vlgp_allreduce_dev(ctx, red, 2 * n, 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->h_pin, ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
     rc = vlgp_mstep_pump(ctx, 2);      // an overlapped M-step gets its next launches while this round runs
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->shm && ctx->n_ranks > 1) {
+    if (ctx->shm && ctx->n_ranks > 1 && !p2p) {
         rc = vlgp_comm_allreduce(ctx, ctx->h_pin + VLGP_MAX_L * 8, 2 * n, 0);
         if (rc) return rc;
     }

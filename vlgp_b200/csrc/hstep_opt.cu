@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "lbfgsb.cuh"
+#include "p2p.cuh"
 
 extern "C" {
 
@@ -176,7 +177,7 @@ VLGP_API int vlgp_hstep_optimize(vlgp_ctx *ctx, int set_id, int n_lat, const int
         if (task) task[k] = st[k].task;
     }
     if (n_rounds) *n_rounds = rounds;
-    return VLGP_OK;
+    return vlgp_p2p_check(ctx);
 }
 
 }   // extern "C"

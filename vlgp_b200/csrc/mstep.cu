@@ -8,6 +8,7 @@
 //   mstep_solve   : one thread per neuron: L x L Cholesky solve (gradient fallback when not PD), clip, update
 // The rate is computed once per iteration and every neuron is updated from it (vlgp/core.py:174-176).
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace {
 
@@ -295,14 +296,11 @@ __device__ __forceinline__ bool chol_solve_small(double (&H)[LT][LT], double (&g
     return true;
 }
 
-template <int LT>
-__global__ void mstep_solve_kernel(MsolveArgs p) {
+// Newton / least-squares update of neuron n from its sufficient statistics S(s) and y-moments Y(s).
+template <int LT, class SF, class YF>
+__device__ __forceinline__ void mstep_solve_neuron(const MsolveArgs &p, int n, SF S, YF Y) {
     constexpr int NS = nstat_of(LT);
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= p.N) return;
     const int N = p.N;
-    auto S = [&](int s) { return p.stat[(size_t)s * N + n]; };
-    auto Y = [&](int s) { return p.ymom[(size_t)s * N + n]; };
     if (p.last) {
         const double me = S(NS - 2) / p.count;
         p.noise[n] = S(NS - 1) / p.count - me * me;   // np.var(y - eta, ddof=0), vlgp/core.py:177
@@ -377,6 +375,78 @@ __global__ void mstep_solve_kernel(MsolveArgs p) {
         } else {
             atomicAdd(p.flags + 1, 1);
         }
+    }
+}
+
+template <int LT>
+__global__ void mstep_solve_kernel(MsolveArgs p) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.N) return;
+    const int N = p.N;
+    mstep_solve_neuron<LT>(p, n, [&](int s) { return p.stat[(size_t)s * N + n]; },
+                           [&](int s) { return p.ymom[(size_t)s * N + n]; });
+}
+
+// reduce_parts + (peer-memory allreduce over ranks) + solve in ONE launch: CTA c owns MR_NPB neurons.  Its warps sum the
+// statistics kernel's per-CTA partials of those neurons (warp w takes partials w, w + 8, ...; lanes take the entries),
+// the eight warp sums are added in warp order, the result is exchanged with the peers from inside the kernel
+// (p2p.cuh; chunk = CTA index) and one thread per neuron runs the L x L solve from shared memory.  Replaces three
+// launches and an NCCL call per Newton iteration (25 per M-step) with one; deterministic summation order.
+constexpr int MR_NPB = 4;
+
+template <int LT>
+__global__ void __launch_bounds__(256) mstep_reduce_solve_kernel(MsolveArgs p, const double *__restrict__ part,
+                                                                 const double *__restrict__ ypart, int G, int first,
+                                                                 P2PDev pd, double *__restrict__ stat_out,
+                                                                 double *__restrict__ ymom_out) {
+    constexpr int NS = nstat_of(LT), NY = LT + 1, EMAX = (NS + NY) * MR_NPB;
+    __shared__ double red[8][EMAX];
+    __shared__ double tot[EMAX];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = p.N, n0 = blockIdx.x * MR_NPB;
+    const int nn = N - n0 < MR_NPB ? N - n0 : MR_NPB;
+    const int E = NS * MR_NPB, ET = E + (first ? NY * MR_NPB : 0);
+    for (int e = lane; e < ET; e += 32) {
+        const bool isy = e >= E;
+        const int e2 = isy ? e - E : e;
+        const int st = e2 / MR_NPB, nl = e2 - st * MR_NPB;
+        const double *src = (isy ? ypart : part) + (size_t)st * N + n0 + nl;
+        const size_t stride = (size_t)(isy ? NY : NS) * N;
+        double a0 = 0.0, a1 = 0.0;
+        if (nl < nn) {
+            int g = wid;
+            for (; g + 8 < G; g += 16) {
+                a0 += src[(size_t)g * stride];
+                a1 += src[(size_t)(g + 8) * stride];
+            }
+            if (g < G) a0 += src[(size_t)g * stride];
+        }
+        red[wid][e] = a0 + a1;
+    }
+    __syncthreads();
+    for (int e = tid; e < ET; e += 256) {
+        double x = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) x += red[w][e];
+        tot[e] = x;
+    }
+    __syncthreads();
+    p2p_allreduce_cta(pd, blockIdx.x, (size_t)blockIdx.x * EMAX, tot, ET);
+    for (int e = tid; e < ET; e += 256) {
+        const bool isy = e >= E;
+        const int e2 = isy ? e - E : e;
+        const int st = e2 / MR_NPB, nl = e2 - st * MR_NPB;
+        if (nl < nn) (isy ? ymom_out : stat_out)[(size_t)st * N + n0 + nl] = tot[e];
+    }
+    if (tid < nn) {
+        const int n = n0 + tid;
+        const double *ym = p.ymom;
+        if (first)
+            mstep_solve_neuron<LT>(p, n, [&](int s) { return tot[s * MR_NPB + tid]; },
+                                   [&](int s) { return tot[E + s * MR_NPB + tid]; });
+        else
+            mstep_solve_neuron<LT>(p, n, [&](int s) { return tot[s * MR_NPB + tid]; },
+                                   [&](int s) { return ym[(size_t)s * N + n]; });
     }
 }
 
@@ -490,6 +560,18 @@ int mstep_iter_t(vlgp_ctx *ctx, MstepJob &job, int it) {
         CKL();
     }
     int rc;
+    // one launch for reduce + exchange + solve when the exchange can happen inside the kernel (one rank, or peer memory)
+    constexpr int EMAX = (nstat_of(LT) + LT + 1) * MR_NPB;
+    const int nblk = (N + MR_NPB - 1) / MR_NPB;
+    const bool fused = (ctx->n_ranks == 1 || vlgp_p2p_enabled(ctx)) && nblk <= VLGP_P2P_NCH &&
+                       (size_t)nblk * EMAX <= (size_t)VLGP_P2P_PAY && !getenv("VLGP_MSTEP_UNFUSED");
+    if (fused) {
+        P2PDev pd = vlgp_p2p_next(ctx);
+        mstep_reduce_solve_kernel<LT><<<nblk, 256, 0, ctx->stream>>>(so, ctx->d_mpart, job.ypart, (int)gx, it == 0 ? 1 : 0,
+                                                                      pd, ctx->d_mstat, ctx->d_ymom);
+        CKL();
+        return VLGP_OK;
+    }
     if (it == 0) {      // y-moments mu'y, sum y: once per M-step
         reduce_parts_kernel<<<(KY + 127) / 128, 128, 0, ctx->stream>>>(job.ypart, (int)gx, KY, ctx->d_ymom);
         CKL();

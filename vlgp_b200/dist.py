@@ -46,7 +46,8 @@ def init_from_env(backend: str = "gloo"):
         td.init_process_group(backend=backend, rank=r, world_size=world)
     _STATE["pg"] = True
     eng = get_engine()              # cuda:$LOCAL_RANK
-    box = [eng.comm_unique_id() if r == 0 else None]
+    no_nccl = bool(os.environ.get("VLGP_COMM_NO_NCCL"))   # peer + shared memory only (ranks may then share a GPU)
+    box = [(os.urandom(128) if no_nccl else eng.comm_unique_id()) if r == 0 else None]
     td.broadcast_object_list(box, src=0)
     eng.comm_init(r, world, box[0])
     # One node, one process per GPU: scalars that end up on the host are reduced through shared memory (shmcomm.cu).
@@ -56,12 +57,16 @@ def init_from_env(backend: str = "gloo"):
 
         name = "/vlgp_" + hashlib.sha1(box[0]).hexdigest()[:20]
         eng.attach_host_allreduce(name)
+        if not os.environ.get("VLGP_NO_P2P"):
+            eng.enable_peer_memory()     # in-kernel allreduce of the M-/H-step statistics over NVLink peer memory
         td.barrier()                     # every rank has mapped the segment: the name can go
         if r == 0:
             try:
                 os.unlink("/dev/shm" + name)
             except OSError:
                 pass
+    if no_nccl and not eng.peer_memory:
+        raise RuntimeError("VLGP_COMM_NO_NCCL=1 needs the peer-memory path (one node, shared memory, CUDA IPC)")
     return eng
 
 

@@ -94,6 +94,7 @@ class Engine:
         self.N = self.L = self.rank = 0
         self.world_size = 1
         self.rank_id = 0
+        self.peer_memory = False
 
     # -- plumbing ---------------------------------------------------------------------------------------------------
     def _ck(self, rc, what):
@@ -207,6 +208,16 @@ class Engine:
             raise _lib.VlgpNativeError("vlgp_shm_open(%s) failed with status %d" % (name, rc))
         self._ck(self.lib.vlgp_comm_attach_shm(self.ctx, h), "comm_attach_shm")
         self.host_allreduce = True
+
+    def enable_peer_memory(self) -> bool:
+        """Map every rank's mailbox (collective; after attach_host_allreduce): the small device-side reductions then go
+        through peer memory from inside the kernels (csrc/p2p.cuh).  False when some rank cannot map some peer."""
+        if self.world_size <= 1:
+            return False
+        on = C.c_int()
+        self._ck(self.lib.vlgp_comm_enable_p2p(self.ctx, C.byref(on)), "comm_enable_p2p")
+        self.peer_memory = bool(on.value)
+        return self.peer_memory
 
     def allreduce(self, x, op="sum"):
         """In-place allreduce of a small host array (<= 256 doubles per call; chunked here)."""
