@@ -52,29 +52,16 @@ print("hstep_prepare            : %8.1f us" % timeit(ts.hstep_prepare, 20))
 print("make_cholesky (session)  : %8.1f us" % timeit(lambda: s.make_cholesky(params), 20))
 print("norms                    : %8.1f us" % timeit(ts.norms, 50))
 
-calls = {"n": 0, "t": 0.0}
-orig = ts.hstep_objective_batch
-
-
-def wrapped(l, x):
-    t0 = time.perf_counter()
-    r = orig(l, x)
-    calls["t"] += time.perf_counter() - t0
-    calls["n"] += 1
-    return r
-
-
-ts.hstep_objective_batch = wrapped
 p2 = dict(params)
 R = 10
+config["hstep_rounds"] = []
 t0 = time.perf_counter()
 for _ in range(R):
     pp = dict(p2)
     gp._optimize_dev(s, pp, config)
 tot = (time.perf_counter() - t0) / R
-print("whole H-step: %.2f ms; %d rounds, device calls %.2f ms, host (setulb + python) %.2f ms" % (
-    tot * 1e3, calls["n"] / R, calls["t"] / R * 1e3, (tot - calls["t"] / R) * 1e3))
-ts.hstep_objective_batch = orig
+print("whole H-step (native optimiser): %.2f ms; %.1f device rounds -> %.1f us per round" % (
+    tot * 1e3, np.mean(config["hstep_rounds"]), tot * 1e6 / max(np.mean(config["hstep_rounds"]), 1)))
 print("mstep(25)                : %8.1f us" % timeit(lambda: ts.mstep(25), 10))
 print("estep(25)                : %8.1f us" % timeit(lambda: ts.estep(25), 10))
 for ov in (True, False, True, False):

@@ -28,7 +28,7 @@ def _n_gpus():
 def _launch(port, **env):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "scripts", "fit_spmd_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **env))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=ROOT, env=dict(os.environ, **env))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("same_on_all_ranks True") == 4, r.stdout[-3000:]
     return r.stdout

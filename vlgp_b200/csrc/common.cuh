@@ -197,64 +197,117 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
-// exp(min(x, 10)) -- vlgp/math.py:24-38.  Branch-free (the library exp() carries a slow-path branch for out-of-range
-// arguments that keeps the compiler from interleaving several evaluations; this link function is the single most
-// executed operation of the E- and M-step): x = t ln2 + r with t = rint(x log2 e) via the 2^52+2^51 shift, |r| <= ln2/2,
-// degree-13 Taylor polynomial in Horner form (truncation 4e-18), scaling by 2^t through the exponent field.
-// Maximum error 1 ulp on [-708, 10] (checked against numpy.exp on 4e6 points, scripts/check_exp.py).  Arguments
-// below -708 are clamped: the result is then 3e-308 instead of a denormal/0, an absolute difference of 3e-308.
-//
-// The Taylor coefficients 1/13! .. 1/2!, 1 live in constant memory: written as literals, ptxas re-materialised every one
-// of them with two UMOV per loop iteration (24 of the 156 instructions of the E-step's two-neuron rate-pass body, as
-// many in the M-step kernel); from the constant bank they are loaded into uniform registers once, outside the loops
-// (136 instructions; same FP64 instructions in the same order, so results are unchanged bit for bit).
-static __constant__ double VLGP_EXP_C[13] = {1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08,
-                                             2.755731922398589e-07,  2.7557319223985893e-06, 2.48015873015873e-05,
-                                             1.984126984126984e-04,  1.388888888888889e-03,  8.333333333333333e-03,
-                                             4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0};
+// exp(min(x, 10)) -- vlgp/math.py:24-38.  Branch-free and table-driven (the library exp() carries a slow-path branch
+// that keeps the compiler from interleaving several evaluations, and this link function is the single most executed
+// operation of the E- and M-step): x = m ln2/32 + r with m = rint(x 32/ln2) via the 2^52+2^51 shift, |r| <= ln2/64, so
+// exp(x) = 2^(m >> 5) T[m & 31] exp(r) with T[j] = 2^(j/32) and a degree-6 Taylor polynomial for exp(r) (truncation
+// 3e-18).  11 FP64-pipe instructions per value against 19 for the table-free degree-13 form used before; maximum error
+// 0.9 ulp on [-700, 10] against a 50-digit reference (scripts/check_exp.py).  Arguments below -708 are clamped: the
+// result is then ~3e-308 instead of a denormal / 0, an absolute difference of 3e-308.
+static __constant__ double VLGP_EXP_C[6] = {1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0};
+static __device__ const double VLGP_EXP_T[32] = {
+    1.00000000000000000e+00, 1.02189714865411663e+00, 1.04427378242741375e+00, 1.06714040067682370e+00,
+    1.09050773266525769e+00, 1.11438674259589243e+00, 1.13878863475669156e+00, 1.16372485877757748e+00,
+    1.18920711500272103e+00, 1.21524735998046896e+00, 1.24185781207348400e+00, 1.26905095719173322e+00,
+    1.29683955465100964e+00, 1.32523664315974132e+00, 1.35425554693689265e+00, 1.38390988196383202e+00,
+    1.41421356237309515e+00, 1.44518080697704665e+00, 1.47682614593949935e+00, 1.50916442759342284e+00,
+    1.54221082540794074e+00, 1.57598084510788650e+00, 1.61049033194925428e+00, 1.64575547815396495e+00,
+    1.68179283050742900e+00, 1.71861929812247793e+00, 1.75625216037329945e+00, 1.79470907500310717e+00,
+    1.83400808640934243e+00, 1.87416763411029996e+00, 1.91520656139714740e+00, 1.95714412417540018e+00};
+#define VLGP_EXP_INV 4.61662413084468283841e+01      // 32 / ln2
+#define VLGP_EXP_HI 2.16608493865351192653e-02       // ln2 / 32, upper 32 bits
+#define VLGP_EXP_LO 5.96317165397058656257e-12       // ln2 / 32 - HI
 
 __device__ __forceinline__ double trunc_exp(double x) {
     x = x > 10.0 ? 10.0 : x;                                       // plain compare-select: no NaN-propagating min/max
     x = x < -708.0 ? -708.0 : x;
     const double shift = 6755399441055744.0;                       // 2^52 + 2^51
-    const double tmp = fma(x, 1.4426950408889634, shift);
-    const int ti = __double2loint(tmp);                            // rint(x log2 e) in the low word
+    const double tmp = fma(x, VLGP_EXP_INV, shift);
+    const int mi = __double2loint(tmp);                            // rint(x 32 / ln2) in the low word
     const double t = tmp - shift;
-    double r = fma(t, -6.93147180369123816490e-01, x);             // ln2 high part
-    r = fma(t, -1.90821492927058770002e-10, r);                    // ln2 low part
-    double p = VLGP_EXP_C[0];                                      // 1/13!
+    double r = fma(t, -VLGP_EXP_HI, x);
+    r = fma(t, -VLGP_EXP_LO, r);
+    double p = VLGP_EXP_C[0];
 #pragma unroll
-    for (int k = 1; k < 13; ++k) p = fma(p, r, VLGP_EXP_C[k]);     // 1/12! ... 1/2!, 1
-    p = fma(p, r, 1.0);
-    return p * __hiloint2double((ti + 1023) << 20, 0);             // 2^t, t in [-1022, 15]
+    for (int k = 1; k < 6; ++k) p = fma(p, r, VLGP_EXP_C[k]);      // 1/120 ... 1/2, 1
+    p *= r;                                                        // exp(r) - 1
+    const double tj = __ldg(&VLGP_EXP_T[mi & 31]);
+    const double e = fma(tj, p, tj);
+    const int ex = max(mi >> 5, -1022);
+    return __hiloint2double(__double2hiint(e) + (ex << 20), __double2loint(e));      // e 2^ex through the exponent field
 }
 
-// Two independent evaluations with their Horner chains interleaved statement by statement (the polynomial is a chain
-// of 14 dependent DFMAs; two chains in flight double the FP64-pipe utilisation of a warp -- when ptxas keeps them
-// interleaved, which it does not under an 80-register cap).  Bitwise identical to two calls of
-// trunc_exp.
+// Two independent evaluations with their chains interleaved statement by statement.  Bitwise identical to two calls
+// of trunc_exp.
 __device__ __forceinline__ void trunc_exp2(double x0, double x1, double &e0, double &e1) {
     x0 = x0 > 10.0 ? 10.0 : x0;
     x1 = x1 > 10.0 ? 10.0 : x1;
     x0 = x0 < -708.0 ? -708.0 : x0;
     x1 = x1 < -708.0 ? -708.0 : x1;
     const double shift = 6755399441055744.0;
-    const double m0 = fma(x0, 1.4426950408889634, shift), m1 = fma(x1, 1.4426950408889634, shift);
+    const double m0 = fma(x0, VLGP_EXP_INV, shift), m1 = fma(x1, VLGP_EXP_INV, shift);
     const int i0 = __double2loint(m0), i1 = __double2loint(m1);
+    const double tj0 = __ldg(&VLGP_EXP_T[i0 & 31]), tj1 = __ldg(&VLGP_EXP_T[i1 & 31]);
     const double t0 = m0 - shift, t1 = m1 - shift;
-    double r0 = fma(t0, -6.93147180369123816490e-01, x0), r1 = fma(t1, -6.93147180369123816490e-01, x1);
-    r0 = fma(t0, -1.90821492927058770002e-10, r0);
-    r1 = fma(t1, -1.90821492927058770002e-10, r1);
+    double r0 = fma(t0, -VLGP_EXP_HI, x0), r1 = fma(t1, -VLGP_EXP_HI, x1);
+    r0 = fma(t0, -VLGP_EXP_LO, r0);
+    r1 = fma(t1, -VLGP_EXP_LO, r1);
     double p0 = VLGP_EXP_C[0], p1 = VLGP_EXP_C[0];
 #pragma unroll
-    for (int k = 1; k < 13; ++k) {
+    for (int k = 1; k < 6; ++k) {
         p0 = fma(p0, r0, VLGP_EXP_C[k]);
         p1 = fma(p1, r1, VLGP_EXP_C[k]);
     }
-    p0 = fma(p0, r0, 1.0);
-    p1 = fma(p1, r1, 1.0);
-    e0 = p0 * __hiloint2double((i0 + 1023) << 20, 0);
-    e1 = p1 * __hiloint2double((i1 + 1023) << 20, 0);
+    p0 *= r0;
+    p1 *= r1;
+    const double q0 = fma(tj0, p0, tj0), q1 = fma(tj1, p1, tj1);
+    const int ex0 = max(i0 >> 5, -1022), ex1 = max(i1 >> 5, -1022);
+    e0 = __hiloint2double(__double2hiint(q0) + (ex0 << 20), __double2loint(q0));
+    e1 = __hiloint2double(__double2hiint(q1) + (ex1 << 20), __double2loint(q1));
+}
+
+// Four independent evaluations, statement-interleaved (two accumulator tiles of the tensor-path rate pass at a time).
+__device__ __forceinline__ void trunc_exp4(double x0, double x1, double x2, double x3, double &e0, double &e1, double &e2,
+                                           double &e3) {
+    double x[4] = {x0, x1, x2, x3}, m[4], t[4], r[4], tj[4], p[4];
+    int mi[4];
+    const double shift = 6755399441055744.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = x[i] > 10.0 ? 10.0 : x[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = x[i] < -708.0 ? -708.0 : x[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = fma(x[i], VLGP_EXP_INV, shift);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mi[i] = __double2loint(m[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tj[i] = __ldg(&VLGP_EXP_T[mi[i] & 31]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = m[i] - shift;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fma(t[i], -VLGP_EXP_HI, x[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = fma(t[i], -VLGP_EXP_LO, r[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = VLGP_EXP_C[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = fma(p[i], r[i], VLGP_EXP_C[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] *= r[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fma(tj[i], p[i], tj[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ex = max(mi[i] >> 5, -1022);
+        p[i] = __hiloint2double(__double2hiint(p[i]) + (ex << 20), __double2loint(p[i]));
+    }
+    e0 = p[0];
+    e1 = p[1];
+    e2 = p[2];
+    e3 = p[3];
 }
 
 // 1 / d for a normal, finite d (sweep pivots: >= 1 for I + PSD matrices, > 0 otherwise) without the special-case

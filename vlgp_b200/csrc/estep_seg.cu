@@ -7,6 +7,7 @@ namespace segk {
 template <> int launch_seg_variant<2, true>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
 template <> int launch_seg_variant<2, false>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
 template <> int launch_seg_variant<4, false>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<4, true>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
 }
 
 int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled,
@@ -53,14 +54,18 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     if (p.tpb < 1) return VLGP_OK;
     if (p.tpb > N) p.tpb = N;
     p.chunk = (N + p.tpb - 1) / p.tpb;
-    const size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8);
+    p.np = 8 * ((N + 7) / 8);
+    if (p.np % 16 == 0) p.np += 8;               // = 8 mod 16: the B-operand fragment loads are bank-conflict-free
+    p.kp = 4 * ((2 * L + 1 + 3) / 4);
+    const size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8, p.kp, p.np);
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
     int rc = VLGP_OK;
     bool big = false;
     for (int l = 0; l < L; ++l)
         if (p.nc[l] > 16) big = true;
     const bool fast = !ctx->any_gauss && ts->ydtype == VLGP_Y_U8 && !getenv("VLGP_NO_FAST_ESTEP");
-    if (big && p.use_dmma) rc = launch_seg_variant<4, false>(ctx, ts, p, smem, handled);
+    if (big && p.use_dmma && fast) rc = launch_seg_variant<4, true>(ctx, ts, p, smem, handled);
+    else if (big && p.use_dmma) rc = launch_seg_variant<4, false>(ctx, ts, p, smem, handled);
     else if (fast) rc = launch_seg_variant<2, true>(ctx, ts, p, smem, handled);
     else rc = launch_seg_variant<2, false>(ctx, ts, p, smem, handled);
     return rc;

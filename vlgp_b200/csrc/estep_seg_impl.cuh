@@ -47,6 +47,7 @@ struct SegArgs {
     int method_vb;
     int *flags;
     int tpb, chunk;               // threads per bin and neurons per thread in the rate passes
+    int np, kp;                   // tensor-path rate passes: padded neuron count (= 8 mod 16) and rows of the operand Bx
     int skip;                     // debug/timing only (VLGP_DEBUG_SKIP): 1 rate passes, 2 mean step, 4 factor, 8 variance
 };
 
@@ -59,10 +60,11 @@ struct Smem {
     __device__ Smem(unsigned char *base, const SegArgs &p) {
         double *d = (double *)base;
         const int N = p.N, W = p.W;
-        a = d; d += 2 * LT * N;                  // interleaved (a, a^2) pairs: one 128-bit load per (latent, neuron)
-        a2 = a;
-        b = d; d += 2 * N;                       // interleaved (bias, 1 / noise) pairs
+        a = d;                                   // interleaved (a, a^2) pairs: one 128-bit load per (latent, neuron)
+        a2 = a;                                  // (tensor-path rate passes: the kp x np operand Bx lives here instead)
+        b = d + 2 * LT * N;                      // interleaved (bias, 1 / noise) pairs
         inv_noise = b;
+        d += max(2 * LT * N + 2 * N, p.kp * p.np);
         Gs = d; d += p.g_total;
         Mi = d; d += p.m_total;
         mu = d; d += W * LT;
@@ -78,9 +80,11 @@ struct Smem {
     }
 };
 
-__host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8) {
+__host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8,
+                                                 int kp, int np) {
     const size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
-    size_t d = (size_t)2 * LT * N + 2 * N + g_total + m_total + (size_t)5 * W * LT + un;
+    const size_t par = (size_t)2 * LT * N + 2 * N > (size_t)kp * np ? (size_t)2 * LT * N + 2 * N : (size_t)kp * np;
+    size_t d = par + g_total + m_total + (size_t)5 * W * LT + un;
     size_t bytes = d * sizeof(double) + ((N + 15) / 16) * 16;
     if (y_u8) bytes += ((size_t)W * N + 15) / 16 * 16;
     return bytes;
@@ -164,8 +168,108 @@ __device__ __forceinline__ void rate_pass_two_bins(const SegArgs &p, const Smem<
 }
 #endif
 
+// Rate pass on the FP64 tensor path (all channels Poisson, counts staged as uint8): warp i owns the 8 bins of row tile
+// i and walks over the column tiles of 8 neurons.  Per tile pair:
+//   x[t][n] = b_n + sum_l mu_tl a_ln + 1/2 sum_l v_tl a_ln^2   as ONE contraction over k = (mu | v | 1) against the
+//             operand Bx = (a ; a^2 / 2 ; b), KS = ceil((2L + 1) / 4) DMMA; the accumulator tile hands every lane two
+//             (bin, neuron) entries -> two interleaved exponentials;
+//   acc[t][l] += sum_n coef[t][n] Bx[l or L + l][n]  (coef = y - rate or rate): the accumulator entries ARE the A
+//             operand of this second contraction when its k index is taken as n = 8 j + 2 (lane % 4) + {0, 1} -- the
+//             sum over neurons does not care about the order, so no shuffle is needed; the B operand is one 128-bit load.
+// 3 + 2 DMMA and 22 FP64-pipe instructions per 64 (bin, neuron) entries at L = 5 against ~70 FP64-pipe instructions
+// per entry pair in the scalar form: the contractions move to the tensor pipe and run beside the exponentials.  The
+// row tile's output is complete inside the warp: no partial sums in shared memory, one barrier per pass instead of two.
+template <int LT, int STAGE>
+__device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> &s) {
+    constexpr int KS = (2 * LT + 1 + 3) / 4;        // k4 steps of the x contraction
+    constexpr int NOT = (LT + 7) / 8;               // output tiles of 8 latents
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int W = p.W, N = p.N, NP = p.np;
+    if (8 * wid < W) {
+        const int t = 8 * wid + r;
+        const bool tin = t < W;
+        double afr[KS];
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            const int k = 4 * kk + q;
+            double val = 0.0;
+            if (tin) {
+                if (k < LT) val = s.mu[t * LT + k];
+                else if (k < 2 * LT) val = s.v[t * LT + k - LT];
+                else if (k == 2 * LT) val = 1.0;
+            }
+            afr[kk] = val;
+        }
+        Tile acc[NOT];
+#pragma unroll
+        for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.0;
+        const double *Bx = s.a;
+        const uint8_t *yrow = s.ys + (tin ? t : 0) * N;
+        const int brow = (STAGE == 1 ? 0 : LT) + r;
+        // (build option VLGP_ESTEP_RATE_ILP2: two column tiles per step, four exponentials in flight per lane)
+        const int nct = NP >> 3;
+        auto tile_pair = [&](int j, double ea, double eb) {
+            const int n0 = 8 * j + 2 * q;
+            double c0 = ea, c1 = eb;
+            if (STAGE == 1) {
+                const double y0 = (tin && n0 < N) ? (double)yrow[n0] : 0.0;
+                const double y1 = (tin && n0 + 1 < N) ? (double)yrow[n0 + 1] : 0.0;
+                c0 = y0 - ea;
+                c1 = y1 - eb;
+            }
+#pragma unroll
+            for (int o = 0; o < NOT; ++o) {
+                double2 b2 = make_double2(0.0, 0.0);
+                if (8 * o + r < LT) b2 = *reinterpret_cast<const double2 *>(Bx + (brow + 8 * o) * NP + n0);
+                dmma(acc[o], c0, b2.x);
+                dmma(acc[o], c1, b2.y);
+            }
+        };
+        int j = 0;
+#ifdef VLGP_ESTEP_RATE_ILP2      // measured on B200 (profiles/ab_estep_variants_r2.txt): 0.5 ms SLOWER per launch than one tile at a time
+        for (; j + 1 < nct; j += 2) {
+            Tile xa{0.0, 0.0}, xb{0.0, 0.0};
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                dmma(xa, afr[kk], Bx[(4 * kk + q) * NP + 8 * j + r]);
+                dmma(xb, afr[kk], Bx[(4 * kk + q) * NP + 8 * j + 8 + r]);
+            }
+            double e0, e1, e2, e3;
+            trunc_exp4(xa.x, xa.y, xb.x, xb.y, e0, e1, e2, e3);
+            tile_pair(j, e0, e1);
+            tile_pair(j + 1, e2, e3);
+        }
+#endif
+        for (; j < nct; ++j) {
+            Tile x{0.0, 0.0};
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) dmma(x, afr[kk], Bx[(4 * kk + q) * NP + 8 * j + r]);
+            double e0, e1;
+            trunc_exp2(x.x, x.y, e0, e1);
+            tile_pair(j, e0, e1);
+        }
+        double *out = (STAGE == 1) ? s.ra : s.w;
+        const double sc = (STAGE == 1) ? 1.0 : 2.0;          // Bx holds a^2 / 2
+        if (tin) {
+#pragma unroll
+            for (int o = 0; o < NOT; ++o) {
+                const int l0 = 8 * o + 2 * q;
+                if (l0 < LT) out[t * LT + l0] = sc * acc[o].x;
+                if (l0 + 1 < LT) out[t * LT + l0 + 1] = sc * acc[o].y;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int LT, int STAGE, bool FAST>
 __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, int64_t bin0) {
+#ifndef VLGP_ESTEP_SCALAR_RATE_PASS
+    if (FAST) {
+        rate_pass_dmma<LT, STAGE>(p, s);
+        return;
+    }
+#endif
     const int tid = threadIdx.x;
 #ifdef VLGP_ESTEP_TWO_BINS
     if (FAST) {
@@ -616,6 +720,63 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
     __syncthreads();
 }
 
+// out[j] = sum_t G[t][j] f(t) for the nc columns of one latent's factor, by one warp: the bins are split over 32 / J
+// groups of J = 8, 16 or 32 lanes (J >= nc when nc <= 32) whose partial sums are combined by shuffles.
+template <class F>
+__device__ __forceinline__ void warp_gt_product(const double *g, int ld, int nc, int W, F f, double *out) {
+    const int lane = threadIdx.x & 31;
+    if (nc <= 16) {
+        const int J = nc <= 8 ? 8 : 16, j = lane & (J - 1), part = lane / J, nparts = 32 / J;
+        double acc = 0.0;
+        if (j < nc)
+            for (int t = part; t < W; t += nparts) acc = fma(g[t * ld + j], f(t), acc);
+        for (int o = 16; o >= J; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane < nc) out[lane] = acc;
+    } else {
+        for (int j = lane; j < nc; j += 32) {
+            double acc = 0.0;
+            for (int t = 0; t < W; ++t) acc = fma(g[t * ld + j], f(t), acc);
+            out[j] = acc;
+        }
+    }
+}
+
+// Newton step of the posterior mean of ONE latent by ONE warp (vlgp/core.py:81-97): the five mat-vec stages are
+// separated by __syncwarp only, so the latents proceed concurrently in their own warps and the whole mean step costs
+// one block barrier instead of five.  vec: per latent 3 x 64 doubles (p, m | c | u).
+template <int LT>
+__device__ __forceinline__ void mean_step_warp(const SegArgs &p, const Smem<LT> &s, int l, bool bad) {
+    const int lane = threadIdx.x & 31, W = p.W, nc = p.nc[l], ld = ldodd(nc), ldm = p.ldm[l];
+    const double *g = s.Gs + p.goff[l], *M = s.Mi + p.moff[l];
+    double *pv = s.vec + l * 192, *cv = pv + 64, *uv = pv + 128;
+    warp_gt_product(g, ld, nc, W, [&](int t) { return s.ra[t * LT + l]; }, pv);          // p = G' (resid a_l)
+    __syncwarp();
+    for (int t = lane; t < W; t += 32) {                                                  // u = G p - mu_l
+        double acc = 0.0;
+        for (int j = 0; j < nc; ++j) acc = fma(g[t * ld + j], pv[j], acc);
+        uv[t] = acc - s.mu[t * LT + l];
+    }
+    __syncwarp();
+    warp_gt_product(g, ld, nc, W, [&](int t) { return s.w[t * LT + l] * uv[t]; }, cv);    // c = G' (w_l o u)
+    __syncwarp();
+    for (int i = lane; i < nc; i += 32) {                                                 // m = Minv c  (M = -Minv)
+        double acc = 0.0;
+        for (int j = 0; j < nc; ++j) acc = fma(M[j * ldm + i], cv[j], acc);
+        pv[i] = -acc;
+    }
+    __syncwarp();
+    for (int t = lane; t < W; t += 32) {        // delta = clip(u - G m); a failed factorisation zeroes the step (:92-94)
+        double d = 0.0;
+        if (!bad) {
+            double acc = 0.0;
+            for (int j = 0; j < nc; ++j) acc = fma(g[t * ld + j], pv[j], acc);
+            d = clipd(uv[t] - acc, p.dmu_bound);
+        }
+        s.dmu[t * LT + l] = d;
+        s.mu[t * LT + l] += d;
+    }
+}
+
 template <int LT, int NBMAX, bool FAST>
 #ifdef VLGP_ESTEP_TWO_BINS
 __global__ void __launch_bounds__(NT, 2) estep_seg_kernel(SegArgs p) {
@@ -629,11 +790,25 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
     const int W = p.W, N = p.N;
 
     // ---- once per CTA: parameters and the compact prior factors ------------------------------------------------------
-    for (int i = tid; i < LT * N; i += NT) ((double2 *)s.a)[i] = p.pa[i];
-    for (int n = tid; n < N; n += NT) {
-        ((double2 *)s.b)[n] = p.pb[n];
-        s.pois[n] = p.poisson[n];
+#ifndef VLGP_ESTEP_SCALAR_RATE_PASS
+    if (FAST) {          // operand of the tensor-path rate passes: rows a_l | a_l^2 / 2 | b | 0, columns padded with 0
+        for (int i = tid; i < p.kp * p.np; i += NT) {
+            const int k = i / p.np, n = i - k * p.np;
+            double val = 0.0;
+            if (n < N) {
+                if (k < LT) val = p.pa[k * N + n].x;
+                else if (k < 2 * LT) val = 0.5 * p.pa[(k - LT) * N + n].y;
+                else if (k == 2 * LT) val = p.pb[n].x;
+            }
+            s.a[i] = val;
+        }
+    } else
+#endif
+    {
+        for (int i = tid; i < LT * N; i += NT) ((double2 *)s.a)[i] = p.pa[i];
+        for (int n = tid; n < N; n += NT) ((double2 *)s.b)[n] = p.pb[n];
     }
+    for (int n = tid; n < N; n += NT) s.pois[n] = p.poisson[n];
     for (int l = 0; l < LT; ++l) {
         const int nc = p.nc[l], ldg = ldodd(nc);
         const double *Gsrc = p.G + (size_t)l * W * p.rank;
@@ -663,7 +838,14 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
         for (int it = 0; it < p.n_iter; ++it) {
             if (!(p.skip & 1)) rate_pass<LT, 1, FAST>(p, s, bin0);    // ends with a barrier; part (aliases vec) is free again
             if (it == 0) factor_all<LT, NBMAX>(p, s, bad, false);      // the first mean step uses the incoming w
-            if (!(p.skip & 2)) mean_step_all<LT>(p, s, bad);
+            if (!(p.skip & 2)) {
+#ifdef VLGP_ESTEP_WARP_MEAN_STEP     // one warp per latent, one barrier: measured 0.2 ms SLOWER per launch than the flat form
+                for (int l = tid >> 5; l < LT; l += NWARP) mean_step_warp<LT>(p, s, l, bad[l] != 0);
+                __syncthreads();
+#else
+                mean_step_all<LT>(p, s, bad);
+#endif
+            }
             if (!(p.skip & 1)) rate_pass<LT, 2, FAST>(p, s, bin0);
             if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT, NBMAX>(p, s, bad, p.method_vb != 0);
         }

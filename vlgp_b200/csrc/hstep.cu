@@ -14,6 +14,7 @@
 // the FP64 tensor path with one warp per segment, the CTA-wide register sweep below is the fallback for W > 56.
 #include "common.cuh"
 #include "linalg.cuh"
+#include "dmma.cuh"
 #include "p2p.cuh"
 
 int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, bool *handled);   // hstep_dmma.cu
@@ -71,33 +72,49 @@ __global__ void reduce_parts_kernel2(const double *__restrict__ part, int G, int
 
 // ---- per evaluation, one CTA (blockIdx.x = evaluation): K, dK, K^-1 terms -------------------------------------------
 // out[e][0] = tr(K^-1 M), [1] = sum log diag chol(K), [2] = (K^-1 M K^-1):dK, [5] = 1 if K is not PD.
+// This launch is on the critical path of an optimiser round when a rank holds few segments (the per-segment kernel next
+// to it is then shorter), so it is built for latency: K, dK and M staged in shared memory (padded to whole 8 x 8 tiles),
+// the CTA-wide register sweep with the pivots' logarithms taken in parallel afterwards, and the two W^3 products on the
+// FP64 tensor path: with T = K^-1 M and U = dK K^-1 (all three matrices symmetric), tr(K^-1 M K^-1 dK) = sum_ij T_ij U_ij,
+// so every warp forms matching tiles of T and U by DMMA and multiplies them element by element in registers.
 __global__ void __launch_bounds__(NT) hstep_global_kernel(HEvalBatch eb, int W, double dt, const double *__restrict__ Mall,
-                                                          double *__restrict__ Kall, double *__restrict__ outall) {
+                                                          double *__restrict__ Kall, double *__restrict__ outall,
+                                                          int write_k) {
     extern __shared__ double sm[];
     const int e = blockIdx.x;
     const double sigmasq = eb.sigmasq[e], omega = eb.omega[e], eps = eb.eps[e];
     const double *M = Mall + (size_t)eb.latent[e] * W * W;
     double *Kout = Kall + (size_t)e * 2 * W * W, *dKout = Kout + (size_t)W * W;
     double *out = outall + e * 8;
-    const int ld = W | 1;
-    double *Aw = sm;                   // W x ld : K -> -K^-1
-    double *Tm = Aw + W * ld;          // W x ld : K^-1 M
-    double *ck = Tm + W * ld;          // 2 x 64
-    double *red = ck + 128;            // 32
+    const int NB = (W + 7) >> 3, WP = 8 * NB, ld = WP + 1;
+    double *Aw = sm;                   // WP x ld : K -> -K^-1
+    double *Mw = Aw + WP * ld;         // WP x ld : M
+    double *Dw = Mw + WP * ld;         // WP x ld : dK / dlog(omega)
+    double *ck = Dw + WP * ld;         // 2 x 64
+    double *piv = ck + 128;            // 64
+    double *red = piv + 64;            // 32
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    for (int i = ty; i < W; i += 16)
-        for (int j = tx; j < W; j += 16) {
-            const double dx = (double)(i - j) * dt;
-            const double d2 = dx * dx;
-            const double ks = sigmasq * exp(-omega * d2);
-            const double k = ks + (i == j ? eps : 0.0);
+    for (int i = ty; i < WP; i += 16)
+        for (int j = tx; j < WP; j += 16) {
+            double k = 0.0, dk = 0.0, m = 0.0;
+            if (i < W && j < W) {
+                const double dx = (double)(i - j) * dt;
+                const double d2 = dx * dx;
+                const double ks = sigmasq * exp(-omega * d2);
+                k = ks + (i == j ? eps : 0.0);
+                dk = -ks * d2 * omega;
+                m = M[i * W + j];
+                if (write_k) {
+                    Kout[i * W + j] = k;
+                    dKout[i * W + j] = dk;
+                }
+            }
             Aw[i * ld + j] = k;
-            Kout[i * W + j] = k;
-            dKout[i * W + j] = -ks * d2 * omega;
+            Dw[i * ld + j] = dk;
+            Mw[i * ld + j] = m;
         }
     __syncthreads();
-    double logdet = 0.0;
-    const bool ok = block_sweep_spd(Aw, ld, W, ck, &logdet);
+    const bool ok = block_sweep_spd(Aw, ld, W, ck, nullptr, piv);
     if (!ok) {
         if (tid == 0) {
             out[0] = out[1] = out[2] = 0.0;
@@ -105,24 +122,26 @@ __global__ void __launch_bounds__(NT) hstep_global_kernel(HEvalBatch eb, int W, 
         }
         return;
     }
-    // Tm = K^-1 M  (Aw = -K^-1)
-    double t1 = 0.0;
-    for (int i = ty; i < W; i += 16)
-        for (int j = tx; j < W; j += 16) {
-            double s = 0.0;
-            for (int k = 0; k < W; ++k) s = fma(Aw[i * ld + k], M[k * W + j], s);
-            Tm[i * ld + j] = -s;
-            if (i == j) t1 -= s;
+    const double logdet = block_sum(tid < W ? log(piv[tid]) : 0.0, red);
+    // tiles of T' = (-K^-1) M and U' = dK (-K^-1); T' o U' = T o U, tr(T) = -tr(T')
+    const int lane = tid & 31, wid = tid >> 5, r = lane >> 2, q = lane & 3;
+    double t1 = 0.0, gr = 0.0;
+    for (int tile = wid; tile < NB * NB; tile += NT / 32) {
+        const int ti = tile / NB, tj = tile - ti * NB;
+        Tile T{0.0, 0.0}, U{0.0, 0.0};
+        const double *arow = Aw + (8 * ti + r) * ld + q, *drow = Dw + (8 * ti + r) * ld + q;
+        const double *mcol = Mw + q * ld + 8 * tj + r, *acol = Aw + q * ld + 8 * tj + r;
+        for (int k = 0; 4 * k < WP; ++k) {
+            dmma(T, arow[4 * k], mcol[4 * k * ld]);
+            dmma(U, drow[4 * k], acol[4 * k * ld]);
         }
-    __syncthreads();
-    // Q = Tm K^-1 ;  grad = Q : dK
-    double gr = 0.0;
-    for (int i = ty; i < W; i += 16)
-        for (int j = tx; j < W; j += 16) {
-            double s = 0.0;
-            for (int k = 0; k < W; ++k) s = fma(Tm[i * ld + k], Aw[k * ld + j], s);
-            gr = fma(-s, dKout[i * W + j], gr);
+        gr = fma(T.x, U.x, gr);
+        gr = fma(T.y, U.y, gr);
+        if (ti == tj) {
+            if (r == 2 * q) t1 -= T.x;
+            if (r == 2 * q + 1) t1 -= T.y;
         }
+    }
     t1 = block_sum(t1, red);
     gr = block_sum(gr, red);
     if (tid == 0) {
@@ -221,6 +240,11 @@ __global__ void __launch_bounds__(NT) hstep_final_kernel(int nseg, const double 
 
 }   // namespace
 
+static size_t hstep_global_smem(int W) {
+    const int WP = 8 * ((W + 7) / 8);
+    return ((size_t)3 * WP * (WP + 1) + 128 + 64 + 32) * sizeof(double);
+}
+
 int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     const int W = ts->max_len, L = ctx->L, S = ts->n_trials;
     const int WW = W * W;
@@ -261,7 +285,7 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, 0));
         ts->h_seg_grid = (per_sm < 1 ? 1 : per_sm) * ctx->prop.multiProcessorCount;
         if (ts->h_seg_grid > S) ts->h_seg_grid = S;
-        const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
+        const size_t smem_g = hstep_global_smem(W);
         if (smem_g > 48 * 1024)
             CK(cudaFuncSetAttribute(hstep_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
         ts->h_geometry = true;
@@ -273,7 +297,7 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
 // Evaluates eb.n (latent, hyper) pairs in one pass: 3 launches, one allreduce, one D2H copy, one synchronisation.
 int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, double *ll, double *dll, int *info) {
     const int W = ts->max_len, S = ts->n_trials, n = eb.n;
-    const size_t smem_g = ((size_t)2 * W * (W | 1) + 160) * sizeof(double);
+    const size_t smem_g = hstep_global_smem(W);
     double *red = ts->d_hout + VLGP_MAX_L * 8;
     // The K^-1 terms (one CTA per evaluation, latency-bound) run on a second stream concurrently with the per-segment
     // kernel; the DMMA kernel builds K itself, only the W > 56 fallback reads the K written by the global kernel.
@@ -281,11 +305,11 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
     if (dmma_ok) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        hstep_global_kernel<<<n, NT, smem_g, ctx->stream2>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout);
+        hstep_global_kernel<<<n, NT, smem_g, ctx->stream2>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout, 0);
         CKL();
         CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     } else {
-        hstep_global_kernel<<<n, NT, smem_g, ctx->stream>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout);
+        hstep_global_kernel<<<n, NT, smem_g, ctx->stream>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout, 1);
         CKL();
     }
     {

@@ -9,7 +9,10 @@
 // Per step only the current column travels through shared memory (ck: 2 x 64 doubles, double-buffered -> one barrier
 // per step).  Elements with an index >= n must be zero on entry and stay zero.
 // Returns false (uniformly) on a non-positive pivot; *logdet (if non-null) receives sum_k log d_k.
-__device__ __forceinline__ bool block_sweep_regs(double (&a)[4][4], int n, double *ck, double *logdet) {
+// piv (optional, n doubles of SMEM): receives the pivots instead of their logarithms being summed inside the loop (the
+// caller takes the n logarithms in parallel afterwards: log() on the critical path of every step is most of its cost).
+__device__ __forceinline__ bool block_sweep_regs(double (&a)[4][4], int n, double *ck, double *logdet,
+                                                 double *piv = nullptr) {
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     double lsum = 0.0;
@@ -28,7 +31,11 @@ __device__ __forceinline__ bool block_sweep_regs(double (&a)[4][4], int n, doubl
         __syncthreads();
         const double d = buf[k];
         if (!(d > 0.0)) { ok = false; break; }      // uniform: every thread reads the same value
-        if (logdet) lsum += log(d);
+        if (piv) {
+            if (tid == 0) piv[k] = d;
+        } else if (logdet) {
+            lsum += log(d);
+        }
         const double pinv = fast_rcp(d);
         double ci[4], cj[4];
 #pragma unroll
@@ -64,7 +71,8 @@ __device__ __forceinline__ bool block_sweep_regs(double (&a)[4][4], int n, doubl
 
 // Same sweep for a matrix held in full (both triangles) in SMEM with leading dimension ld: loads it into the register
 // layout above, sweeps, stores -A^-1 back.  Must be called by all 256 threads.
-__device__ __forceinline__ bool block_sweep_spd(double *Aw, int ld, int n, double *ck, double *logdet) {
+__device__ __forceinline__ bool block_sweep_spd(double *Aw, int ld, int n, double *ck, double *logdet,
+                                                double *piv = nullptr) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double a[4][4];
 #pragma unroll
@@ -74,7 +82,7 @@ __device__ __forceinline__ bool block_sweep_spd(double *Aw, int ld, int n, doubl
             const int i = ty + 16 * p, j = tx + 16 * q;
             a[p][q] = (i < n && j < n) ? Aw[i * ld + j] : 0.0;
         }
-    const bool ok = block_sweep_regs(a, n, ck, logdet);
+    const bool ok = block_sweep_regs(a, n, ck, logdet, piv);
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll

@@ -23,7 +23,7 @@
 #define VLGP_P2P_CHUNK 256            // doubles per chunk of the generic kernel
 #define VLGP_P2P_SLOT (VLGP_P2P_PAY + VLGP_P2P_NCH)
 #define VLGP_P2P_CHANNEL_DOUBLES ((size_t)2 * VLGP_P2P_MAX_RANKS * VLGP_P2P_SLOT)
-#define VLGP_P2P_TIMEOUT_CYCLES 20000000000LL      // ~10 s at 2 GHz
+#define VLGP_P2P_TIMEOUT_CYCLES 8000000000LL       // ~4 s at 2 GHz
 
 struct P2PDev {
     int n_ranks, rank;
