@@ -14,7 +14,7 @@
  *   y            nbin x N          (float64, or uint8 when every count is an integer in [0,255])
  *   mu,v,w,dmu   nbin x L
  *   a, da        L x N             (params["a"], params["da"])
- *   b, db        N                 (params["b"][0,:]; xdim == 1 with an all-ones regressor, vlgp/preprocess.py:43-44)
+ *   b, db        xdim x N          (params["b"]; xdim == 1 with an all-ones regressor by default, vlgp/preprocess.py:43-44)
  *   noise        N
  *   G            L x length x rank (params["cholesky"][length], vlgp/gp.py:150-162)
  */
@@ -71,6 +71,10 @@ VLGP_API int vlgp_set_params(vlgp_ctx *ctx, const double *a, const double *b, co
 VLGP_API int vlgp_get_params(vlgp_ctx *ctx, double *a, double *b, double *noise, double *da, double *db, double *sigma,
                     double *omega);
 
+/* Number of regressors per neuron, xdim = max(history, 1) (vlgp/preprocess.py:59): b and db become xdim x N (row-major,
+ * params["b"]).  Call right after vlgp_set_model (which resets xdim to 1) and before creating trial sets. */
+VLGP_API int vlgp_set_regressors(vlgp_ctx *ctx, int xdim);
+
 /* ---- trial sets: replaces the list of trial dicts ------------------------------------------------------------------ */
 VLGP_API int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int *set_id);
 VLGP_API int vlgp_trials_free(vlgp_ctx *ctx, int set_id);
@@ -80,6 +84,10 @@ VLGP_API int vlgp_trials_set_y(vlgp_ctx *ctx, int set_id, const void *y, int ydt
  * blocks holding only integer counts in [0,255] are stored as uint8; *stored_dtype returns the choice. */
 VLGP_API int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *const *parts, const int64_t *rows,
                             int src_dtype, int *stored_dtype);
+/* General regressors x (nbin x xdim x N float64, the trial dicts' "x" concatenated, vlgp/core.py:66): only needed when x
+ * is not the all-ones bias column; the E-/M-step then use eta = mu a + einsum(x, b) and update b with the design x
+ * (vlgp/core.py:205-220,229-235; csrc/regress.cu). */
+VLGP_API int vlgp_trials_set_x(vlgp_ctx *ctx, int set_id, const double *x);
 VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w);
 /* Per-trial-block variants (which: 0 mu, 1 v, 2 w, 3 dmu [get only]; parts[i]: rows[i] x L float64, C-contiguous):
  * gather / scatter through the pinned double-buffered pipeline, so segment views are read and written in place. */

@@ -380,6 +380,52 @@ def golden_vem_options(ref):
     print("vem_options.npz", len(out))
 
 
+VEM_REGRESSOR_CASES = {
+    # name: (likelihoods or None, number of regressors xdim = max(history, 1), config keywords)
+    "history2_poisson": (None, 3, dict(Hstep=False)),
+    "history1_mixed_hstep": (["poisson"] * 6 + ["gaussian"] * 4, 2, dict()),
+    "scaled_bias_only": (None, 1, dict(Hstep=False, use_hessian=False, learning_rate=1e-4)),
+}
+
+
+def regressor_design(y, xdim, scale_bias=1.0):
+    """x (bins, xdim, neurons): the bias column (times scale_bias) and xdim - 1 spike-history regressors y[t - k]."""
+    T, N = y.shape
+    x = np.zeros((T, xdim, N))
+    x[:, 0, :] = scale_bias
+    for k in range(1, xdim):
+        x[k:, k, :] = y[:-k]
+    return x
+
+
+def golden_vem_regressors(ref):
+    """Two vem iterations of the reference with regressors other than the all-ones bias column (vlgp/core.py:66,
+    205-220,229-235): spike-history designs with xdim = 3 (Poisson) and xdim = 2 (mixed likelihoods, H-step on), and a
+    single regressor that is not all ones.  The reference takes b of shape (xdim, N) from the caller in that case."""
+    out = {}
+    for name, (lik, xdim, kw) in VEM_REGRESSOR_CASES.items():
+        segs, params, config = build_problem(ref, seed=23, n_trials=4, T=100, N=10, L=2, lik=lik, window=50,
+                                             max_iter=2, min_iter=2, **kw)
+        rng = np.random.default_rng(5)
+        b = np.zeros((xdim, 10))
+        b[0] = params["b"][0] / (0.5 if name == "scaled_bias_only" else 1.0)
+        b[1:] = 0.05 * rng.standard_normal((xdim - 1, 10))
+        params["b"], params["db"], params["xdim"] = b, np.zeros_like(b), xdim
+        for sg in segs:
+            sg["x"] = regressor_design(sg["y"], xdim, 0.5 if name == "scaled_bias_only" else 1.0)
+        ref.core.update_w(segs, params, config)
+        ref.core.update_v(segs, params, config)
+        p = name + "/"
+        out[p + "y"] = np.stack([s["y"] for s in segs])
+        out[p + "poisson"] = params["likelihood"] == "poisson"
+        out.update(pack_state(p + "in_", segs, params))
+        ref.core.vem(segs, params, config)
+        out.update(pack_state(p + "out_", segs, params))
+        out[p + "n_it"] = np.array(config["runtime"]["it"])
+    np.savez_compressed(os.path.join(OUT, "vem_regressors.npz"), **out)
+    print("vem_regressors.npz", len(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -387,7 +433,7 @@ def main():
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
                golden_fit_fixed_omega, golden_vem_options, golden_api_extras,
-               golden_fit_options, golden_fit_overlap):
+               golden_fit_options, golden_fit_overlap, golden_vem_regressors):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
 

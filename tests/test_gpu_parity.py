@@ -570,6 +570,41 @@ def test_transform_new_trials_golden(vl):
         assert relerr(np.stack([t[k] for t in new]), g["new_" + k]) < 1e-6, k
 
 
+VEM_REGRESSOR_CASES = {
+    "history2_poisson": (3, 0.0, dict(Hstep=False)),
+    "history1_mixed_hstep": (2, 0.0, dict()),
+    "scaled_bias_only": (1, 0.5, dict(Hstep=False, use_hessian=False, learning_rate=1e-4)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(VEM_REGRESSOR_CASES))
+def test_vem_general_regressors_golden(vl, case):
+    """Regressors other than the all-ones bias column (xdim = max(history, 1) > 1 or a user design; vlgp/core.py:66,
+    205-220,229-235) against the reference's outputs (tests/golden/vem_regressors.npz): E-step with the offsets
+    einsum(x, b), M-step Newton / least-squares update of b with the design x (csrc/regress.cu)."""
+    from vlgp_b200 import core
+    from vlgp_b200.gp import make_cholesky
+    from test_oracle_golden import regressor_design
+
+    g = load_golden("vem_regressors")
+    p = case + "/"
+    xdim, scale, kw = VEM_REGRESSOR_CASES[case]
+    segs = _segs(g, p)
+    for sg in segs:
+        sg["x"] = regressor_design(sg["y"], xdim, scale)
+    params = _params(g, p)
+    params["xdim"] = xdim
+    cfg = _cfg(max_iter=2, min_iter=2, **kw)
+    make_cholesky(segs, params, cfg)
+    core.vem(segs, params, cfg)
+    assert params["b"].shape == (xdim, 10) and params["db"].shape == (xdim, 10)
+    tol = 5e-4 if cfg["Hstep"] else 1e-8
+    for k in ("a", "b", "noise"):
+        assert relerr(params[k], g[p + "out_" + k]) < tol, k
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
+
+
 def test_reference_api_smoke(vl):
     """The reference's own API test (tests/test_api.py:4-38 there) with `import vlgp_b200 as vlgp`: integer counts from
     np.random.poisson, an extra user key per trial, fit with every default, then transform on the fitted trials."""
@@ -641,8 +676,8 @@ def test_errors_are_loud(vl):
     del params["cholesky"]
     with pytest.raises(KeyError):
         core.estep(segs, params, _cfg())
-    segs[0]["x"] = np.zeros((50, 1, 6))
-    with pytest.raises(NotImplementedError):
+    segs[0]["x"] = np.zeros((50, 2, 6))                      # a regressor block that does not match xdim = 1
+    with pytest.raises(ValueError):
         core.mstep(segs, params, _cfg())
     eng = __import__("vlgp_b200.engine", fromlist=["get_engine"]).get_engine()
     with pytest.raises(VlgpNativeError):

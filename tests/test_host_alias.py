@@ -99,7 +99,7 @@ def test_pull_params_writes_into_the_arrays_of_the_dict():
             return 0
 
     eng = Engine.__new__(Engine)
-    eng.lib, eng.ctx, eng.L, eng.N = Lib, None, L, N
+    eng.lib, eng.ctx, eng.L, eng.N, eng.xdim = Lib, None, L, N, 1
     eng._ck = lambda rc, what: None
     params = {"a": np.zeros((L, N)), "b": np.zeros((1, N)), "noise": np.zeros(N)}
     ka, kb, kn = params["a"], params["b"], params["noise"]
@@ -132,8 +132,9 @@ def test_fitted_loading_reaches_the_factor_analysis_map():
 # ----------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("use_c_helper", [True, False])
 def test_regressor_check_scans_owners_not_segments(monkeypatch, use_c_helper):
-    """Only the all-ones bias regressor is supported (xdim == 1).  Segments are views of their trial's x: the check
-    must accept them, scan each owning array once, and still catch every way a regressor can be something else."""
+    """The tuned kernels treat the all-ones bias regressor (xdim == 1) as a per-neuron constant; anything else goes
+    through the general-regressor path (csrc/regress.cu).  Segments are views of their trial's x: the classification
+    must accept them, scan each owning array once, and still notice every way a regressor can be something else."""
     from vlgp_b200 import core
 
     if not use_c_helper:
@@ -141,33 +142,31 @@ def test_regressor_check_scans_owners_not_segments(monkeypatch, use_c_helper):
     elif core._fastpack is None:
         pytest.skip("_fastpack not built")
     T, N = 120, 7
+    P = dict(xdim=1)
     x = np.ones((T, 1, N))
     segs = [dict(x=x[s:s + 40]) for s in range(0, T, 40)] + [dict(), dict(x=None), dict(x=np.ones((30, 1, N)))]
     scans = []
     real = core._all_ones
     monkeypatch.setattr(core, "_all_ones", lambda a: scans.append(a.shape) or real(a))
-    core._check_regressors(segs)
+    assert core._bias_only(segs, P)
     if use_c_helper:
         assert sorted(scans) == [(30, 1, N), (T, 1, N)]          # one scan per owner, not per segment
     bad = np.ones((T, 1, N))
     bad[77, 0, 3] = 0.5
-    with pytest.raises(NotImplementedError):
-        core._check_regressors(segs + [dict(x=bad[40:80])])
-    core._check_regressors(segs + [dict(x=bad[:40])])            # the view itself is all ones even if its owner is not
-    with pytest.raises(NotImplementedError):
-        core._check_regressors([dict(x=np.ones((T, 2, N)))])
-    with pytest.raises(NotImplementedError):
-        core._check_regressors([dict(x=np.ones((T, N)))])
+    assert not core._bias_only(segs + [dict(x=bad[40:80])], P)
+    assert core._bias_only(segs + [dict(x=bad[:40])], P)         # the view itself is all ones even if its owner is not
+    assert not core._bias_only([dict(x=np.ones((T, 2, N)))], P)
+    assert not core._bias_only([dict(x=np.ones((T, N)))], P)
+    assert not core._bias_only(segs, dict(xdim=2))               # history > 1: b has xdim rows
     # (an array verified once is remembered as all ones for as long as it lives, hence fresh arrays per case)
     wide = np.ones((T, 2, N))
-    core._check_regressors([dict(x=wide[:, :1, :])])             # a (T, 1, N) view of a wider array of ones
+    assert core._bias_only([dict(x=wide[:, :1, :])], P)          # a (T, 1, N) view of a wider array of ones
     wide = np.ones((T, 2, N))
     wide[5, 1, 0] = 3.0
-    core._check_regressors([dict(x=wide[:, :1, :])])             # ... judged by its own entries
+    assert core._bias_only([dict(x=wide[:, :1, :])], P)          # ... judged by its own entries
     wide = np.ones((T, 2, N))
     wide[5, 0, 0] = 3.0
-    with pytest.raises(NotImplementedError):
-        core._check_regressors([dict(x=wide[:, :1, :])])
+    assert not core._bias_only([dict(x=wide[:, :1, :])], P)
 
 
 def test_row_views_equal_np_split():

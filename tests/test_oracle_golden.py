@@ -222,6 +222,46 @@ def test_vem_option_branches(case):
         assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
 
 
+VEM_REGRESSOR_CASES = {
+    "history2_poisson": (3, 0.0, dict(Hstep=False)),
+    "history1_mixed_hstep": (2, 0.0, dict()),
+    "scaled_bias_only": (1, 0.5, dict(Hstep=False, use_hessian=False, learning_rate=1e-4)),
+}
+
+
+def regressor_design(y, xdim, scale_bias):
+    """Same design as oracle/make_golden.py::regressor_design: bias column and xdim - 1 spike-history regressors."""
+    T, N = y.shape
+    x = np.zeros((T, xdim, N))
+    x[:, 0, :] = scale_bias or 1.0
+    for k in range(1, xdim):
+        x[k:, k, :] = y[:-k]
+    return x
+
+
+@pytest.mark.parametrize("case", sorted(VEM_REGRESSOR_CASES))
+def test_vem_general_regressors(case):
+    """Two vem iterations of the reference with regressors other than the all-ones bias column (vlgp/core.py:66,
+    205-220,229-235): xdim = 3 spike-history design, xdim = 2 with Gaussian channels and the H-step, one scaled column."""
+    g = load_golden("vem_regressors")
+    p = case + "/"
+    xdim, scale, kw = VEM_REGRESSOR_CASES[case]
+    segs = _segs(g, p)
+    for sg in segs:
+        sg["x"] = regressor_design(sg["y"], xdim, scale)
+    params = _params(g, p)
+    params["xdim"] = xdim
+    params["cholesky"] = orc.make_cholesky([50], params["omega"], params["sigma"], 50)
+    cfg = orc.default_config(max_iter=2, min_iter=2, **kw)
+    orc.vem(segs, params, cfg)
+    assert params["b"].shape == (xdim, 10)
+    tol = 1e-6 if cfg["Hstep"] else 1e-9
+    for k in ("a", "b", "noise"):
+        assert relerr(params[k], g[p + "out_" + k]) < tol, k
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
+
+
 def test_sample_posterior_matches_reference():
     """api.sample_posterior is host-side NumPy in the reference and here: same seed,
     same inputs, same draws (vlgp/api.py:142-168)."""

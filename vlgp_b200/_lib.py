@@ -33,6 +33,8 @@ EXPORTS = {
     "vlgp_timer_stop": (C.c_int, [ctx_p, C.POINTER(C.c_float)]),
     "vlgp_counters": (C.c_int, [ctx_p, c_i64_p]),
     "vlgp_set_model": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_u8_p, C.c_double, C.c_double]),
+    "vlgp_set_regressors": (C.c_int, [ctx_p, C.c_int]),
+    "vlgp_trials_set_x": (C.c_int, [ctx_p, C.c_int, c_double_p]),
     "vlgp_set_params": (C.c_int, [ctx_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "vlgp_get_params": (C.c_int, [ctx_p] + [c_double_p] * 7),
     "vlgp_trials_create": (C.c_int, [ctx_p, C.c_int, c_i32_p, c_int_p]),

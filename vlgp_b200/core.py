@@ -63,31 +63,28 @@ def _remember_ones(base):
         pass
 
 
-def _check_regressors(trials):
-    """Only the all-ones bias regressor is supported.  Segments made by cut_trials are views of their trial's x, so
-    the scan runs once per underlying array (and at most once per process per array, see _all_ones), not once per
-    segment: 5120 segments of 256 trials cost 256 scans, and finding those 256 is one pass in C (_fastpack)."""
-    xs = [tr.get("x") for tr in trials]
+def _bias_only(trials, params):
+    """True when every trial's regressor x is the all-ones bias column with xdim == 1 (the reference's default,
+    vlgp/preprocess.py:43-44): the tuned kernels then treat the regression as a per-neuron constant b[n].  Anything else
+    -- xdim = max(history, 1) > 1 or a user-supplied design -- is uploaded and handled by csrc/regress.cu.
+    Segments made by cut_trials are views of their trial's x, so the scan runs once per underlying array (and at most
+    once per process per array, see _all_ones): 5120 segments of 256 trials cost 256 scans, and finding those 256 is
+    one pass in C (_fastpack)."""
+    if int(params.get("xdim", 1) or 1) != 1:
+        return False
+    xs = [x for x in (tr.get("x") for tr in trials) if x is not None]     # a missing x is the default regressor
+    if not xs:
+        return True
     owners = None
     if _fastpack is not None:
         try:
             owners = _fastpack.block_owners(xs, 3, 1, 1)
-        except ValueError:
-            raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)") from None
-        except (TypeError, BufferError, AttributeError):
+        except (ValueError, TypeError, BufferError, AttributeError):
             owners = None
-    if owners is None:
-        owners = [x for x in xs if x is not None]
-        if any(x.ndim != 3 or x.shape[1] != 1 for x in owners):
-            raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
-    else:
-        if not any(o.ndim != 3 or o.shape[1] != 1 for o in owners) and all(_all_ones(o) for o in owners):
-            return
-        # views that cover only part of an owner which is not all ones as a whole: judge every view by its own entries
-        owners = [x for x in xs if x is not None]
-    for x in owners:
-        if not _all_ones(x):
-            raise NotImplementedError("vlgp_b200 supports only the all-ones bias regressor x (xdim == 1)")
+    if owners is not None and all(o.ndim == 3 and o.shape[1] == 1 for o in owners) and all(_all_ones(o) for o in owners):
+        return True
+    # views that cover only part of an owner which is not all ones as a whole: judge every view by its own entries
+    return all(x.ndim == 3 and x.shape[1] == 1 and _all_ones(x) for x in xs)
 
 
 def _row_views(a, starts, lengths):
@@ -162,10 +159,17 @@ class Session:
         eng.push_params(params)
         self.n = len(trials)
         lengths = [tr["y"].shape[0] for tr in trials]
-        _check_regressors(trials)
+        bias_only = _bias_only(trials, params)
         self.ts: TrialSet = eng.new_trials(lengths)
         try:
             self.ts.set_y_parts([tr["y"] for tr in trials])
+            if not bias_only:
+                N, xd = eng.N, eng.xdim
+                xs = [np.asarray(tr["x"], dtype=np.float64) if tr.get("x") is not None else np.ones((n, xd, N))
+                      for tr, n in zip(trials, lengths)]
+                if any(x.shape != (n, xd, N) for x, n in zip(xs, lengths)):
+                    raise ValueError("every trial's x must have shape (bins, %d, %d)" % (xd, N))
+                self.ts.set_x(np.concatenate(xs, axis=0))
             L = eng.L
 
             def blocks(key):

@@ -186,7 +186,7 @@ void free_set(TrialSet &ts, cudaStream_t stream = nullptr) {
     };
     F(ts.d_len); F(ts.d_start); F(ts.d_fidx); F(ts.d_Gptr); F(ts.d_ncolptr); F(ts.d_y);
     F(ts.d_mu); F(ts.d_v); F(ts.d_w); F(ts.d_dmu); F(ts.d_ra); F(ts.d_u); F(ts.d_minv);
-    F(ts.d_M); F(ts.d_K); F(ts.d_hpart); F(ts.d_hout); F(ts.d_mompart);
+    F(ts.d_M); F(ts.d_K); F(ts.d_hpart); F(ts.d_hout); F(ts.d_mompart); F(ts.d_x); F(ts.d_xb);
     for (auto &pf : ts.factors) {
         F(pf.d_G); F(pf.d_ncol); F(pf.d_piv);
     }
@@ -266,6 +266,7 @@ int vlgp_destroy(vlgp_ctx *ctx) {
         p = nullptr;
     };
     F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db);
+    F(ctx->d_bpart); F(ctx->d_bstat);
     F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_ymom); F(ctx->d_ppack); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_small); F(ctx->d_flush);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -340,8 +341,10 @@ int vlgp_set_model(vlgp_ctx *ctx, int N, int L, int rank, const uint8_t *poisson
         p = nullptr;
     };
     F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db); F(ctx->d_mstat);
-    F(ctx->d_mpart); F(ctx->d_ymom); F(ctx->d_ppack);
+    F(ctx->d_mpart); F(ctx->d_ymom); F(ctx->d_ppack); F(ctx->d_bpart); F(ctx->d_bstat);
     ctx->mpart_grid = 0;
+    ctx->bpart_len = 0;
+    ctx->xdim = 1;
     ctx->N = N; ctx->L = L; ctx->rank = rank; ctx->gp_noise = gp_noise; ctx->dt = dt;
     CK(cudaMalloc(&ctx->d_poisson, N));
     CK(cudaMalloc(&ctx->d_a, (size_t)L * N * sizeof(double)));
@@ -366,6 +369,41 @@ int vlgp_set_model(vlgp_ctx *ctx, int N, int L, int rank, const uint8_t *poisson
     return VLGP_OK;
 }
 
+int vlgp_set_regressors(vlgp_ctx *ctx, int xdim) {
+    if (!ctx) return VLGP_ERR_ARG;
+    REQUIRE(ctx->N > 0, "set_regressors before set_model");
+    REQUIRE(xdim >= 1 && xdim <= VLGP_MAX_XDIM, "set_regressors: xdim %d outside [1, %d]", xdim, VLGP_MAX_XDIM);
+    if (xdim == ctx->xdim) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    SETTLE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &ts : ctx->sets)
+        REQUIRE(!ts.used, "set_regressors: free the trial sets of the previous model first");
+    if (ctx->d_b) CK(cudaFree(ctx->d_b));
+    if (ctx->d_db) CK(cudaFree(ctx->d_db));
+    ctx->d_b = ctx->d_db = nullptr;
+    const size_t bytes = (size_t)xdim * ctx->N * sizeof(double);
+    CK(cudaMalloc(&ctx->d_b, bytes));
+    CK(cudaMalloc(&ctx->d_db, bytes));
+    CK(cudaMemset(ctx->d_b, 0, bytes));
+    CK(cudaMemset(ctx->d_db, 0, bytes));
+    ctx->xdim = xdim;
+    return VLGP_OK;
+}
+
+int vlgp_trials_set_x(vlgp_ctx *ctx, int set_id, const double *x) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && x, "trials_set_x: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    SETTLE();
+    const size_t n = (size_t)ts->nbin * ctx->xdim * ctx->N;
+    if (!ts->d_x) CK(vlgp_dalloc(ctx, &ts->d_x, n * sizeof(double)));
+    if (!ts->d_xb) CK(vlgp_dalloc(ctx, &ts->d_xb, (size_t)ts->nbin * ctx->N * sizeof(double)));
+    CK(cudaMemcpyAsync(ts->d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
+}
+
 int vlgp_set_params(vlgp_ctx *ctx, const double *a, const double *b, const double *noise, const double *sigma,
                     const double *omega) {
     if (!ctx) return VLGP_ERR_ARG;
@@ -374,7 +412,7 @@ int vlgp_set_params(vlgp_ctx *ctx, const double *a, const double *b, const doubl
     CK(cudaSetDevice(ctx->device));
     if (a || b || noise) SETTLE();
     if (a) CK(cudaMemcpyAsync(ctx->d_a, a, L * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (b) CK(cudaMemcpyAsync(ctx->d_b, b, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(ctx->d_b, b, ctx->xdim * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (noise) CK(cudaMemcpyAsync(ctx->d_noise, noise, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (sigma) ctx->h_sigma.assign(sigma, sigma + L);
     if (omega) ctx->h_omega.assign(omega, omega + L);
@@ -391,8 +429,8 @@ int vlgp_get_params(vlgp_ctx *ctx, double *a, double *b, double *noise, double *
     SETTLE();
     if (a) CK(cudaMemcpyAsync(a, ctx->d_a, L * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (da) CK(cudaMemcpyAsync(da, ctx->d_da, L * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (b) CK(cudaMemcpyAsync(b, ctx->d_b, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (db) CK(cudaMemcpyAsync(db, ctx->d_db, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(b, ctx->d_b, ctx->xdim * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (db) CK(cudaMemcpyAsync(db, ctx->d_db, ctx->xdim * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (noise) CK(cudaMemcpyAsync(noise, ctx->d_noise, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (sigma) std::copy(ctx->h_sigma.begin(), ctx->h_sigma.end(), sigma);
@@ -413,9 +451,11 @@ int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int 
         ctx->sets.emplace_back();
         id = (int)ctx->sets.size() - 1;
     }
+    REQUIRE(id < 0x1000, "trials_create: too many live trial sets");
     TrialSet &ts = ctx->sets[id];
     ts = TrialSet();
     ts.used = true;
+    ts.gen = (++ctx->set_gen) & 0x7ffff;
     ts.n_trials = n_trials;
     ts.h_len.assign(lengths, lengths + n_trials);
     ts.h_start.resize(n_trials);
@@ -480,7 +520,7 @@ int vlgp_trials_create(vlgp_ctx *ctx, int n_trials, const int32_t *lengths, int 
     CK(cudaMemsetAsync(ts.d_dmu, 0, nb * L * sizeof(double), ctx->stream));
     (void)N;
     CK(cudaStreamSynchronize(ctx->stream));     // the host tables above are borrowed by the async copies
-    *set_id = id;
+    *set_id = id | (ts.gen << 12);
     return VLGP_OK;
 }
 

@@ -11,6 +11,7 @@
 
 #define VLGP_MAX_L 16        // latents (register-array bound of the templated kernels)
 #define VLGP_MAX_RANK 64     // rank of the prior factor (reference hard-codes 50, vlgp/preprocess.py:75)
+#define VLGP_MAX_XDIM 8      // regressors per neuron (xdim = max(history, 1), vlgp/preprocess.py:59)
 #define VLGP_MAX_W 64        // window length handled by the SMEM-resident segment kernels (reference default 50)
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -57,6 +58,10 @@ struct TrialSet {
     bool h_geometry = false;
     int dmma_grid = 0;                 // cached launch geometry of the DMMA segment kernel
     double *d_mompart = nullptr;       // per-chunk partial second moments
+    // general regressors (regress.cu): null for the all-ones bias column
+    double *d_x = nullptr;             // nbin x xdim x N
+    double *d_xb = nullptr;            // nbin x N : einsum(x, b), the offset of the linear predictor
+    int gen = 0;                       // generation of the slot: stale handles of freed sets are refused
 };
 
 // A batch of H-step objective evaluations (one per latent when the host optimisers run in lockstep), by value.
@@ -83,6 +88,10 @@ struct vlgp_ctx {
     std::string err;
     // model
     int N = 0, L = 0, rank = 0;
+    int xdim = 1;                                // regressors per neuron; b, db are xdim x N
+    double *d_bpart = nullptr, *d_bstat = nullptr;   // regression statistics of the general-x M-step (regress.cu)
+    size_t bpart_len = 0;
+    int set_gen = 0;
     double gp_noise = 1e-4, dt = 1.0;
     uint8_t *d_poisson = nullptr;
     bool any_gauss = false;
@@ -160,9 +169,13 @@ int vlgp_mstep_pump(vlgp_ctx *ctx, int max_iters);
         if (!(cond)) return vlgp_fail(ctx, VLGP_ERR_ARG, __VA_ARGS__);                                        \
     } while (0)
 
+// A set handle is slot + (generation << 12): a handle that outlived its set (vlgp_trials_free, or vlgp_set_model, which
+// drops every set) never resolves to whatever occupies the slot now.
 static inline TrialSet *get_set(vlgp_ctx *ctx, int id) {
-    if (!ctx || id < 0 || id >= (int)ctx->sets.size() || !ctx->sets[id].used) return nullptr;
-    return &ctx->sets[id];
+    if (!ctx || id < 0) return nullptr;
+    const int slot = id & 0xfff, gen = id >> 12;
+    if (slot >= (int)ctx->sets.size() || !ctx->sets[slot].used || ctx->sets[slot].gen != gen) return nullptr;
+    return &ctx->sets[slot];
 }
 
 struct ProfScope {   // accumulates device time of one kernel class when profiling is enabled

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "linalg.cuh"
 
+int vlgp_launch_xb(vlgp_ctx *ctx, TrialSet *ts);      // regress.cu
+
 namespace {
 
 struct EstepArgs {
@@ -29,6 +31,7 @@ struct EstepArgs {
     int ydtype;
     double *mu, *v, *w, *dmu, *ra, *u, *minv;
     const double *a, *b, *noise;
+    const double *xb;            // nbin x N offsets einsum(x, b) for general regressors (regress.cu), or null: b[n]
     const uint8_t *poisson;
     int n_iter;
     double dmu_bound;
@@ -55,7 +58,7 @@ __device__ __forceinline__ void rate_stage(const EstepArgs &p, int64_t s0, int T
         }
         for (int n = lane; n < N; n += 32) {
             double al[LT];
-            double eta = p.b[n], h = 0.0;
+            double eta = p.xb ? p.xb[bin * N + n] : p.b[n], h = 0.0;
 #pragma unroll
             for (int l = 0; l < LT; ++l) {
                 al[l] = p.a[l * N + n];
@@ -337,6 +340,11 @@ int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter,
     p.do_v = (mode == 0 && method_vb) || mode == 2;
     p.flags = ctx->d_flags;
     int rc = VLGP_OK;
+    if (ts->d_x && p.do_w) {                  // general regressors: refresh einsum(x, b) with the current b
+        rc = vlgp_launch_xb(ctx, ts);
+        if (rc) return rc;
+        p.xb = ts->d_xb;
+    }
     DISPATCH_L(ctx->L, rc = launch_estep_t<LT>(ctx, ts, p));
     return rc;
 }

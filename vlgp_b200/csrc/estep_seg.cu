@@ -15,6 +15,7 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     *handled = false;
     if (getenv("VLGP_FORCE_GENERIC_ESTEP")) return VLGP_OK;
     if (ts->min_len != ts->max_len || ts->max_len > VLGP_MAX_W || ts->factors.size() != 1) return VLGP_OK;
+    if (ts->d_x) return VLGP_OK;             // general regressors: the any-length kernel takes the offsets einsum(x, b)
     const int W = ts->max_len, L = ctx->L, N = ctx->N;
     SegArgs p{};
     p.n_seg = d_subset ? n_subset : ts->n_trials; p.subset = d_subset; p.W = W; p.N = N; p.rank = ctx->rank;

@@ -10,6 +10,12 @@
 #include "common.cuh"
 #include "p2p.cuh"
 
+// regress.cu: general regressors
+int vlgp_launch_xb(vlgp_ctx *ctx, TrialSet *ts);
+int vlgp_launch_bstats(vlgp_ctx *ctx, TrialSet *ts);
+int vlgp_launch_bsolve(vlgp_ctx *ctx, int use_hessian, double eps, double lr, double db_bound);
+int vlgp_bstat_muxb_offset(vlgp_ctx *ctx);
+
 namespace {
 
 // Per-iteration statistic slots per neuron (Poisson): [0,L) sum_t s_l r (s = mu + v o a_n) ; [L, L+L(L+1)/2) packed lower
@@ -26,6 +32,7 @@ struct MstatArgs {
     int ydtype;
     const double *mu, *v, *a, *b;
     const uint8_t *poisson;
+    const double *xb;            // nbin x N offsets einsum(x, b) for general regressors (regress.cu), or null: b[n]
     double *part;                // gridDim.x x nstat x N
     double *ypart;               // gridDim.x x (L+1) x N   (FIRST only)
     int last;                    // accumulate the noise moments
@@ -34,7 +41,7 @@ struct MstatArgs {
 constexpr int MS_U = 2;          // bins per thread per tile: MS_U independent exp chains in flight
 constexpr int MS_TB_MAX = 128;   // bins per SMEM tile (= MS_U * J <= 128)
 
-template <int LT, bool FIRST>
+template <int LT, bool FIRST, bool XB = false>
 __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(MstatArgs p) {
     constexpr int NS = nstat_of(LT);
     extern __shared__ double sm[];
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
             lin[u] = 0.0;
             if (t < nb) {
                 const double *mv = muv + t * 2 * LT;
-                double e = bn, h = 0.0;
+                double e = XB ? p.xb[(t0 + t) * p.N + n] : bn, h = 0.0;
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
                     e = fma(mv[l], al[l], e);
@@ -257,6 +264,8 @@ struct MsolveArgs {
     int use_hessian, last;
     double eps, lr, da_bound, db_bound;
     int *flags;                  // flags[1] += gradient fallbacks
+    const double *gmuxb;         // general regressors: L x N sums mu'(x b) for the Gaussian channels; b is then updated
+                                 // by mstep_bsolve_kernel (regress.cu), not here
 };
 
 // Solve H x = g for SPD H (L x L, full storage, destroyed).  Returns false if not positive definite
@@ -341,6 +350,7 @@ __device__ __forceinline__ void mstep_solve_neuron(const MsolveArgs &p, int n, S
             p.da[l * N + n] = d;
             p.a[l * N + n] += d;
         }
+        if (p.gmuxb != nullptr) return;                        // b: regress.cu
         const double gb = Y(LT) - S(NS - 3);                   // sum (y - r)
         double sb;
         const double hb = S(NS - 3) + p.eps;
@@ -362,7 +372,7 @@ __device__ __forceinline__ void mstep_solve_neuron(const MsolveArgs &p, int n, S
             for (int k = 0; k < LT; ++k) H[l][k] = p.gshared[l * LT + k];
             H[l][l] += p.gshared[LT * LT + l];
             smu[l] = p.gshared[LT * LT + LT + l];
-            rhs[l] = Y(l) - smu[l] * bn;
+            rhs[l] = p.gmuxb ? Y(l) - p.gmuxb[(size_t)l * N + n] : Y(l) - smu[l] * bn;
         }
         if (chol_solve_small<LT>(H, rhs)) {
             double dot = 0.0;
@@ -371,7 +381,7 @@ __device__ __forceinline__ void mstep_solve_neuron(const MsolveArgs &p, int n, S
                 p.a[l * N + n] = rhs[l];
                 dot = fma(smu[l], rhs[l], dot);
             }
-            p.b[n] = (Y(LT) - dot) / p.count;
+            if (p.gmuxb == nullptr) p.b[n] = (Y(LT) - dot) / p.count;
         } else {
             atomicAdd(p.flags + 1, 1);
         }
@@ -461,6 +471,8 @@ struct MstepJob {
     int64_t gx = 0;
     double *ypart = nullptr;
     int n_iter = 0, next_it = 0;
+    bool general_x = false;
+    TrialSet *ts = nullptr;
 };
 
 template <int LT>
@@ -541,6 +553,8 @@ int mstep_setup_t(vlgp_ctx *ctx, TrialSet *ts, MstepJob &job, int n_iter, int us
     job.grid = dim3((unsigned)gx, nchunk);
     job.nt = nt; job.K = K; job.KY = KY; job.LT = LT; job.smem = smem; job.gx = gx; job.ypart = ypart;
     job.n_iter = n_iter; job.next_it = 0;
+    job.general_x = ts->d_x != nullptr;
+    job.ts = ts;
     return VLGP_OK;
 }
 
@@ -551,15 +565,46 @@ int mstep_iter_t(vlgp_ctx *ctx, MstepJob &job, int it) {
     const int K = job.K, KY = job.KY, N = so.N;
     const int64_t gx = job.gx;
     sa.last = so.last = (it == job.n_iter - 1);
+    if (job.general_x) {
+        int rcx = vlgp_launch_xb(ctx, job.ts);
+        if (rcx) return rcx;
+        sa.xb = job.ts->d_xb;
+    }
     {
         ProfScope ps(ctx, 1);
-        if (it == 0)
+        if (job.general_x) {
+            if (it == 0)
+                mstep_stats_kernel<LT, true, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
+            else
+                mstep_stats_kernel<LT, false, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
+        } else if (it == 0) {
             mstep_stats_kernel<LT, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
-        else
+        } else {
             mstep_stats_kernel<LT, false><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
+        }
         CKL();
     }
     int rc;
+    if (job.general_x) {
+        // general regressors: statistics of b in their own pass (same parameters as the loading statistics above), then
+        // the loading solve, then the b solve (Gaussian channels use the NEW loading, vlgp/core.py:226-234)
+        rc = vlgp_launch_bstats(ctx, job.ts);
+        if (rc) return rc;
+        so.gmuxb = ctx->d_bstat + (size_t)vlgp_bstat_muxb_offset(ctx) * N;
+        if (it == 0) {
+            reduce_parts_kernel<<<(KY + 127) / 128, 128, 0, ctx->stream>>>(job.ypart, (int)gx, KY, ctx->d_ymom);
+            CKL();
+            rc = vlgp_allreduce_dev(ctx, ctx->d_ymom, KY, 0);
+            if (rc) return rc;
+        }
+        reduce_parts_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_mpart, (int)gx, K, ctx->d_mstat);
+        CKL();
+        rc = vlgp_allreduce_dev(ctx, ctx->d_mstat, K, 0);
+        if (rc) return rc;
+        mstep_solve_kernel<LT><<<(N + 63) / 64, 64, 0, ctx->stream>>>(so);
+        CKL();
+        return vlgp_launch_bsolve(ctx, so.use_hessian, so.eps, so.lr, so.db_bound);
+    }
     // one launch for reduce + exchange + solve when the exchange can happen inside the kernel (one rank, or peer memory)
     constexpr int EMAX = (nstat_of(LT) + LT + 1) * MR_NPB;
     const int nblk = (N + MR_NPB - 1) / MR_NPB;

@@ -92,6 +92,7 @@ class Engine:
         self.device = int(device)
         self.model_key = None
         self.N = self.L = self.rank = 0
+        self.xdim = 1
         self.world_size = 1
         self.rank_id = 0
         self.peer_memory = False
@@ -145,20 +146,23 @@ class Engine:
         bad = ~np.isin(lik, ("poisson", "gaussian"))
         if bad.any():
             raise ValueError("unsupported likelihood(s): %s" % sorted(set(lik[bad].tolist())))
-        if int(params.get("xdim", 1)) != 1:
-            raise NotImplementedError("vlgp_b200 supports xdim == 1 (bias only, history=0); got xdim=%s" % params["xdim"])
+        xdim = int(params.get("xdim", 1) or 1)
+        if not 1 <= xdim <= 8:
+            raise ValueError("xdim (history) must be between 1 and 8, got %d" % xdim)
         key = (int(params["ydim"]), int(params["zdim"]), int(params["rank"]), mask.tobytes(),
-               float(params["gp_noise"]), float(params["dt"]))
+               float(params["gp_noise"]), float(params["dt"]), xdim)
         if key != self.model_key:
+            # (vlgp_set_model drops every trial set of the previous model; their handles are refused from then on)
             self._ck(self.lib.vlgp_set_model(self.ctx, key[0], key[1], key[2], mask.ctypes.data_as(_lib.c_u8_p),
                                              key[4], key[5]), "set_model")
+            self._ck(self.lib.vlgp_set_regressors(self.ctx, xdim), "set_regressors")
             self.model_key = key
-            self.N, self.L, self.rank = key[0], key[1], key[2]
+            self.N, self.L, self.rank, self.xdim = key[0], key[1], key[2], xdim
 
     def push_params(self, params, which=("a", "b", "noise", "sigma", "omega")):
         L, N = self.L, self.N
         a = as_f64(params["a"], (L, N)) if "a" in which else None
-        b = as_f64(np.asarray(params["b"]).reshape(-1), (N,)) if "b" in which else None
+        b = as_f64(np.asarray(params["b"]).reshape(self.xdim, -1), (self.xdim, N)) if "b" in which else None
         noise = as_f64(params["noise"], (N,)) if "noise" in which else None
         sigma = as_f64(params["sigma"], (L,)) if "sigma" in which else None
         omega = as_f64(params["omega"], (L,)) if "omega" in which else None
@@ -169,12 +173,12 @@ class Engine:
         """Copy device parameters into the reference-shaped arrays of ``params`` (b/db are (1, N))."""
         L, N = self.L, self.N
         out = {k: np.empty((L, N)) for k in ("a", "da") if k in which}
-        out.update({k: np.empty((N,)) for k in ("b", "db", "noise") if k in which})
+        out.update({k: np.empty((self.xdim, N)) for k in ("b", "db") if k in which})
+        out.update({k: np.empty((N,)) for k in ("noise",) if k in which})
         g = out.get
         self._ck(self.lib.vlgp_get_params(self.ctx, dptr(g("a")), dptr(g("b")), dptr(g("noise")), dptr(g("da")),
                                           dptr(g("db")), None, None), "get_params")
         for k, val in out.items():
-            val = val.reshape(1, N) if k in ("b", "db") else val
             if k == "noise":
                 params[k] = val              # the reference rebinds noise (vlgp/core.py:177,244) ...
             else:
@@ -278,6 +282,7 @@ class TrialSet:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.y_stored = None          # dtype code of y in HBM once uploaded (1 = uint8 counts, 0 = float64)
+        self.general_x = False        # True once regressors other than the all-ones bias column were uploaded
 
     def free(self):
         if self.id is not None and self.eng.ctx:
@@ -324,6 +329,14 @@ class TrialSet:
         self.h2d_bytes += self.nbin * N * (1 if stored.value == 1 else 8)
         self.y_stored = stored.value
         return stored.value
+
+    def set_x(self, x):
+        """General regressors: the trials' x blocks concatenated, (nbin, xdim, N) float64 (csrc/regress.cu)."""
+        lib, ctx = self._lib()
+        x = as_f64(x, (self.nbin, self.eng.xdim, self.eng.N))
+        self.eng._ck(lib.vlgp_trials_set_x(ctx, self.id, dptr(x)), "trials_set_x")
+        self.h2d_bytes += x.nbytes
+        self.general_x = True
 
     _WHICH = {"mu": 0, "v": 1, "w": 2, "dmu": 3}
 
