@@ -114,6 +114,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["VLGP_NO_FASTPACK"] = "1"      # the CPU arm loads none of the product's native code
     out_fd = _claim_stdout()
     from vlgp_b200.synth import CONFIGS
 
@@ -122,6 +123,9 @@ def run_reference(args):
     sample = max(1, min(args.cpu_sample_trials, full_trials))
     probe = {}
     sec, nseg, _ = cpu_em_iteration_time(args.config, sample, args.steps, args.warmup, all_threads_probe=probe)
+    # evidence for the linear extrapolation in the number of trials: one more iteration on half the sample
+    half = max(1, sample // 2)
+    sec_half, nseg_half, _ = cpu_em_iteration_time(args.config, half, 1, 0) if half < sample else (sec, nseg, None)
     threads = int(os.environ.get("OPENBLAS_NUM_THREADS", os.environ.get("OMP_NUM_THREADS", "0")) or 0) or os.cpu_count()
     sec_one = sec
     if probe.get("sec") and probe["sec"] < sec:     # the opened-up pool won: that is the baseline then
@@ -137,6 +141,9 @@ def run_reference(args):
                          "sample": "%d of %d trials (%d of %d segments), %.2f s per EM iteration measured, scaled "
                                    "linearly in segments" % (sample, full_trials, nseg, nseg * full_trials // sample,
                                                              sec),
+                         "linearity": {"trials": [half, sample], "segments": [nseg_half, nseg],
+                                       "sec_per_em_iteration": [sec_half, sec_one],
+                                       "sec_per_segment": [sec_half / nseg_half, sec_one / nseg]},
                          "blas_threads_tried": {"1": sec_one, str(probe.get("threads", "all")): probe.get("sec")},
                          "note": "seconds per EM iteration of the sample at each BLAS pool size; the reference is a "
                                  "single Python process, the faster setting is reported"},
@@ -149,8 +156,10 @@ def run_reference(args):
 def workload_config(name, c, gpus):
     T = c["T"]
     return {"workload": "%s: %d trials x T=%s x %d neurons x %d latents, Poisson, window=50 rank=50 Eniter=25 Mniter=25 "
-                        "Hstep=True" % (name, c["n_trials"], T, c["N"], c["L"]),
-            "segments": c["n_trials"] * (T // 50) if isinstance(T, int) else None,
+                        "Hstep=True" % (name, c["n_trials"], T if isinstance(T, int) else "U[%d,%d]" % tuple(T), c["N"],
+                                        c["L"]),
+            "segments": c["n_trials"] * (T // 50) if isinstance(T, int) else "overlapping windows of 50 bins "
+                        "(vlgp/util.py:482-498), processed with the reference's in-place semantics",
             "sharding": "trials over %d rank(s), sum-allreduce of M-/H-step statistics (in-kernel over NVLink peer memory; "
                         "NCCL when peers cannot be mapped)" % gpus,
             "l2": "256 MiB write between steps evicts the 126 MB L2 (inside the timed region, <0.1 ms/step)"}
@@ -348,7 +357,8 @@ def run_ours(args):
     config["max_iter"] = 1
     config["min_iter"] = 1
     W, N, L = config["window"], c["N"], c["L"]
-    S_local, S_total = len(segs), len(trials) * (c["T"] // W)
+    S_local = len(segs)
+    S_total = int(sum(-(-tr["y"].shape[0] // W) for tr in trials))
 
     peaks = {}
     if rank == 0:

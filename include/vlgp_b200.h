@@ -89,6 +89,10 @@ VLGP_API int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, con
  * (vlgp/core.py:205-220,229-235; csrc/regress.cu). */
 VLGP_API int vlgp_trials_set_x(vlgp_ctx *ctx, int set_id, const double *x);
 VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const double *v, const double *w);
+/* Initial posterior means on the device (vlgp/preprocess.py:36-41: mu = FactorAnalysis.transform(y) per trial):
+ * mu[bin] = ((y[bin] - mean) P) Cz with mean (N), P = Wpsi' (N x L) and Cz = cov_z (L x L) of the factor model fitted
+ * on the host (sklearn FactorAnalysis.transform evaluates the two products in this order). */
+VLGP_API int vlgp_trials_project_y(vlgp_ctx *ctx, int set_id, const double *mean, const double *P, const double *Cz);
 /* Per-trial-block variants (which: 0 mu, 1 v, 2 w, 3 dmu [get only]; parts[i]: rows[i] x L float64, C-contiguous):
  * gather / scatter through the pinned double-buffered pipeline, so segment views are read and written in place. */
 VLGP_API int vlgp_trials_set_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, const double *const *parts,

@@ -34,7 +34,7 @@ ys = [t["y"] for t in segs]
 T("  set_y_parts", lambda: ts.set_y_parts(ys))
 mu = [t["mu"] for t in segs]
 T("  set_state_parts(mu)", lambda: ts.set_state_parts(mu=mu))
-T("  _check_regressors", lambda: core._check_regressors(segs))
+T("  _bias_only", lambda: core._bias_only(segs, params))
 T("  ensure+push params", lambda: (s.eng.ensure_model(params), s.eng.push_params(params)))
 T("  set_cholesky", lambda: ts.set_cholesky(50, params["cholesky"][50]))
 T("pull(all)", lambda: s.pull(segs))

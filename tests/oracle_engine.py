@@ -149,6 +149,12 @@ class OracleTrialSet:
     def set_y(self, y, ydtype=None):
         self.y[...] = np.asarray(y, dtype=float)
 
+    def project_y(self, mean, P, Cz):
+        """FactorAnalysis.transform of every bin (vlgp/preprocess.py:36-41) -- the engine's device projection, here with
+        scikit-learn's own order of operations per trial."""
+        for blk, dst in zip(self._split(self.y), self._split(self.state["mu"])):
+            dst[...] = np.dot(np.dot(blk - np.asarray(mean, dtype=float), np.asarray(P, dtype=float)), Cz)
+
     def set_state_parts(self, **blocks):
         for key, arrs in blocks.items():
             if arrs is None:

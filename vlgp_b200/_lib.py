@@ -42,6 +42,7 @@ EXPORTS = {
     "vlgp_trials_set_y": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_int]),
     # the two pointer/row tables are passed as packed byte strings (uint64 / int64), see _fastpack.pointers
     "vlgp_trials_set_y_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, c_int_p]),
+    "vlgp_trials_project_y": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "vlgp_trials_set_state": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "vlgp_trials_set_state_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "vlgp_trials_get_state_parts": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),

@@ -35,23 +35,53 @@ def fit(trials, n_factors, **kwargs):
     params = get_params(trials, n_factors, **kwargs)
 
     _echo("Initializing")
-    initialize(trials, params, config)
+    # the factor model is fitted on the host (scikit-learn, like the reference); the per-trial transform that gives the
+    # initial posterior means runs on the device, where y is uploaded anyway (see below)
+    projection = initialize(trials, params, config, defer_mu=True)
     _echo("Initialized")
 
     fill_params(params)
-    fill_trials(trials)
+    if projection is None:
+        fill_trials(trials)
+
+    world, rank = dist.world_size(), dist.rank()
+    if world > len(trials):
+        raise ValueError("%d ranks for %d trials: every rank needs at least one trial" % (world, len(trials)))
+    if world > 1:
+        # every rank ran the RNG-consuming host set-up above on its own; make rank 0's outcome everybody's, whatever
+        # the state of each process's global NumPy generator was: loading, bias, noise (in place: params["a"] may BE
+        # the factor model's components_), the projection / initial means, and the generator state the window cuts are drawn from
+        from .util import assign_inplace
+
+        for key in ("a", "b", "noise"):
+            assign_inplace(params, key, dist.broadcast_from_root(params[key]))
+        if projection is not None:
+            projection = tuple(dist.broadcast_from_root(p) for p in projection)
+        else:
+            for tr in trials:
+                tr["mu"][...] = dist.broadcast_from_root(tr["mu"])
+        kind, keys, pos, has_gauss, cached = np.random.get_state()
+        st = dist.broadcast_from_root(np.concatenate([keys.astype(float), [float(pos), float(has_gauss), cached]]))
+        np.random.set_state((kind, st[:-3].astype(np.uint32), int(st[-3]), int(st[-2]), float(st[-1])))
 
     # Multi-GPU (one process per GPU, vlgp_b200.dist.init_from_env() called first): SPMD -- every rank makes the same
     # call on the same trials, the host set-up above is replicated, each rank runs the device work of its contiguous
     # shard of trials (the M-/H-step statistics are allreduced inside vem), and at the end every rank holds the
     # posterior of every trial.  With one process this is exactly the reference's sequence (vlgp/api.py:49-71).
-    world, rank = dist.world_size(), dist.rank()
     lo, hi = dist.shard_bounds(len(trials), world, rank)
     mine = trials[lo:hi] if world > 1 else trials
 
     # the uncut trials stay on the device from here to the final infer (one upload of y instead of five)
+    if projection is not None:
+        L = params["zdim"]
+        for tr in trials:                    # placeholders: the device fills in this rank's, the final gather the others'
+            tr["mu"] = np.zeros((tr["y"].shape[0], L))
     full = Session(mine, params, upload_factors=False)
     try:
+        if projection is not None:
+            full.ts.project_y(*projection)
+            full.pull(mine, ("mu",))
+            fill_trials(trials)
         return _fit_on_device(trials, mine, lo, hi, world, full, params, config)
     finally:
         full.close()

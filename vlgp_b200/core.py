@@ -98,22 +98,44 @@ def _shared_rows(trials):
     """Junctions between consecutive segments that are overlapping views of one trial (windows cut from a trial whose
     length is not a multiple of the window, vlgp/util.py:482-498): list of (k, n) -- the last n rows of segment k ARE
     the first n rows of segment k + 1 in the reference (one block of memory).  Found from the addresses of the mu
-    arrays, so it needs nothing beyond what cut_trials returns."""
+    arrays, so it needs nothing beyond what cut_trials returns.  One vectorised pass over the address table (5120
+    segments: 0.3 ms); only candidate pairs are looked at one by one."""
+    n = len(trials)
+    if n < 2:
+        return []
+    ptr = rows = None
+    if _fastpack is not None:          # address table in C: every mu a C-contiguous float64 (rows, L) block, else fall through
+        try:
+            mus = [tr["mu"] for tr in trials]
+            L = mus[0].shape[1]
+            pb, rb = _fastpack.pointers(mus, 8, L, False, "d")
+            ptr = np.frombuffer(pb, dtype=np.uint64).astype(np.int64)
+            rows = np.frombuffer(rb, dtype=np.int64)
+            width = np.full(n, L, dtype=np.int64)
+            ok = np.ones(n, dtype=bool)
+        except (KeyError, TypeError, ValueError, BufferError, AttributeError, IndexError):
+            ptr = None
+    if ptr is None:
+        ptr = np.zeros(n, dtype=np.int64)
+        rows = np.zeros(n, dtype=np.int64)
+        width = np.zeros(n, dtype=np.int64)
+        ok = np.zeros(n, dtype=bool)
+        for k, tr in enumerate(trials):
+            a = tr.get("mu")
+            if isinstance(a, np.ndarray) and a.ndim == 2 and a.dtype == np.float64 and a.flags.c_contiguous:
+                ptr[k] = a.__array_interface__["data"][0]
+                rows[k], width[k] = a.shape
+                ok[k] = True
+    step = width[:-1] * 8
+    d = ptr[1:] - ptr[:-1]
+    cand = ok[:-1] & ok[1:] & (width[:-1] == width[1:]) & (d > 0) & (step > 0)
+    cand &= np.where(step > 0, d % np.maximum(step, 1), 1) == 0
+    shared = rows[:-1] - d // np.maximum(step, 1)
+    cand &= (shared > 0) & (shared < np.minimum(rows[:-1], rows[1:]))
     out = []
-    for k in range(len(trials) - 1):
-        a, b = trials[k].get("mu"), trials[k + 1].get("mu")
-        if not (isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.ndim == 2 and b.ndim == 2):
-            continue
-        if not (a.dtype == np.float64 == b.dtype and a.flags.c_contiguous and b.flags.c_contiguous
-                and a.shape[1] == b.shape[1] and np.may_share_memory(a, b)):
-            continue
-        row = a.strides[0]
-        d = b.__array_interface__["data"][0] - a.__array_interface__["data"][0]
-        if d <= 0 or d % row:
-            continue
-        n = a.shape[0] - d // row
-        if 0 < n < min(a.shape[0], b.shape[0]):
-            out.append((k, int(n)))
+    for k in np.flatnonzero(cand):
+        if np.may_share_memory(trials[k]["mu"], trials[k + 1]["mu"]):
+            out.append((int(k), int(shared[k])))
     return out
 
 

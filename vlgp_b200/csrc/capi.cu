@@ -632,7 +632,7 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
                                cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaEventRecord(ctx->stage_ev[buf], ctx->stream));
         }
-        CK(cudaStreamSynchronize(ctx->stream));
+        // (no synchronisation: the sources were consumed by the host threads above; see pipeline_copy)
         if (exact.load()) {
             if (stored_dtype) *stored_dtype = dst_dtype;
             return VLGP_OK;
@@ -712,7 +712,9 @@ static int pipeline_copy(vlgp_ctx *ctx, void *dev, size_t esz, int n_parts, void
                                cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaEventRecord(ctx->stage_ev[buf], ctx->stream));
         }
-        CK(cudaStreamSynchronize(ctx->stream));
+        // no synchronisation here: the caller's blocks have been copied into the pinned staging buffers (they are no
+        // longer needed), the staging buffers are protected by their events, and whatever uses the device array is
+        // enqueued on the same stream -- so the next upload's gather overlaps this one's transfer
     } else {
         // issue chunk k+1's D2H before scattering chunk k
         int buf = 0;
@@ -1150,6 +1152,48 @@ int vlgp_hstep_objective(vlgp_ctx *ctx, int set_id, int latent, const double hyp
     int rc = vlgp_hstep_objective_batch(ctx, set_id, 1, &l, hyper, ll, dll, &inf);
     *info = inf;
     return rc;
+}
+
+// ---- initial posterior means: FactorAnalysis.transform of every bin (vlgp/preprocess.py:36-41) ----------------------
+// mu[bin] = ((y[bin] - mean) P) Cz, P = Wpsi' (N x L), Cz = cov_z (L x L) of the fitted factor model.
+static __global__ void project_y_kernel(int64_t nbin, int N, int L, const void *__restrict__ y, int ydtype,
+                                        const double *__restrict__ mean, const double *__restrict__ P,
+                                        const double *__restrict__ Cz, double *__restrict__ mu) {
+    const int lane = threadIdx.x & 31;
+    const int64_t bin = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (bin >= nbin) return;
+    double acc[VLGP_MAX_L];
+    for (int l = 0; l < L; ++l) acc[l] = 0.0;
+    for (int n = lane; n < N; n += 32) {
+        const double c = load_y(y, ydtype, bin * N + n) - mean[n];
+        for (int l = 0; l < L; ++l) acc[l] = fma(c, P[(size_t)n * L + l], acc[l]);
+    }
+    for (int l = 0; l < L; ++l) acc[l] = warp_sum(acc[l]);
+    if (lane < L) {
+        double s = 0.0;
+        for (int k = 0; k < L; ++k) s = fma(acc[k], Cz[k * L + lane], s);
+        mu[bin * L + lane] = s;
+    }
+}
+
+extern "C" int vlgp_trials_project_y(vlgp_ctx *ctx, int set_id, const double *mean, const double *P, const double *Cz) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && ts->d_y && mean && P && Cz, "trials_project_y: bad arguments (y must be set)");
+    CK(cudaSetDevice(ctx->device));
+    SETTLE();
+    const size_t N = ctx->N, L = ctx->L;
+    double *d = nullptr;
+    CK(vlgp_dalloc(ctx, &d, (N + N * L + L * L) * sizeof(double)));
+    CK(cudaMemcpyAsync(d, mean, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + N, P, N * L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + N + N * L, Cz, L * L * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t threads = ts->nbin * 32;
+    project_y_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ts->nbin, (int)N, (int)L, ts->d_y, ts->ydtype,
+                                                                                d, d + N, d + N + N * L, ts->d_mu);
+    CKL();
+    CK(vlgp_dfree(ctx, d));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VLGP_OK;
 }
 
 // ---- constraints / bookkeeping ---------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
         po += nc * (nc + 1) / 2;
         co += nc;
     }
+    for (int l = 0; l < L; ++l) p.ldg[l] = p.nc[l] | 1;
     p.pairoff[L] = po; p.coloff[L] = co;
     p.pair_total = po; p.col_total = co;
     p.g_total = goff; p.m_total = moff;
@@ -58,12 +59,24 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     p.np = 8 * ((N + 7) / 8);
     if (p.np % 16 == 0) p.np += 8;               // = 8 mod 16: the B-operand fragment loads are bank-conflict-free
     p.kp = 4 * ((2 * L + 1 + 3) / 4);
-    const size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8, p.kp, p.np);
-    if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
-    int rc = VLGP_OK;
+    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8, p.kp, p.np);
     bool big = false;
     for (int l = 0; l < L; ++l)
         if (p.nc[l] > 16) big = true;
+    if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin && p.use_dmma) {
+        // many latents x many neurons x wide factors (config 3 in its first EM iterations: 10 x 200, 29 columns): leave
+        // the factors where they are (L x W x rank doubles, L2-resident, shared by every segment) and keep the rest in SMEM
+        p.g_global = 1;
+        p.g_total = 0;
+        for (int l = 0; l < L; ++l) {
+            p.goff[l] = l * W * ctx->rank;
+            p.ldg[l] = ctx->rank;
+        }
+        big = true;                          // the NBMAX = 4 instantiations carry the in-place path
+        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8, p.kp, p.np);
+    }
+    if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
+    int rc = VLGP_OK;
     const bool fast = !ctx->any_gauss && ts->ydtype == VLGP_Y_U8 && !getenv("VLGP_NO_FAST_ESTEP");
     if (big && p.use_dmma && fast) rc = launch_seg_variant<4, true>(ctx, ts, p, smem, handled);
     else if (big && p.use_dmma) rc = launch_seg_variant<4, false>(ctx, ts, p, smem, handled);

@@ -34,6 +34,9 @@ struct SegArgs {
     int coloff[VLGP_MAX_L + 1];   // prefix sums of nc : (latent, column) items
     int pair_total, col_total;
     int ldm[VLGP_MAX_L];          // leading dimension of latent l's r x r matrix in SMEM
+    int ldg[VLGP_MAX_L];          // leading dimension of latent l's factor: nc | 1 (compact copy in SMEM) or rank (in place)
+    int g_global;                 // 1: the factors do not fit in SMEM next to everything else and are read in place from
+                                  //    HBM / L2 (NBMAX = 4 variants only; goff then indexes p.G, g_total = 0)
     int use_dmma;                 // every nc <= 32: Gram / inverse / variance on the FP64 tensor path
     const void *y;
     int ydtype;
@@ -55,7 +58,8 @@ __device__ __forceinline__ int ldodd(int n) { return n | 1; }
 
 template <int LT>
 struct Smem {
-    double *a, *a2, *b, *inv_noise, *Gs, *Mi, *mu, *v, *w, *ra, *dmu, *part, *vec;
+    double *a, *a2, *b, *inv_noise, *Mi, *mu, *v, *w, *ra, *dmu, *part, *vec;
+    const double *Gs;             // compact factors in SMEM, or p.G itself (SegArgs::g_global)
     uint8_t *pois, *ys;
     __device__ Smem(unsigned char *base, const SegArgs &p) {
         double *d = (double *)base;
@@ -65,7 +69,7 @@ struct Smem {
         b = d + 2 * LT * N;                      // interleaved (bias, 1 / noise) pairs
         inv_noise = b;
         d += max(2 * LT * N + 2 * N, p.kp * p.np);
-        Gs = d; d += p.g_total;
+        Gs = d; d += p.g_total;                  // (g_total = 0 and Gs re-pointed by the kernel when g_global)
         Mi = d; d += p.m_total;
         mu = d; d += W * LT;
         v = d; d += W * LT;
@@ -388,7 +392,7 @@ __device__ __forceinline__ void gram_all(const SegArgs &p, const Smem<LT> &s) {
     for (int idx = threadIdx.x; idx < p.pair_total; idx += NT) {
         int l, i, j;
         decode_pair(p, LT, idx, l, i, j);
-        const int ldg = ldodd(p.nc[l]);
+        const int ldg = p.ldg[l];
         const double *g = s.Gs + p.goff[l];
         const double *wl = s.w + l;
         double c0 = 0.0, c1 = 0.0;
@@ -442,7 +446,7 @@ template <int LT, int NB>
 __device__ __forceinline__ bool factor_variance_dmma_nb(const SegArgs &p, const Smem<LT> &s, int l, bool do_var) {
     constexpr int NTL = NB * (NB + 1) / 2;
     const int lane = threadIdx.x & 31, r = lane >> 2, c0 = 2 * (lane & 3);
-    const int W = p.W, nc = p.nc[l], ldg = ldodd(nc);
+    const int W = p.W, nc = p.nc[l], ldg = p.ldg[l];
     const double *G = s.Gs + p.goff[l];
     const double *wl = s.w + l;
     Tile A[NTL];
@@ -637,7 +641,7 @@ __device__ __forceinline__ void variance_all(const SegArgs &p, const Smem<LT> &s
         const int l = (int)(((float)idx + 0.5f) * inv_w);
         const int t = idx - l * W;
         if (bad[l]) continue;                                      // failed solve: v keeps its value (core.py:112)
-        const int nc = p.nc[l], ld = ldodd(nc), ldm = p.ldm[l];
+        const int nc = p.nc[l], ld = p.ldg[l], ldm = p.ldm[l];
         const double *g = s.Gs + p.goff[l] + t * ld;
         const double *M = s.Mi + p.moff[l];
         double acc = 0.0;
@@ -660,7 +664,7 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
     for (int idx = tid; idx < p.col_total; idx += NT) {
         int l = 0;
         while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
-        const int j = idx - p.coloff[l], ld = ldodd(p.nc[l]);
+        const int j = idx - p.coloff[l], ld = p.ldg[l];
         const double *g = s.Gs + p.goff[l];
         double acc = 0.0;
         for (int t = 0; t < W; ++t) acc = fma(g[t * ld + j], s.ra[t * LT + l], acc);
@@ -670,7 +674,7 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
     // u = G p - mu_l
     for (int idx = tid; idx < LT * W; idx += NT) {
         const int l = (int)(((float)idx + 0.5f) * inv_w), t = idx - l * W;
-        const int nc = p.nc[l], ld = ldodd(nc);
+        const int nc = p.nc[l], ld = p.ldg[l];
         const double *g = s.Gs + p.goff[l] + t * ld;
         const double *pv = s.vec + l * 192;
         double acc = 0.0;
@@ -682,7 +686,7 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
     for (int idx = tid; idx < p.col_total; idx += NT) {
         int l = 0;
         while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
-        const int j = idx - p.coloff[l], ld = ldodd(p.nc[l]);
+        const int j = idx - p.coloff[l], ld = p.ldg[l];
         const double *g = s.Gs + p.goff[l];
         const double *uv = s.vec + l * 192 + 128;
         double acc = 0.0;
@@ -707,7 +711,7 @@ __device__ __forceinline__ void mean_step_all(const SegArgs &p, const Smem<LT> &
         const int l = (int)(((float)idx + 0.5f) * inv_w), t = idx - l * W;
         double d = 0.0;
         if (!bad[l]) {
-            const int nc = p.nc[l], ld = ldodd(nc);
+            const int nc = p.nc[l], ld = p.ldg[l];
             const double *g = s.Gs + p.goff[l] + t * ld;
             const double *mv = s.vec + l * 192;
             double acc = 0.0;
@@ -746,7 +750,7 @@ __device__ __forceinline__ void warp_gt_product(const double *g, int ld, int nc,
 // one block barrier instead of five.  vec: per latent 3 x 64 doubles (p, m | c | u).
 template <int LT>
 __device__ __forceinline__ void mean_step_warp(const SegArgs &p, const Smem<LT> &s, int l, bool bad) {
-    const int lane = threadIdx.x & 31, W = p.W, nc = p.nc[l], ld = ldodd(nc), ldm = p.ldm[l];
+    const int lane = threadIdx.x & 31, W = p.W, nc = p.nc[l], ld = p.ldg[l], ldm = p.ldm[l];
     const double *g = s.Gs + p.goff[l], *M = s.Mi + p.moff[l];
     double *pv = s.vec + l * 192, *cv = pv + 64, *uv = pv + 128;
     warp_gt_product(g, ld, nc, W, [&](int t) { return s.ra[t * LT + l]; }, pv);          // p = G' (resid a_l)
@@ -809,13 +813,18 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
         for (int n = tid; n < N; n += NT) ((double2 *)s.b)[n] = p.pb[n];
     }
     for (int n = tid; n < N; n += NT) s.pois[n] = p.poisson[n];
-    for (int l = 0; l < LT; ++l) {
-        const int nc = p.nc[l], ldg = ldodd(nc);
-        const double *Gsrc = p.G + (size_t)l * W * p.rank;
-        double *Gd = s.Gs + p.goff[l];
-        for (int i = tid; i < W * nc; i += NT) {
-            const int t = i / nc, c = i - t * nc;
-            Gd[t * ldg + c] = Gsrc[(size_t)t * p.rank + c];
+    if (NBMAX == 4 && p.g_global) {
+        s.Gs = p.G;                  // read in place (generic loads; only the NBMAX = 4 instantiations pay for that)
+    } else {
+        double *Gc = const_cast<double *>(s.Gs);
+        for (int l = 0; l < LT; ++l) {
+            const int nc = p.nc[l], ldg = p.ldg[l];
+            const double *Gsrc = p.G + (size_t)l * W * p.rank;
+            double *Gd = Gc + p.goff[l];
+            for (int i = tid; i < W * nc; i += NT) {
+                const int t = i / nc, c = i - t * nc;
+                Gd[t * ldg + c] = Gsrc[(size_t)t * p.rank + c];
+            }
         }
     }
     __syncthreads();

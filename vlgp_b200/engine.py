@@ -15,6 +15,8 @@ from ._lib import VlgpNativeError, as_f64, dptr
 from .util import assign_inplace
 
 try:  # optional C helper for the pointer tables (host plumbing only); pure-Python fallback below
+    if os.environ.get("VLGP_NO_FASTPACK"):      # bench.py --impl reference: none of this package's natives in that process
+        raise ImportError("disabled")
     from . import _fastpack
 except ImportError:  # pragma: no cover
     _fastpack = None
@@ -361,6 +363,16 @@ class TrialSet:
             self.eng._ck(lib.vlgp_trials_get_state_parts(ctx, self.id, self._WHICH[key], len(keep), ptrs, rows),
                          "trials_get_state_parts")
             self.d2h_bytes += self.nbin * self.eng.L * 8
+
+    def project_y(self, mean, P, Cz):
+        """mu <- ((y - mean) @ P) @ Cz on the device: FactorAnalysis.transform of every bin (vlgp/preprocess.py:36-41;
+        P = Wpsi' (N x L), Cz = cov_z (L x L) of the fitted factor model)."""
+        lib, ctx = self._lib()
+        mean = as_f64(mean, (self.eng.N,))
+        P = as_f64(P, (self.eng.N, self.eng.L))
+        Cz = as_f64(Cz, (self.eng.L, self.eng.L))
+        self.eng._ck(lib.vlgp_trials_project_y(ctx, self.id, dptr(mean), dptr(P), dptr(Cz)), "trials_project_y")
+        self.h2d_bytes += mean.nbytes + P.nbytes + Cz.nbytes
 
     def set_state(self, mu=None, v=None, w=None):
         lib, ctx = self._lib()

@@ -85,41 +85,83 @@ def _blas_thread_cap():
     return blas_threads(max(cap, 0))
 
 
-def initialize(trials, params, config):
-    """Factor-analysis initialisation of loading / bias / noise and of every trial's posterior mean."""
+def initialize(trials, params, config, defer_mu=False):
+    """Factor-analysis initialisation of loading / bias / noise and of every trial's posterior mean
+    (vlgp/preprocess.py:4-46).  ``defer_mu=True`` (used by fit): when the factor model is fitted here and no trial
+    brings its own ``mu``, the per-trial ``transform`` calls are left out and the projection ``(mean, P, C)`` with
+    ``mu = ((y - mean) @ P) @ C`` is returned instead, for the engine to evaluate on the device where y lives anyway
+    (TrialSet.project_y); returns None when every ``mu`` has been set on the host."""
     with _blas_thread_cap():
-        _initialize(trials, params, config)
+        return _initialize(trials, params, config, defer_mu)
 
 
-def _initialize(trials, params, config):
+def _rows(ys, lengths, pick):
+    """Rows ``pick`` of the concatenation of the blocks ``ys`` without building the concatenation."""
+    if len(ys) == 1:
+        return ys[0][pick, :]
+    starts = np.concatenate([[0], np.cumsum(lengths)])
+    owner = np.searchsorted(starts, pick, side="right") - 1
+    out = np.empty((pick.size, ys[0].shape[1]), dtype=np.result_type(*[y.dtype for y in ys]))
+    order = np.argsort(owner, kind="stable")
+    bounds = np.searchsorted(owner[order], np.arange(len(ys) + 1))
+    for i in np.flatnonzero(np.diff(bounds)):
+        sel = order[bounds[i]:bounds[i + 1]]
+        out[sel] = ys[i][pick[sel] - starts[i], :]
+    return out
+
+
+def _initialize(trials, params, config, defer_mu=False):
     from sklearn.decomposition import FactorAnalysis
 
     zdim, xdim = params["zdim"], params["xdim"]
-    y_all = np.concatenate([tr["y"] for tr in trials], axis=0)
-    nbin, ydim = y_all.shape
+    ys = [tr["y"] for tr in trials]
+    lengths = [y.shape[0] for y in ys]
+    nbin, ydim = int(sum(lengths)), ys[0].shape[-1]
     pick = np.random.choice(nbin, max(nbin // 10, 50))      # with replacement, like the reference
 
+    projection = None
     if params.get("transform") is None:
+        y_pick = _rows(ys, lengths, pick)                   # y_all[pick, :] of the reference, without the 200 MB concat
         fa = FactorAnalysis(n_components=zdim, random_state=0)
-        z = fa.fit_transform(y_all[pick, :])
+        z = fa.fit_transform(y_pick)
         params["transform"] = fa.transform
         if params.get("a") is None:
             params["a"] = fa.components_
         if params.get("b") is None:
-            params["b"] = np.log(np.maximum(y_all.mean(axis=0, keepdims=True), config["eps"]))
+            mean = np.concatenate(ys, axis=0).mean(axis=0, keepdims=True) if len(ys) == 1 or not _same_dtype(ys) else \
+                _mean_rows(ys, nbin)
+            params["b"] = np.log(np.maximum(mean, config["eps"]))
         if params.get("noise") is None:
-            params["noise"] = np.var(y_all[pick, :] - z @ fa.components_, ddof=0, axis=0)
+            params["noise"] = np.var(y_pick - z @ fa.components_, ddof=0, axis=0)
+        if defer_mu and params["a"] is fa.components_ and all(tr.get("mu") is None for tr in trials):
+            # FactorAnalysis.transform: ((X - mean) @ Wpsi') @ cov_z with Wpsi = components / noise_variance
+            wpsi = fa.components_ / fa.noise_variance_
+            cov_z = np.linalg.inv(np.eye(zdim) + wpsi @ fa.components_.T)
+            projection = (np.array(fa.mean_, dtype=float), np.ascontiguousarray(wpsi.T), cov_z)
 
     to_latent = params["transform"]
     for tr in trials:
         nt = tr["y"].shape[0]
-        if tr.get("mu") is None:
+        if tr.get("mu") is None and projection is None:
             tr["mu"] = to_latent(tr["y"])
         if tr.get("x") is None:
             tr["x"] = np.ones((nt, xdim, ydim))
             _mark_ones(tr["x"])
         tr["w"] = np.zeros((nt, zdim))
         tr["v"] = np.zeros((nt, zdim))
+    return projection
+
+
+def _same_dtype(ys):
+    return len({y.dtype for y in ys}) == 1
+
+
+def _mean_rows(ys, nbin):
+    """Column means of the concatenation of the blocks (one pass per block, no concatenation)."""
+    tot = np.zeros(ys[0].shape[1])
+    for y in ys:
+        tot += y.sum(axis=0)
+    return (tot / nbin)[None, :]
 
 
 def _mark_ones(x):
