@@ -170,6 +170,12 @@ VLGP_API int vlgp_lbfgsb_advance(void *handle, double f, const double *g, double
 VLGP_API int vlgp_lbfgsb_info(void *handle, double *f, int *nfev, int *nit, int *n_collapsed);
 VLGP_API int vlgp_lbfgsb_free(void *handle);
 
+/* ---- full posterior covariance: the T x T algebra of api.sample_posterior / util.posterior_cov ------------------------
+ * cov (T x T, host) = inv(inv(G G' + reg I) + diag(w)) for one latent of one member of the set (vlgp/api.py:160-166;
+ * reg = 0: K - K (1/W + K)^-1 K of vlgp/util.py:541-547), from the set's prior factor and its weights w, through the
+ * rank-r identity of csrc/postcov.cu (one r x r inverse instead of two T x T ones). */
+VLGP_API int vlgp_posterior_cov(vlgp_ctx *ctx, int set_id, int trial, int latent, double reg, double *cov);
+
 /* ---- constraints and convergence bookkeeping (vlgp/core.py:300-305,350-354,366-416) ------------------------------ */
 /* mu <- (mu - shift) @ M for every bin; shift (L) and M (L x L, row-major) may be NULL (0 / identity). */
 VLGP_API int vlgp_latent_affine(vlgp_ctx *ctx, int set_id, const double *shift, const double *M);

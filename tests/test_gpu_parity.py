@@ -605,6 +605,38 @@ def test_vem_general_regressors_golden(vl, case):
         assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
 
 
+def test_posterior_cov_and_sample_posterior(vl):
+    """api.posterior_cov / sample_posterior (vlgp/api.py:142-168, vlgp/util.py:541-547): the T x T covariance from the
+    device against the reference's expression evaluated in NumPy, and draws with the right moments."""
+    from oracle import vlgp_oracle as orc
+
+    g = load_golden("api_extras")
+    G = orc.make_cholesky([200], g["omega"], g["sigma"], 50)[200]
+    params = {"cholesky": {200: G}, "gp_noise": 1e-4, "dt": 1}
+    trial = {"mu": g["trial0_mu"], "w": g["trial0_w"]}
+    for reg in (1e-6, 1e-3, 0.0):
+        cov = vl.posterior_cov(trial, params, reg)
+        assert cov.shape == (3, 200, 200)
+        for k in range(3):
+            K = G[k] @ G[k].T
+            if reg > 0:
+                ref = np.linalg.inv(np.linalg.inv(K + reg * np.eye(200)) + np.diag(trial["w"][:, k]))
+            else:
+                ref = K - K @ np.linalg.solve(np.diag(1.0 / trial["w"][:, k]) + K, K)      # util.posterior_cov
+            assert relerr(cov[k], ref) < 5e-9, (reg, k)
+            assert np.array_equal(cov[k], cov[k].T) or relerr(cov[k], cov[k].T) < 1e-13
+    np.random.seed(5)
+    samples = vl.sample_posterior(trial, params, 400)
+    assert samples.shape == (400, 200, 3) and np.isfinite(samples).all()
+    cov = vl.posterior_cov(trial, params, 1e-6)
+    for k in range(3):
+        sd = np.sqrt(np.diag(cov[k]))
+        z = (samples[:, :, k].mean(axis=0) - trial["mu"][:, k]) / (sd / np.sqrt(400))
+        assert np.abs(z).max() < 6.0                                   # sample means within 6 standard errors
+        ratio = samples[:, :, k].var(axis=0) / np.diag(cov[k])
+        assert 0.6 < np.median(ratio) < 1.4
+
+
 def test_reference_api_smoke(vl):
     """The reference's own API test (tests/test_api.py:4-38 there) with `import vlgp_b200 as vlgp`: integer counts from
     np.random.poisson, an extra user key per trial, fit with every default, then transform on the fitted trials."""

@@ -262,18 +262,26 @@ def test_vem_general_regressors(case):
         assert relerr(np.stack([s[k] for s in segs]), g[p + "out_" + k]) < tol, k
 
 
-def test_sample_posterior_matches_reference():
-    """api.sample_posterior is host-side NumPy in the reference and here: same seed,
-    same inputs, same draws (vlgp/api.py:142-168)."""
-    from vlgp_b200 import api
-
+def test_posterior_cov_low_rank_identity_matches_the_reference_expression():
+    """The device computes the sample_posterior covariance inv(inv(K + reg I) + W) (vlgp/api.py:160-166) through
+    reg E^-1 + F Q^-1 F' (csrc/postcov.cu).  Here the identity itself is pinned, in NumPy, against the reference's
+    expression and against the covariance behind the reference's golden samples (tests/golden/api_extras.npz): equal to
+    the reference's own asymmetry (1e-9); reg = 0 reproduces util.posterior_cov (vlgp/util.py:541-547)."""
     g = load_golden("api_extras")
-    params = {"cholesky": orc.make_cholesky([200], g["omega"], g["sigma"], 50)}
-    trial = {"mu": g["trial0_mu"], "w": g["trial0_w"]}
-    np.random.seed(5)
-    samples = api.sample_posterior(trial, params, 4)
-    assert samples.shape == g["samples"].shape == (4, 200, 3)
-    assert relerr(samples, g["samples"]) < 1e-9
+    G = orc.make_cholesky([200], g["omega"], g["sigma"], 50)[200]
+    w = g["trial0_w"]
+    for k in range(3):
+        K = G[k] @ G[k].T
+        for reg in (1e-6, 1e-3):
+            ref = np.linalg.inv(np.linalg.inv(K + reg * np.eye(200)) + np.diag(w[:, k]))
+            E = 1.0 + reg * w[:, k]
+            F = G[k] / E[:, None]
+            Q = np.eye(50) + G[k].T @ ((w[:, k] / E)[:, None] * G[k])
+            cov = np.diag(reg / E) + F @ np.linalg.solve(Q, F.T)
+            assert relerr(cov, ref) < 5e-9
+        woodbury = K - K @ np.linalg.solve(np.diag(1.0 / w[:, k]) + K, K)
+        Q0 = np.eye(50) + G[k].T @ (w[:, k][:, None] * G[k])
+        assert relerr(G[k] @ np.linalg.solve(Q0, G[k].T), woodbury) < 1e-9
 
 
 def test_transform_new_trials_pipeline():

@@ -5,7 +5,7 @@
 
 The arithmetic runs in libvlgp_b200.so (hand-written sm_100a CUDA, ctypes C ABI); there is no CPU fallback.
 """
-from .api import fit, sample_posterior, transform  # noqa: F401
+from .api import fit, posterior_cov, sample_posterior, transform  # noqa: F401
 
-__all__ = ["fit", "sample_posterior", "transform"]
+__all__ = ["fit", "posterior_cov", "sample_posterior", "transform"]
 __version__ = "0.1.0"

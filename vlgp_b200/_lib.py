@@ -70,6 +70,7 @@ EXPORTS = {
     "vlgp_lbfgsb_advance": (C.c_int, [C.c_void_p, C.c_double, c_double_p, c_double_p, c_int_p]),
     "vlgp_lbfgsb_info": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_int_p, c_int_p]),
     "vlgp_lbfgsb_free": (C.c_int, [C.c_void_p]),
+    "vlgp_posterior_cov": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_double, c_double_p]),
     "vlgp_latent_affine": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p]),
     "vlgp_latent_affine_rows": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_i64_p, C.c_int64]),
     "vlgp_norms": (C.c_int, [ctx_p, C.c_int, c_double_p]),

@@ -14,7 +14,7 @@ from .gp import make_cholesky
 from .preprocess import get_params, get_config, fill_trials, fill_params, initialize
 from .util import cut_trials
 
-__all__ = ["fit", "sample_posterior", "transform"]
+__all__ = ["fit", "sample_posterior", "posterior_cov", "transform"]
 
 logger = logging.getLogger(__name__)
 
@@ -157,16 +157,39 @@ def transform(trials, params, config):
     return trials
 
 
-def sample_posterior(trial, params, nsamples, reg=1e-6):
-    """Draw ``nsamples`` paths from the (full-covariance) posterior of one trial; returns (nsamples, bins, factors).
-    Host-side like the reference (SURVEY.md section 8(f) item 2 lists the device version as future work)."""
-    mu, w = trial["mu"], trial["w"]
+def posterior_cov(trial, params, reg=1e-6):
+    """Full posterior covariance of every latent of one trial, (factors, bins, bins):
+    ``inv(inv(K + reg I) + diag(w))`` with ``K = G G'`` (vlgp/api.py:160-166; ``reg=0`` gives util.posterior_cov,
+    vlgp/util.py:541-547).  Computed on the device from the rank-r prior factor (csrc/postcov.cu)."""
+    from .engine import get_engine
+
+    mu, w = np.asarray(trial["mu"], dtype=float), np.asarray(trial["w"], dtype=float)
     nbins, nfactors = mu.shape
     G = params["cholesky"][nbins]
+    eng = get_engine()
+    model = {"ydim": 1, "zdim": nfactors, "xdim": 1, "rank": G.shape[2], "gp_noise": params.get("gp_noise", 1e-4),
+             "dt": params.get("dt", 1), "likelihood": np.array(["poisson"])}
+    eng.ensure_model(model)
+    out = np.empty((nfactors, nbins, nbins))
+    with eng.new_trials([nbins]) as ts:
+        ts.set_cholesky(nbins, G)
+        ts.set_state(mu=mu, v=np.zeros_like(mu), w=w)
+        for k in range(nfactors):
+            out[k] = ts.posterior_cov(0, k, reg)
+    return out
+
+
+def sample_posterior(trial, params, nsamples, reg=1e-6):
+    """Draw ``nsamples`` paths from the (full-covariance) posterior of one trial; returns (nsamples, bins, factors)
+    (vlgp/api.py:142-168).  The bins x bins covariance of every latent comes from the device (``posterior_cov``); the
+    draws use ``np.random.multivariate_normal`` on the host like the reference, so they consume the global generator
+    the same way.  (The reference's own draws are not reproducible beyond that: the covariance has ~bins - rank
+    singular values at the level of ``reg``, and the SVD inside multivariate_normal picks an arbitrary basis of that
+    subspace -- a 1e-10 change of the matrix changes individual samples at O(1) while their distribution is the same.)"""
+    mu = np.asarray(trial["mu"], dtype=float)
+    nbins, nfactors = mu.shape
+    cov = posterior_cov(trial, params, reg)
     out = np.empty((nsamples, nbins, nfactors))
-    eye = np.eye(nbins)
     for k in range(nfactors):
-        K = G[k] @ G[k].T
-        cov = np.linalg.inv(np.linalg.inv(K + reg * eye) + np.diag(w[:, k]))
-        out[:, :, k] = np.random.multivariate_normal(mu[:, k], cov, size=nsamples)
+        out[:, :, k] = np.random.multivariate_normal(mu[:, k], cov[k], size=nsamples)
     return out

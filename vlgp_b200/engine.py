@@ -524,6 +524,15 @@ class TrialSet:
                                              C.byref(rounds)), "hstep_optimize")
         return np.exp(res), fval, nfev, task, rounds.value
 
+    def posterior_cov(self, trial, latent, reg=1e-6):
+        """(T, T) posterior covariance inv(inv(G G' + reg I) + diag(w)) of one latent of one member of the set."""
+        lib, ctx = self._lib()
+        T = int(self.lengths[int(trial)])
+        cov = np.empty((T, T))
+        self.eng._ck(lib.vlgp_posterior_cov(ctx, self.id, int(trial), int(latent), float(reg), dptr(cov)), "posterior_cov")
+        self.d2h_bytes += cov.nbytes
+        return cov
+
     def latent_affine(self, shift=None, M=None, rows=None):
         """mu <- (mu - shift) @ M on every bin, or on the listed bins only (``rows``: bin indices, each once)."""
         lib, ctx = self._lib()
