@@ -267,7 +267,7 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     };
     F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db);
     F(ctx->d_bpart); F(ctx->d_bstat);
-    F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_ymom); F(ctx->d_ppack); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_small); F(ctx->d_flush);
+    F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_ymom); F(ctx->d_ppack); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_smslots); F(ctx->d_small); F(ctx->d_flush);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int i = 0; i < 2; ++i) {

@@ -106,6 +106,7 @@ struct vlgp_ctx {
     int mpart_grid = 0;
     double *d_gshared = nullptr; // Gaussian-channel shared moments: L*L + 2L + 1
     int *d_flags = nullptr;      // device counters (failures etc.), 16 ints
+    int *d_smslots = nullptr;    // one counter per SM: the resident CTAs of the segment E-step learn their slot on the SM
     int *h_flags = nullptr;      // pinned
     double *h_pin = nullptr;     // pinned 4 KB staging for tiny D2H/H2D
     double *d_small = nullptr;   // 4 KB device staging

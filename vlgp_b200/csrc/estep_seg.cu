@@ -59,7 +59,10 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     p.np = 8 * ((N + 7) / 8);
     if (p.np % 16 == 0) p.np += 8;               // = 8 mod 16: the B-operand fragment loads are bank-conflict-free
     p.kp = 4 * ((2 * L + 1 + 3) / 4);
-    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8, p.kp, p.np);
+    const bool fast = !ctx->any_gauss && ts->ydtype == VLGP_Y_U8 && !getenv("VLGP_NO_FAST_ESTEP");
+    p.fused = fast && p.use_dmma && !getenv("VLGP_ESTEP_NO_FUSED");
+    const bool stage_y = ts->ydtype == VLGP_Y_U8 && !p.fused;     // the fused pipeline reads the counts once, in place
+    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total);
     bool big = false;
     for (int l = 0; l < L; ++l)
         if (p.nc[l] > 16) big = true;
@@ -73,11 +76,10 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
             p.ldg[l] = ctx->rank;
         }
         big = true;                          // the NBMAX = 4 instantiations carry the in-place path
-        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, ts->ydtype == VLGP_Y_U8, p.kp, p.np);
+        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total);
     }
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
     int rc = VLGP_OK;
-    const bool fast = !ctx->any_gauss && ts->ydtype == VLGP_Y_U8 && !getenv("VLGP_NO_FAST_ESTEP");
     if (big && p.use_dmma && fast) rc = launch_seg_variant<4, true>(ctx, ts, p, smem, handled);
     else if (big && p.use_dmma) rc = launch_seg_variant<4, false>(ctx, ts, p, smem, handled);
     else if (fast) rc = launch_seg_variant<2, true>(ctx, ts, p, smem, handled);

@@ -38,6 +38,7 @@ struct SegArgs {
     int g_global;                 // 1: the factors do not fit in SMEM next to everything else and are read in place from
                                   //    HBM / L2 (NBMAX = 4 variants only; goff then indexes p.G, g_total = 0)
     int use_dmma;                 // every nc <= 32: Gram / inverse / variance on the FP64 tensor path
+    int fused;                    // tensor-path rate passes and use_dmma: the fused pipeline (fused_a .. fused_c)
     const void *y;
     int ydtype;
     double *mu, *v, *w, *dmu;
@@ -51,6 +52,8 @@ struct SegArgs {
     int *flags;
     int tpb, chunk;               // threads per bin and neurons per thread in the rate passes
     int np, kp;                   // tensor-path rate passes: padded neuron count (= 8 mod 16) and rows of the operand Bx
+    int *sm_slots;                // per-SM arrival counters (zeroed before the launch), see estep_seg_kernel
+    int stagger;                  // cycles by which the k-th CTA to arrive on an SM delays its start
     int skip;                     // debug/timing only (VLGP_DEBUG_SKIP): 1 rate passes, 2 mean step, 4 factor, 8 variance
 };
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ int ldodd(int n) { return n | 1; }
 
 template <int LT>
 struct Smem {
-    double *a, *a2, *b, *inv_noise, *Mi, *mu, *v, *w, *ra, *dmu, *part, *vec;
+    double *a, *a2, *b, *inv_noise, *Mi, *mu, *v, *w, *ra, *dmu, *part, *vec, *ya, *etab;
     const double *Gs;             // compact factors in SMEM, or p.G itself (SegArgs::g_global)
     uint8_t *pois, *ys;
     __device__ Smem(unsigned char *base, const SegArgs &p) {
@@ -78,17 +81,21 @@ struct Smem {
         dmu = d; d += W * LT;
         part = d;                                 // rate passes: tpb x W x LT partial sums ...
         vec = d;                                  // ... aliased with the per-latent vectors (3 x 64) of the r x r phases
-        d += max(p.tpb * W * LT, LT * 192);
+                                                  // (fused path: NWARP x col_total partial projections + col_total)
+        d += max(max(p.tpb * W * LT, LT * 192), (NWARP + 1) * p.col_total);
+        ya = d; d += W * LT;                      // fused path: y a_l' per (bin, latent), constant during the launch's iterations
+        etab = d; d += 32;                        // 2^(j/32) (common.cuh: VLGP_EXP_T)
         pois = (uint8_t *)d;
         ys = pois + ((N + 15) / 16) * 16;
     }
 };
 
 __host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8,
-                                                 int kp, int np) {
-    const size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
+                                                 int kp, int np, int col_total) {
+    size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
+    if ((size_t)(NWARP + 1) * col_total > un) un = (size_t)(NWARP + 1) * col_total;
     const size_t par = (size_t)2 * LT * N + 2 * N > (size_t)kp * np ? (size_t)2 * LT * N + 2 * N : (size_t)kp * np;
-    size_t d = par + g_total + m_total + (size_t)5 * W * LT + un;
+    size_t d = par + g_total + m_total + (size_t)6 * W * LT + 32 + un;
     size_t bytes = d * sizeof(double) + ((N + 15) / 16) * 16;
     if (y_u8) bytes += ((size_t)W * N + 15) / 16 * 16;
     return bytes;
@@ -183,13 +190,52 @@ __device__ __forceinline__ void rate_pass_two_bins(const SegArgs &p, const Smem<
 // 3 + 2 DMMA and 22 FP64-pipe instructions per 64 (bin, neuron) entries at L = 5 against ~70 FP64-pipe instructions
 // per entry pair in the scalar form: the contractions move to the tensor pipe and run beside the exponentials.  The
 // row tile's output is complete inside the warp: no partial sums in shared memory, one barrier per pass instead of two.
-template <int LT, int STAGE>
-__device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> &s) {
+// trunc_exp2 (common.cuh) for the tensor-path rate passes: bit-identical values, fewer issue slots.  On sm_100a an FP64
+// instruction holds the issue port of its sub-partition for two cycles and a DMMA for sixteen, every other instruction
+// for one, and nothing overlaps (scripts/mb/mb_rate_pass.cu, mb_fp64_ops.cu: a column-tile step costs the SUM of its
+// slots), so the integer and select instructions around the polynomial are not free:
+//   * the clamps test the high word (x >= 10 <=> hi(x) >= hi(10.0) as signed integers, x < -708 <=> hi(x) > hi(-708.0)
+//     as unsigned ones, up to values within 1e-13 below -708 which need no clamp): 3 slots instead of 4 each;
+//   * the table 2^(j/32) is read from shared memory (2 slots instead of 5 for the generic-address __ldg);
+//   * no lower bound on the exponent: x >= -708 already implies (m >> 5) >= -1022.
+__device__ __forceinline__ void trunc_exp2_tile(double x0, double x1, const double *tab, double &e0, double &e1) {
+    const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
+    x0 = h0 >= 0x40240000 ? 10.0 : x0;
+    x1 = h1 >= 0x40240000 ? 10.0 : x1;
+    x0 = (unsigned)h0 > 0xC0862000u ? -708.0 : x0;
+    x1 = (unsigned)h1 > 0xC0862000u ? -708.0 : x1;
+    const double shift = 6755399441055744.0;
+    const double m0 = fma(x0, VLGP_EXP_INV, shift), m1 = fma(x1, VLGP_EXP_INV, shift);
+    const int i0 = __double2loint(m0), i1 = __double2loint(m1);
+    const double tj0 = tab[i0 & 31], tj1 = tab[i1 & 31];
+    const double t0 = m0 - shift, t1 = m1 - shift;
+    double r0 = fma(t0, -VLGP_EXP_HI, x0), r1 = fma(t1, -VLGP_EXP_HI, x1);
+    r0 = fma(t0, -VLGP_EXP_LO, r0);
+    r1 = fma(t1, -VLGP_EXP_LO, r1);
+    double p0 = VLGP_EXP_C[0], p1 = VLGP_EXP_C[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+        p0 = fma(p0, r0, VLGP_EXP_C[k]);
+        p1 = fma(p1, r1, VLGP_EXP_C[k]);
+    }
+    p0 *= r0;
+    p1 *= r1;
+    const double q0 = fma(tj0, p0, tj0), q1 = fma(tj1, p1, tj1);
+    e0 = __hiloint2double(__double2hiint(q0) + ((i0 >> 5) << 20), __double2loint(q0));
+    e1 = __hiloint2double(__double2hiint(q1) + ((i1 >> 5) << 20), __double2loint(q1));
+}
+
+// The column-tile loop of one row tile (warp wid, 8 wid < W): on return lane (r, q) holds, per output tile o, the sums over
+// neurons for bin 8 wid + r and latents 8 o + 2 q, 8 o + 2 q + 1 (STAGE 2: of a^2 / 2, to be doubled by the caller).
+// FUSED: the y term of stage 1 is left out (the fused pipeline keeps y a_l' in s.ya and subtracts the sum of rate x a_l),
+// the exponential reads its table from shared memory.
+template <int LT, int STAGE, bool FUSED = false>
+__device__ __forceinline__ void rate_tiles(const SegArgs &p, const Smem<LT> &s, Tile (&acc)[(LT + 7) / 8]) {
     constexpr int KS = (2 * LT + 1 + 3) / 4;        // k4 steps of the x contraction
     constexpr int NOT = (LT + 7) / 8;               // output tiles of 8 latents
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
     const int W = p.W, N = p.N, NP = p.np;
-    if (8 * wid < W) {
+    {
         const int t = 8 * wid + r;
         const bool tin = t < W;
         double afr[KS];
@@ -204,7 +250,6 @@ __device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> 
             }
             afr[kk] = val;
         }
-        Tile acc[NOT];
 #pragma unroll
         for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.0;
         const double *Bx = s.a;
@@ -215,7 +260,7 @@ __device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> 
         auto tile_pair = [&](int j, double ea, double eb) {
             const int n0 = 8 * j + 2 * q;
             double c0 = ea, c1 = eb;
-            if (STAGE == 1) {
+            if (STAGE == 1 && !FUSED) {
                 const double y0 = (tin && n0 < N) ? (double)yrow[n0] : 0.0;
                 const double y1 = (tin && n0 + 1 < N) ? (double)yrow[n0 + 1] : 0.0;
                 c0 = y0 - ea;
@@ -249,9 +294,57 @@ __device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> 
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) dmma(x, afr[kk], Bx[(4 * kk + q) * NP + 8 * j + r]);
             double e0, e1;
-            trunc_exp2(x.x, x.y, e0, e1);
+            if (FUSED) trunc_exp2_tile(x.x, x.y, s.etab, e0, e1);
+            else trunc_exp2(x.x, x.y, e0, e1);
             tile_pair(j, e0, e1);
         }
+    }
+}
+
+// s.ya[t][l] = sum_n y[t][n] a[l][n] for this warp's row tile (fused path, once per segment; counts read in place)
+template <int LT>
+__device__ __forceinline__ void ya_tiles(const SegArgs &p, const Smem<LT> &s, const uint8_t *yseg) {
+    constexpr int NOT = (LT + 7) / 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int W = p.W, N = p.N, NP = p.np;
+    const int t = 8 * wid + r;
+    const bool tin = t < W;
+    const uint8_t *yrow = yseg + (size_t)(tin ? t : 0) * N;
+    Tile acc[NOT];
+#pragma unroll
+    for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.0;
+    for (int j = 0; j < (NP >> 3); ++j) {
+        const int n0 = 8 * j + 2 * q;
+        const double y0 = (tin && n0 < N) ? (double)yrow[n0] : 0.0;
+        const double y1 = (tin && n0 + 1 < N) ? (double)yrow[n0 + 1] : 0.0;
+#pragma unroll
+        for (int o = 0; o < NOT; ++o) {
+            double2 b2 = make_double2(0.0, 0.0);
+            if (8 * o + r < LT) b2 = *reinterpret_cast<const double2 *>(s.a + (r + 8 * o) * NP + n0);
+            dmma(acc[o], y0, b2.x);
+            dmma(acc[o], y1, b2.y);
+        }
+    }
+    if (tin) {
+#pragma unroll
+        for (int o = 0; o < NOT; ++o) {
+            const int l0 = 8 * o + 2 * q;
+            if (l0 < LT) s.ya[t * LT + l0] = acc[o].x;
+            if (l0 + 1 < LT) s.ya[t * LT + l0 + 1] = acc[o].y;
+        }
+    }
+}
+
+template <int LT, int STAGE>
+__device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> &s) {
+    constexpr int NOT = (LT + 7) / 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int W = p.W;
+    if (8 * wid < W) {
+        const int t = 8 * wid + r;
+        const bool tin = t < W;
+        Tile acc[NOT];
+        rate_tiles<LT, STAGE>(p, s, acc);
         double *out = (STAGE == 1) ? s.ra : s.w;
         const double sc = (STAGE == 1) ? 1.0 : 2.0;          // Bx holds a^2 / 2
         if (tin) {
@@ -596,6 +689,178 @@ __device__ __forceinline__ bool factor_variance_dmma(const SegArgs &p, const Sme
     return factor_variance_dmma_nb<LT, (NBMAX >= 4 ? 4 : 2)>(p, s, l, do_var);
 }
 
+// ---- fused pipeline (tensor-path rate passes + tensor-path factorisation) ---------------------------------------------
+// An iteration of the unfused pipeline spends more time in the r x r phases than in the rate passes (ncu, config 2: 35 %
+// of the warp samples in the two rate passes, 22 % in the five barrier-separated mat-vec stages of the mean step, 35-40 %
+// in the one-warp-per-latent factor / variance phase during which three of the eight warps idle).  The fused pipeline
+// gives the row-tile warps of the rate passes the r x r work that belongs to their own 8 bins and shortens the rest:
+//   mean step     delta = u - G Minv G' W u with u = G G' ra - mu equals, exactly,  G Minv G' (ra + w o mu) - mu
+//                 (Minv = (I + G'WG)^-1: G'Wu = (Minv^-1 - I) p - q with p = G' ra, q = G'(w o mu), so
+//                 Minv G'Wu = p - Minv (p + q)): three products instead of five.  The first one, s = G' z, is summed per
+//                 row tile by the warp that just produced ra (phase A), the small r x r product m = Minv s is spread
+//                 over the CTA (phase B), and G m for a warp's own bins opens its second rate pass (phase C);
+//   variance      v_t = G_t Minv G_t' of a warp's own bins opens its FIRST rate pass of the next iteration (phase A),
+//                 (row tile) x Minv by DMMA as before, 7 warps x L latents instead of L warps x 7 row tiles;
+//   factor        Gram + blocked sweep only, still one warp per latent (phase D).
+// Four block barriers per iteration instead of eight.
+template <int LT, int NB>
+__device__ __forceinline__ void variance_rows_nb(const SegArgs &p, const Smem<LT> &s, int l) {
+    constexpr int LDM = 8 * NB + 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3, c0 = 2 * q;
+    const int nc = p.nc[l], ldg = p.ldg[l];
+    const double *M = s.Mi + p.moff[l];
+    const int trow = 8 * wid + r;
+    const bool tin = trow < p.W;
+    const double *grow = s.Gs + p.goff[l] + (tin ? trow : 0) * ldg;
+    double aop[2 * NB];
+#pragma unroll
+    for (int k = 0; k < 2 * NB; ++k) {
+        const int c = 4 * k + q;
+        aop[k] = (tin && c < nc) ? grow[c] : 0.0;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int jt = 0; jt < NB; ++jt) {
+        Tile T{0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < 2 * NB; ++k)
+            if (4 * k < nc) dmma(T, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
+        const int c = 8 * jt + c0;
+        const double g0 = (tin && c < nc) ? grow[c] : 0.0;
+        const double g1 = (tin && c + 1 < nc) ? grow[c + 1] : 0.0;
+        acc = fma(T.x, g0, acc);
+        acc = fma(T.y, g1, acc);
+    }
+    acc += __shfl_xor_sync(FULL, acc, 1);
+    acc += __shfl_xor_sync(FULL, acc, 2);
+    if (q == 0 && tin) s.v[trow * LT + l] = -acc;
+}
+
+template <int LT, int NBMAX>
+__device__ __forceinline__ void variance_rows(const SegArgs &p, const Smem<LT> &s, int l) {
+    if (p.nc[l] <= 8) variance_rows_nb<LT, 1>(p, s, l);
+    else if (NBMAX == 2 || p.nc[l] <= 16) variance_rows_nb<LT, 2>(p, s, l);
+    else if (p.nc[l] <= 24) variance_rows_nb<LT, (NBMAX >= 3 ? 3 : 2)>(p, s, l);
+    else variance_rows_nb<LT, (NBMAX >= 4 ? 4 : 2)>(p, s, l);
+}
+
+__device__ __forceinline__ int col_latent(const SegArgs &p, int LT, int idx) {
+    int l = 0;
+    while (l + 1 < LT && idx >= p.coloff[l + 1]) ++l;
+    return l;
+}
+
+// Phase A: [variance of the own bins from the previous factorisation] -> rate pass 1 -> z = ra + w o mu -> this row
+// tile's part of s_l = G_l' z_l for every latent.  Ends with a block barrier.
+template <int LT, int NBMAX>
+__device__ __forceinline__ void fused_a(const SegArgs &p, const Smem<LT> &s, const int *bad, bool do_var) {
+    constexpr int NOT = (LT + 7) / 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int W = p.W;
+    if (8 * wid < W) {
+        if (do_var) {
+            for (int l = 0; l < LT; ++l)
+                if (!bad[l]) variance_rows<LT, NBMAX>(p, s, l);      // a failed solve keeps v (vlgp/core.py:112)
+            __syncwarp();
+        }
+        Tile acc[NOT];
+        if (!(p.skip & 1)) rate_tiles<LT, 1, true>(p, s, acc);
+        else
+            for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.0;
+        const int t = 8 * wid + r;
+        if (t < W) {                                  // z = (y - rate) a_l' + w o mu
+#pragma unroll
+            for (int o = 0; o < NOT; ++o) {
+                const int l0 = 8 * o + 2 * q;
+                if (l0 < LT) s.ra[t * LT + l0] = fma(s.w[t * LT + l0], s.mu[t * LT + l0], s.ya[t * LT + l0] - acc[o].x);
+                if (l0 + 1 < LT)
+                    s.ra[t * LT + l0 + 1] = fma(s.w[t * LT + l0 + 1], s.mu[t * LT + l0 + 1], s.ya[t * LT + l0 + 1] - acc[o].y);
+            }
+        }
+        __syncwarp();
+        const int rows = min(8, W - 8 * wid);
+        double *part = s.part + wid * p.col_total;
+        for (int idx = lane; idx < p.col_total; idx += 32) {
+            const int l = col_latent(p, LT, idx), ldg = p.ldg[l];
+            const double *g = s.Gs + p.goff[l] + 8 * wid * ldg + (idx - p.coloff[l]);
+            const double *z = s.ra + 8 * wid * LT + l;
+            double a = 0.0;
+            for (int tt = 0; tt < rows; ++tt) a = fma(g[tt * ldg], z[tt * LT], a);
+            part[idx] = a;
+        }
+    }
+    __syncthreads();
+}
+
+// Phase B: m_l = Minv_l s_l with s_l the sum of the row tiles' parts (fixed order); four lanes per entry.  M holds -Minv.
+template <int LT>
+__device__ __forceinline__ void fused_b(const SegArgs &p, const Smem<LT> &s) {
+    const int tid = threadIdx.x, sub = tid & 3;
+    const int nw = (p.W + 7) >> 3, ct = p.col_total;
+    double *mvec = s.part + NWARP * ct;
+    for (int base = 0; base < ct; base += NT / 4) {
+        const int idx = base + (tid >> 2);
+        double acc = 0.0;
+        if (idx < ct) {
+            const int l = col_latent(p, LT, idx), i = idx - p.coloff[l], nc = p.nc[l], ldm = p.ldm[l];
+            const double *M = s.Mi + p.moff[l];
+            const double *part0 = s.part + p.coloff[l];
+            for (int j = sub; j < nc; j += 4) {
+                double sj = 0.0;
+                for (int w = 0; w < nw; ++w) sj += part0[w * ct + j];
+                acc = fma(M[j * ldm + i], sj, acc);
+            }
+        }
+        acc += __shfl_xor_sync(FULL, acc, 1);
+        acc += __shfl_xor_sync(FULL, acc, 2);
+        if (idx < ct && sub == 0) mvec[idx] = -acc;
+    }
+    __syncthreads();
+}
+
+// Phase C: delta = clip(G m - mu) on the own bins (a failed factorisation zeroes the step, vlgp/core.py:92-94), then
+// rate pass 2 -> w.  Ends with a block barrier.
+template <int LT>
+__device__ __forceinline__ void fused_c(const SegArgs &p, const Smem<LT> &s, const int *bad) {
+    constexpr int NOT = (LT + 7) / 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int W = p.W;
+    if (8 * wid < W) {
+        const double *mvec = s.part + NWARP * p.col_total;
+        for (int idx = lane; idx < 8 * LT; idx += 32) {
+            const int l = idx >> 3, t = 8 * wid + (idx & 7);
+            if (t < W) {
+                double d = 0.0;
+                if (!bad[l]) {
+                    const int nc = p.nc[l];
+                    const double *g = s.Gs + p.goff[l] + t * p.ldg[l];
+                    const double *mv = mvec + p.coloff[l];
+                    double a = 0.0;
+                    for (int j = 0; j < nc; ++j) a = fma(g[j], mv[j], a);
+                    d = clipd(a - s.mu[t * LT + l], p.dmu_bound);
+                }
+                s.dmu[t * LT + l] = d;
+                s.mu[t * LT + l] += d;
+            }
+        }
+        __syncwarp();
+        Tile acc[NOT];
+        if (!(p.skip & 1)) rate_tiles<LT, 2, true>(p, s, acc);
+        else
+            for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.5;
+        const int t = 8 * wid + r;
+        if (t < W) {
+#pragma unroll
+            for (int o = 0; o < NOT; ++o) {
+                const int l0 = 8 * o + 2 * q;
+                if (l0 < LT) s.w[t * LT + l0] = 2.0 * acc[o].x;              // Bx holds a^2 / 2
+                if (l0 + 1 < LT) s.w[t * LT + l0 + 1] = 2.0 * acc[o].y;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // Factorisation for every latent: on return M_l = -(I + G_l' W_l G_l)^-1, bad[l] says whether that failed (not positive
 // definite), and -- if do_var -- v holds the new marginal variances of the latents that did not fail.  Ends with a
 // block barrier.
@@ -793,6 +1058,21 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
     const int tid = threadIdx.x;
     const int W = p.W, N = p.N;
 
+    // The CTAs resident on one SM run the same phase sequence at the same pace: started together they stay in lockstep,
+    // all of them in the pipe-bound rate passes at the same time and all of them in the latency-bound r x r phases at the
+    // same time.  The k-th CTA to arrive on an SM therefore waits k * stagger cycles once, so that the phases interleave.
+    if (p.stagger > 0) {
+        __shared__ int slot_s;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            slot_s = atomicAdd(p.sm_slots + smid, 1);
+        }
+        __syncthreads();
+        const long long wait = (long long)slot_s * p.stagger, t0 = clock64();
+        while (clock64() - t0 < wait) __nanosleep(200);
+    }
+
     // ---- once per CTA: parameters and the compact prior factors ------------------------------------------------------
 #ifndef VLGP_ESTEP_SCALAR_RATE_PASS
     if (FAST) {          // operand of the tensor-path rate passes: rows a_l | a_l^2 / 2 | b | 0, columns padded with 0
@@ -813,6 +1093,7 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
         for (int n = tid; n < N; n += NT) ((double2 *)s.b)[n] = p.pb[n];
     }
     for (int n = tid; n < N; n += NT) s.pois[n] = p.poisson[n];
+    if (tid < 32) s.etab[tid] = VLGP_EXP_T[tid];
     if (NBMAX == 4 && p.g_global) {
         s.Gs = p.G;                  // read in place (generic loads; only the NBMAX = 4 instantiations pay for that)
     } else {
@@ -837,13 +1118,30 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
             s.w[i] = p.w[bin0 * LT + i];
             s.dmu[i] = 0.0;
         }
-        if (p.ydtype == VLGP_Y_U8) {
+        if (FAST && p.fused) {
+            if (8 * (tid >> 5) < W) ya_tiles<LT>(p, s, (const uint8_t *)p.y + bin0 * N);
+        } else if (p.ydtype == VLGP_Y_U8) {
             const uint8_t *ysrc = (const uint8_t *)p.y + bin0 * N;
             for (int i = tid; i < W * N; i += NT) s.ys[i] = ysrc[i];
         }
         if (tid < LT) bad[tid] = 0;
         __syncthreads();
 
+        if (FAST && p.fused && p.n_iter > 0) {
+            factor_all<LT, NBMAX>(p, s, bad, false);                  // the first mean step uses the incoming w
+            for (int it = 0; it < p.n_iter; ++it) {
+                fused_a<LT, NBMAX>(p, s, bad, it > 0 && p.method_vb && !(p.skip & 8));
+                if (!(p.skip & 2)) fused_b<LT>(p, s);
+                fused_c<LT>(p, s, bad);
+                if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT, NBMAX>(p, s, bad, false);
+            }
+            if (p.method_vb && p.n_iter > 0) {                         // variances of the last factorisation
+                if (8 * (tid >> 5) < W)
+                    for (int l = 0; l < LT; ++l)
+                        if (!bad[l]) variance_rows<LT, NBMAX>(p, s, l);
+                __syncthreads();
+            }
+        } else
         for (int it = 0; it < p.n_iter; ++it) {
             if (!(p.skip & 1)) rate_pass<LT, 1, FAST>(p, s, bin0);    // ends with a barrier; part (aliases vec) is free again
             if (it == 0) factor_all<LT, NBMAX>(p, s, bad, false);      // the first mean step uses the incoming w
@@ -893,6 +1191,13 @@ int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *han
     if (per_sm < 1) return VLGP_OK;       // does not fit: let the general kernel handle it
     int grid = per_sm * ctx->prop.multiProcessorCount;
     if (grid > p.n_seg) grid = p.n_seg;
+    if (!ctx->d_smslots) CK(cudaMalloc(&ctx->d_smslots, 1024 * sizeof(int)));
+    p.sm_slots = ctx->d_smslots;
+    {
+        static const char *env = getenv("VLGP_ESTEP_STAGGER");
+        p.stagger = env ? atoi(env) : 0;
+    }
+    if (p.stagger > 0) CK(cudaMemsetAsync(ctx->d_smslots, 0, 1024 * sizeof(int), ctx->stream));
     estep_seg_kernel<LT, NBMAX, FAST><<<grid, NT, smem, ctx->stream>>>(p);
     CKL();
     *handled = true;
