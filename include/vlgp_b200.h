@@ -228,6 +228,14 @@ VLGP_API int vlgp_comm_attach_shm(vlgp_ctx *ctx, void *handle);
  * instead of an NCCL launch in between.  *enabled = 0 (and nothing changes) when some rank cannot map some peer. */
 VLGP_API int vlgp_comm_enable_p2p(vlgp_ctx *ctx, int *enabled);
 
+/* ---- arithmetic of the E-step rate passes (BASELINE.json configs[2]: "fp32") ----------------------------------------
+ * bits = 64 (default): everything in double precision, results match the reference (vlgp/core.py:68-113) to 1e-10.
+ * bits = 32: the rate passes of the segment E-step (linear predictor, exp link, sums over neurons -- the bulk of the
+ * arithmetic) run in single precision; Gram matrices, inverses, variances, the mean step, the M- and H-step and all state
+ * stay double.  Applies to window-length segments with Poisson channels and uint8 counts; other inputs keep 64.
+ * Posterior means then agree with the reference to about 1e-5 relative (tests/test_gpu_parity.py). */
+VLGP_API int vlgp_set_precision(vlgp_ctx *ctx, int bits);
+
 /* ---- measurement helpers (used by bench.py only) ------------------------------------------------------------------ */
 /* Measured FP64 FMA peak (TFLOP/s) of this GPU with a register-resident DFMA loop, and with mma.sync.m8n8k4.f64. */
 VLGP_API int vlgp_peak_fp64(vlgp_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

@@ -145,8 +145,8 @@ int main() {
     for (int i = 0; i < 12 * NP; ++i) h[i] = 0.01 * ((i * 7) % 13 - 6);
     cudaMemcpy(Bx, h, sizeof(h), cudaMemcpyHostToDevice);
     cudaMemset(y, 1, W * N);
-    for (int c : {3, 1}) {
-        for (int w : {7, 4, 1}) {
+    for (int c : {3}) {
+        for (int w : {8, 7, 6, 4}) {
             run<7>("full (x DMMA, exp, acc DMMA)", c, w, Bx, y, out);
             run<5>("no exp", c, w, Bx, y, out);
             run<2>("exp only", c, w, Bx, y, out);

@@ -19,6 +19,8 @@ core.update_v(trials, params, config)
 segs = bench.cut(trials, params, config)
 make_cholesky(segs, params, config)
 config["max_iter"] = config["min_iter"] = 1
+if os.environ.get("VLGP_TIME_DTYPE"):
+    config["dtype"] = os.environ["VLGP_TIME_DTYPE"]
 out = sys.stdout
 sys.stdout = open(os.devnull, "w")
 eng = get_engine()

@@ -301,14 +301,14 @@ def test_fit_fixed_omega_golden(vl):
 # ----------------------------------------------------------------------------------------------------------------------
 # seeded comparisons with the oracle at sizes it finishes in seconds, and properties at full size
 # ----------------------------------------------------------------------------------------------------------------------
-def _problem(seed, n_trials, T, N, L, lik=None, window=50):
+def _problem(seed, n_trials, T, N, L, lik=None, window=50, a_scale=0.3):
     from vlgp_b200.synth import make_trials
     from oracle import vlgp_oracle as orc
 
     rng = np.random.default_rng(seed)
     trials = make_trials(n_trials, T, N, L, seed=seed + 100)
     poisson = np.ones(N, bool) if lik is None else np.asarray(lik) == "poisson"
-    params = dict(a=0.3 * rng.standard_normal((L, N)), b=np.full((1, N), np.log(0.08)), noise=0.5 + rng.random(N),
+    params = dict(a=a_scale * rng.standard_normal((L, N)), b=np.full((1, N), np.log(0.08)), noise=0.5 + rng.random(N),
                   omega=np.exp(rng.uniform(np.log(2e-3), np.log(4e-2), L)), sigma=np.ones(L),
                   likelihood=np.where(poisson, "poisson", "gaussian"), zdim=L, ydim=N, xdim=1, rank=50, gp_noise=1e-4,
                   dt=1)
@@ -388,6 +388,49 @@ def test_estep_config2_shape_subset_vs_oracle(vl):
     orc.update_w(s_ref, params)
     for j, i in enumerate(pick):
         assert relerr(segs[i]["w"], s_ref[j]["w"]) < STEP_TOL
+
+
+F32_TOL = 1e-5          # posterior means, single-precision rate passes (north_star: "within 1e-5 relative of reference")
+
+
+@pytest.mark.parametrize("shape", ["golden_poisson_it25", "config2", "config3"])
+def test_estep_float32_rate_passes(vl, shape):
+    """config["dtype"] = "float32" (BASELINE.json configs[2]): the segment E-step with its rate passes in single precision
+    (csrc/estep_seg_impl.cuh: rate_tiles_f32; Gram / inverse / variance / mean step stay double).  Posterior means within
+    F32_TOL of the reference's output (golden from vlgp/core.py:22-120) and of the oracle on the config-2 and config-3
+    shapes (N = 200, L = 10); variances and weights within 1e-4.  The result must DIFFER from the double-precision run
+    (the switch did something) and dtype="float64" afterwards must be bit-identical to a run that never switched."""
+    from vlgp_b200 import core
+    from oracle import vlgp_oracle as orc
+
+    if shape.startswith("golden"):
+        g = load_golden("estep")
+        p = "poisson_it25_"
+        segs, params = _segs(g, p), _params(g, p)
+        params["cholesky"] = {50: g[p + "G"]}
+        ref = {k: g[p + "out_" + k] for k in ("mu", "v", "w")}
+    else:
+        # (at L = 10 a loading of scale 0.3 makes the Jacobi-over-latents Newton iteration of some segments oscillate
+        # against the +-dmu_bound clip: rounding differences between any two implementations are then amplified to
+        # 1e-2 within 25 iterations, double precision included; scale 0.1 is a contracting iteration)
+        N, L, sc = (100, 5, 0.3) if shape == "config2" else (200, 10, 0.1)
+        segs, params = _problem(11, 4, 1000, N, L, a_scale=sc)
+        s_ref = copy.deepcopy(segs)
+        orc.estep(s_ref, copy.deepcopy(params), _cfg(Eniter=25))
+        ref = {k: np.stack([s[k] for s in s_ref]) for k in ("mu", "v", "w")}
+    s64, s32, s64b = copy.deepcopy(segs), copy.deepcopy(segs), copy.deepcopy(segs)
+    core.estep(s64, copy.deepcopy(params), _cfg(Eniter=25))
+    core.estep(s32, copy.deepcopy(params), _cfg(Eniter=25, dtype="float32"))
+    core.estep(s64b, copy.deepcopy(params), _cfg(Eniter=25))
+    got32 = {k: np.stack([s[k] for s in s32]) for k in ("mu", "v", "w")}
+    got64 = {k: np.stack([s[k] for s in s64]) for k in ("mu", "v", "w")}
+    assert relerr(got64["mu"], ref["mu"]) < STEP_TOL
+    err = {k: relerr(got32[k], ref[k]) for k in ref}
+    assert err["mu"] < F32_TOL, err
+    assert err["v"] < 1e-4 and err["w"] < 1e-4, err
+    assert relerr(got32["mu"], got64["mu"]) > 1e-12                      # single precision really ran
+    for a, b in zip(s64, s64b):
+        assert np.array_equal(a["mu"], b["mu"])                          # and did not leak into the default path
 
 
 def test_overlapping_windows_and_unequal_lengths(vl):

@@ -90,6 +90,7 @@ EXPORTS = {
     "vlgp_peak_fp64": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "vlgp_peak_hbm": (C.c_int, [ctx_p, C.c_uint64, c_double_p]),
     "vlgp_flush_l2": (C.c_int, [ctx_p]),
+    "vlgp_set_precision": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_profile_enable": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_profile_get": (C.c_int, [ctx_p, C.c_int, c_double_p, c_i64_p]),
 }

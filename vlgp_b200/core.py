@@ -292,12 +292,18 @@ def _with_session(trials, params, session, **kw):
     return contextlib.nullcontext(session) if session is not None else Session(trials, params, **kw)
 
 
+def _precision_bits(config):
+    """32 when the configuration asks for single-precision rate passes (config["dtype"] = "float32"), else 64."""
+    return 32 if str(config.get("dtype", "float64")).lower() in ("float32", "f32", "fp32", "single") else 64
+
+
 def estep(trials, params, config, session=None):
     """Update the variational posterior q (E-step) of every trial."""
     if config["Eniter"] < 1:
         return
     with _with_session(trials, params, session) as s:
         s.require_factors()
+        s.eng.set_precision(_precision_bits(config))
         if s.alias is None:
             nfail = s.ts.estep(config["Eniter"], config["dmu_bound"], config["method"])
         else:
@@ -471,6 +477,7 @@ def _em_iteration(s: Session, trials, params, config):
     Returns (e_elapsed, m_elapsed, h_elapsed) wall-clock seconds; every stage ends with a device synchronisation."""
     ts = s.ts
     t0 = time.perf_counter()
+    s.eng.set_precision(_precision_bits(config))
     _constrain_loading_dev(s, params, config)
     if config["Eniter"] >= 1:
         if s.alias is None:

@@ -1376,6 +1376,13 @@ int vlgp_flush_l2(vlgp_ctx *ctx) {
     return VLGP_OK;
 }
 
+int vlgp_set_precision(vlgp_ctx *ctx, int bits) {
+    if (!ctx) return VLGP_ERR_ARG;
+    REQUIRE(bits == 32 || bits == 64, "set_precision: bits must be 32 or 64, not %d", bits);
+    ctx->estep_f32 = bits == 32 ? 1 : 0;
+    return VLGP_OK;
+}
+
 int vlgp_profile_enable(vlgp_ctx *ctx, int mask) {
     if (!ctx) return VLGP_ERR_ARG;
     ctx->profile = mask;

@@ -89,6 +89,7 @@ struct vlgp_ctx {
     // model
     int N = 0, L = 0, rank = 0;
     int xdim = 1;                                // regressors per neuron; b, db are xdim x N
+    int estep_f32 = 0;                           // vlgp_set_precision: single-precision rate passes in the segment E-step
     double *d_bpart = nullptr, *d_bstat = nullptr;   // regression statistics of the general-x M-step (regress.cu)
     size_t bpart_len = 0;
     int set_gen = 0;

@@ -4,10 +4,12 @@
 using namespace segk;
 
 namespace segk {
-template <> int launch_seg_variant<2, true>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
-template <> int launch_seg_variant<2, false>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
-template <> int launch_seg_variant<4, false>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
-template <> int launch_seg_variant<4, true>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<2, 1>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<2, 0>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<4, 0>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<4, 1>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<2, 2>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
+template <> int launch_seg_variant<4, 2>(vlgp_ctx *, TrialSet *, SegArgs &, size_t, bool *);
 }
 
 int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled,
@@ -61,8 +63,9 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     p.kp = 4 * ((2 * L + 1 + 3) / 4);
     const bool fast = !ctx->any_gauss && ts->ydtype == VLGP_Y_U8 && !getenv("VLGP_NO_FAST_ESTEP");
     p.fused = fast && p.use_dmma && !getenv("VLGP_ESTEP_NO_FUSED");
+    p.f32 = p.fused && ctx->estep_f32;                            // vlgp_set_precision(ctx, 32)
     const bool stage_y = ts->ydtype == VLGP_Y_U8 && !p.fused;     // the fused pipeline reads the counts once, in place
-    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total);
+    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total, p.f32);
     bool big = false;
     for (int l = 0; l < L; ++l)
         if (p.nc[l] > 16) big = true;
@@ -76,13 +79,14 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
             p.ldg[l] = ctx->rank;
         }
         big = true;                          // the NBMAX = 4 instantiations carry the in-place path
-        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total);
+        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total, p.f32);
     }
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
     int rc = VLGP_OK;
-    if (big && p.use_dmma && fast) rc = launch_seg_variant<4, true>(ctx, ts, p, smem, handled);
-    else if (big && p.use_dmma) rc = launch_seg_variant<4, false>(ctx, ts, p, smem, handled);
-    else if (fast) rc = launch_seg_variant<2, true>(ctx, ts, p, smem, handled);
-    else rc = launch_seg_variant<2, false>(ctx, ts, p, smem, handled);
+    if (p.f32) rc = big ? launch_seg_variant<4, 2>(ctx, ts, p, smem, handled) : launch_seg_variant<2, 2>(ctx, ts, p, smem, handled);
+    else if (big && p.use_dmma && fast) rc = launch_seg_variant<4, 1>(ctx, ts, p, smem, handled);
+    else if (big && p.use_dmma) rc = launch_seg_variant<4, 0>(ctx, ts, p, smem, handled);
+    else if (fast) rc = launch_seg_variant<2, 1>(ctx, ts, p, smem, handled);
+    else rc = launch_seg_variant<2, 0>(ctx, ts, p, smem, handled);
     return rc;
 }

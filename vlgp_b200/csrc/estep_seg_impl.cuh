@@ -39,6 +39,7 @@ struct SegArgs {
                                   //    HBM / L2 (NBMAX = 4 variants only; goff then indexes p.G, g_total = 0)
     int use_dmma;                 // every nc <= 32: Gram / inverse / variance on the FP64 tensor path
     int fused;                    // tensor-path rate passes and use_dmma: the fused pipeline (fused_a .. fused_c)
+    int f32;                      // fused pipeline with single-precision rate passes (FAST == 2 instantiations)
     const void *y;
     int ydtype;
     double *mu, *v, *w, *dmu;
@@ -71,7 +72,7 @@ struct Smem {
         a2 = a;                                  // (tensor-path rate passes: the kp x np operand Bx lives here instead)
         b = d + 2 * LT * N;                      // interleaved (bias, 1 / noise) pairs
         inv_noise = b;
-        d += max(2 * LT * N + 2 * N, p.kp * p.np);
+        d += p.f32 ? LT * N + (N + 2) / 2 : max(2 * LT * N + 2 * N, p.kp * p.np);
         Gs = d; d += p.g_total;                  // (g_total = 0 and Gs re-pointed by the kernel when g_global)
         Mi = d; d += p.m_total;
         mu = d; d += W * LT;
@@ -91,10 +92,11 @@ struct Smem {
 };
 
 __host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8,
-                                                 int kp, int np, int col_total) {
+                                                 int kp, int np, int col_total, bool f32 = false) {
     size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
     if ((size_t)(NWARP + 1) * col_total > un) un = (size_t)(NWARP + 1) * col_total;
-    const size_t par = (size_t)2 * LT * N + 2 * N > (size_t)kp * np ? (size_t)2 * LT * N + 2 * N : (size_t)kp * np;
+    size_t par = (size_t)2 * LT * N + 2 * N > (size_t)kp * np ? (size_t)2 * LT * N + 2 * N : (size_t)kp * np;
+    if (f32) par = (size_t)LT * N + (N + 2) / 2;
     size_t d = par + g_total + m_total + (size_t)6 * W * LT + 32 + un;
     size_t bytes = d * sizeof(double) + ((N + 15) / 16) * 16;
     if (y_u8) bytes += ((size_t)W * N + 15) / 16 * 16;
@@ -301,8 +303,80 @@ __device__ __forceinline__ void rate_tiles(const SegArgs &p, const Smem<LT> &s, 
     }
 }
 
+// Single-precision rate pass for the fused pipeline (FAST == 2, BASELINE.json configs[2] "fp32"): the linear predictor,
+// the exponential and the sums over neurons in FP32 on the FMA pipe (one issue slot per instruction instead of two, no
+// tensor-path padding); everything that is ill-conditioned -- the Gram matrices, their inverses, the variances, the mean
+// step -- stays FP64, and so do the state arrays and y a_l'.  Lane (r, q) of a row-tile warp takes bin 8 wid + r and the
+// neurons n = q (mod 4): the four lanes of a bin read consecutive (a, a^2 / 2) pairs, the eight bins of the warp the
+// same ones (shared-memory broadcast).  Returns the sums in the accumulator layout of rate_tiles.
+template <int LT, int STAGE>
+__device__ __forceinline__ void rate_tiles_f32(const SegArgs &p, const Smem<LT> &s, Tile (&acc)[(LT + 7) / 8]) {
+    constexpr int NOT = (LT + 7) / 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int N = p.N, t = 8 * wid + r;
+    const bool tin = t < p.W;
+    float mu[LT], hv[LT], sum[LT];
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+        mu[l] = tin ? (float)s.mu[t * LT + l] : 0.f;
+        hv[l] = tin ? (float)s.v[t * LT + l] : 0.f;
+        sum[l] = 0.f;
+    }
+    const float2 *af = (const float2 *)s.a;            // [l * N + n] : (a, a^2 / 2)
+    const float *bf = (const float *)(af + LT * N);    // [n] : bias
+    int n = q;
+    for (; n + 4 < N; n += 8) {                        // two neurons in flight
+        float x0 = bf[n], x1 = bf[n + 4];
+        float2 c0[LT], c1[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            c0[l] = af[l * N + n];
+            c1[l] = af[l * N + n + 4];
+            x0 = fmaf(mu[l], c0[l].x, x0);
+            x1 = fmaf(mu[l], c1[l].x, x1);
+            x0 = fmaf(hv[l], c0[l].y, x0);
+            x1 = fmaf(hv[l], c1[l].y, x1);
+        }
+        const float e0 = expf(fminf(x0, 10.f)), e1 = expf(fminf(x1, 10.f));
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            sum[l] = fmaf(e0, STAGE == 1 ? c0[l].x : c0[l].y, sum[l]);
+            sum[l] = fmaf(e1, STAGE == 1 ? c1[l].x : c1[l].y, sum[l]);
+        }
+    }
+    if (n < N) {
+        float x0 = bf[n];
+        float2 c0[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            c0[l] = af[l * N + n];
+            x0 = fmaf(mu[l], c0[l].x, x0);
+            x0 = fmaf(hv[l], c0[l].y, x0);
+        }
+        const float e0 = expf(fminf(x0, 10.f));
+#pragma unroll
+        for (int l = 0; l < LT; ++l) sum[l] = fmaf(e0, STAGE == 1 ? c0[l].x : c0[l].y, sum[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+        sum[l] += __shfl_xor_sync(FULL, sum[l], 1);
+        sum[l] += __shfl_xor_sync(FULL, sum[l], 2);
+    }
+#pragma unroll
+    for (int o = 0; o < NOT; ++o) {
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            if (l == 8 * o + 2 * q) ax = sum[l];
+            if (l == 8 * o + 2 * q + 1) ay = sum[l];
+        }
+        acc[o].x = (double)ax;
+        acc[o].y = (double)ay;
+    }
+}
+
 // s.ya[t][l] = sum_n y[t][n] a[l][n] for this warp's row tile (fused path, once per segment; counts read in place)
-template <int LT>
+template <int LT, bool F32>
 __device__ __forceinline__ void ya_tiles(const SegArgs &p, const Smem<LT> &s, const uint8_t *yseg) {
     constexpr int NOT = (LT + 7) / 8;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
@@ -320,7 +394,14 @@ __device__ __forceinline__ void ya_tiles(const SegArgs &p, const Smem<LT> &s, co
 #pragma unroll
         for (int o = 0; o < NOT; ++o) {
             double2 b2 = make_double2(0.0, 0.0);
-            if (8 * o + r < LT) b2 = *reinterpret_cast<const double2 *>(s.a + (r + 8 * o) * NP + n0);
+            if (8 * o + r < LT) {
+                if (F32) {                             // FP32 mode keeps no FP64 loading in SMEM: read it in place
+                    if (n0 < N) b2.x = p.pa[(r + 8 * o) * N + n0].x;
+                    if (n0 + 1 < N) b2.y = p.pa[(r + 8 * o) * N + n0 + 1].x;
+                } else {
+                    b2 = *reinterpret_cast<const double2 *>(s.a + (r + 8 * o) * NP + n0);
+                }
+            }
             dmma(acc[o], y0, b2.x);
             dmma(acc[o], y1, b2.y);
         }
@@ -359,7 +440,7 @@ __device__ __forceinline__ void rate_pass_dmma(const SegArgs &p, const Smem<LT> 
     __syncthreads();
 }
 
-template <int LT, int STAGE, bool FAST>
+template <int LT, int STAGE, int FAST>
 __device__ __forceinline__ void rate_pass(const SegArgs &p, const Smem<LT> &s, int64_t bin0) {
 #ifndef VLGP_ESTEP_SCALAR_RATE_PASS
     if (FAST) {
@@ -752,7 +833,7 @@ __device__ __forceinline__ int col_latent(const SegArgs &p, int LT, int idx) {
 
 // Phase A: [variance of the own bins from the previous factorisation] -> rate pass 1 -> z = ra + w o mu -> this row
 // tile's part of s_l = G_l' z_l for every latent.  Ends with a block barrier.
-template <int LT, int NBMAX>
+template <int LT, int NBMAX, bool F32>
 __device__ __forceinline__ void fused_a(const SegArgs &p, const Smem<LT> &s, const int *bad, bool do_var) {
     constexpr int NOT = (LT + 7) / 8;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
@@ -764,7 +845,8 @@ __device__ __forceinline__ void fused_a(const SegArgs &p, const Smem<LT> &s, con
             __syncwarp();
         }
         Tile acc[NOT];
-        if (!(p.skip & 1)) rate_tiles<LT, 1, true>(p, s, acc);
+        if (F32) rate_tiles_f32<LT, 1>(p, s, acc);
+        else if (!(p.skip & 1)) rate_tiles<LT, 1, true>(p, s, acc);
         else
             for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.0;
         const int t = 8 * wid + r;
@@ -820,7 +902,7 @@ __device__ __forceinline__ void fused_b(const SegArgs &p, const Smem<LT> &s) {
 
 // Phase C: delta = clip(G m - mu) on the own bins (a failed factorisation zeroes the step, vlgp/core.py:92-94), then
 // rate pass 2 -> w.  Ends with a block barrier.
-template <int LT>
+template <int LT, bool F32>
 __device__ __forceinline__ void fused_c(const SegArgs &p, const Smem<LT> &s, const int *bad) {
     constexpr int NOT = (LT + 7) / 8;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
@@ -845,7 +927,8 @@ __device__ __forceinline__ void fused_c(const SegArgs &p, const Smem<LT> &s, con
         }
         __syncwarp();
         Tile acc[NOT];
-        if (!(p.skip & 1)) rate_tiles<LT, 2, true>(p, s, acc);
+        if (F32) rate_tiles_f32<LT, 2>(p, s, acc);
+        else if (!(p.skip & 1)) rate_tiles<LT, 2, true>(p, s, acc);
         else
             for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.5;
         const int t = 8 * wid + r;
@@ -1046,7 +1129,7 @@ __device__ __forceinline__ void mean_step_warp(const SegArgs &p, const Smem<LT> 
     }
 }
 
-template <int LT, int NBMAX, bool FAST>
+template <int LT, int NBMAX, int FAST>
 #ifdef VLGP_ESTEP_TWO_BINS
 __global__ void __launch_bounds__(NT, 2) estep_seg_kernel(SegArgs p) {
 #else
@@ -1075,7 +1158,12 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
 
     // ---- once per CTA: parameters and the compact prior factors ------------------------------------------------------
 #ifndef VLGP_ESTEP_SCALAR_RATE_PASS
-    if (FAST) {          // operand of the tensor-path rate passes: rows a_l | a_l^2 / 2 | b | 0, columns padded with 0
+    if (FAST == 2) {     // single-precision rate passes: (a, a^2 / 2) pairs and the bias as floats
+        float2 *af = (float2 *)s.a;
+        float *bf = (float *)(af + LT * N);
+        for (int i = tid; i < LT * N; i += NT) af[i] = make_float2((float)p.pa[i].x, 0.5f * (float)p.pa[i].y);
+        for (int n = tid; n < N; n += NT) bf[n] = (float)p.pb[n].x;
+    } else if (FAST) {   // operand of the tensor-path rate passes: rows a_l | a_l^2 / 2 | b | 0, columns padded with 0
         for (int i = tid; i < p.kp * p.np; i += NT) {
             const int k = i / p.np, n = i - k * p.np;
             double val = 0.0;
@@ -1119,7 +1207,7 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
             s.dmu[i] = 0.0;
         }
         if (FAST && p.fused) {
-            if (8 * (tid >> 5) < W) ya_tiles<LT>(p, s, (const uint8_t *)p.y + bin0 * N);
+            if (8 * (tid >> 5) < W) ya_tiles<LT, FAST == 2>(p, s, (const uint8_t *)p.y + bin0 * N);
         } else if (p.ydtype == VLGP_Y_U8) {
             const uint8_t *ysrc = (const uint8_t *)p.y + bin0 * N;
             for (int i = tid; i < W * N; i += NT) s.ys[i] = ysrc[i];
@@ -1130,9 +1218,9 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
         if (FAST && p.fused && p.n_iter > 0) {
             factor_all<LT, NBMAX>(p, s, bad, false);                  // the first mean step uses the incoming w
             for (int it = 0; it < p.n_iter; ++it) {
-                fused_a<LT, NBMAX>(p, s, bad, it > 0 && p.method_vb && !(p.skip & 8));
+                fused_a<LT, NBMAX, FAST == 2>(p, s, bad, it > 0 && p.method_vb && !(p.skip & 8));
                 if (!(p.skip & 2)) fused_b<LT>(p, s);
-                fused_c<LT>(p, s, bad);
+                fused_c<LT, FAST == 2>(p, s, bad);
                 if ((p.method_vb || it + 1 < p.n_iter) && !(p.skip & 4)) factor_all<LT, NBMAX>(p, s, bad, false);
             }
             if (p.method_vb && p.n_iter > 0) {                         // variances of the last factorisation
@@ -1176,7 +1264,7 @@ static __global__ void pack_params_kernel(int LN, int N, const double *__restric
     if (i < N) pb[i] = make_double2(b[i], 1.0 / noise[i]);
 }
 
-template <int LT, int NBMAX, bool FAST>
+template <int LT, int NBMAX, int FAST>
 int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *handled) {
     const int LN = LT * p.N;
     if (!ctx->d_ppack) CK(cudaMalloc(&ctx->d_ppack, (size_t)(VLGP_MAX_L + 1) * p.N * sizeof(double2)));
@@ -1205,7 +1293,7 @@ int launch_seg_t(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *han
 }
 
 
-template <int NBMAX, bool FAST>
+template <int NBMAX, int FAST>
 int launch_seg_variant(vlgp_ctx *ctx, TrialSet *ts, SegArgs &p, size_t smem, bool *handled);
 
 }   // namespace segk

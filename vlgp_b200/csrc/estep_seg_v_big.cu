@@ -1,3 +1,3 @@
 // Instantiation of the segment E-step kernel: NBMAX = 4, FAST = false (see estep_seg_impl.cuh).
 #include "estep_seg_impl.cuh"
-VLGP_DEFINE_SEG_VARIANT(4, false)
+VLGP_DEFINE_SEG_VARIANT(4, 0)

@@ -1,3 +1,3 @@
 // Instantiation of the segment E-step kernel: NBMAX = 2, FAST = false (see estep_seg_impl.cuh).
 #include "estep_seg_impl.cuh"
-VLGP_DEFINE_SEG_VARIANT(2, false)
+VLGP_DEFINE_SEG_VARIANT(2, 0)

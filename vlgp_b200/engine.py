@@ -257,6 +257,11 @@ class Engine:
     def flush_l2(self):
         self._ck(self.lib.vlgp_flush_l2(self.ctx), "flush_l2")
 
+    def set_precision(self, bits=64):
+        """Arithmetic of the segment E-step's rate passes: 64 (default, reference-exact) or 32 (include/vlgp_b200.h)."""
+        self._ck(self.lib.vlgp_set_precision(self.ctx, int(bits)), "set_precision")
+        self.precision = int(bits)
+
     def profile_enable(self, mask=0xF):
         """Time kernel classes with CUDA events: bit 0 E-step, 1 M-step statistics, 2 H-step segments, 3 ichol."""
         self._ck(self.lib.vlgp_profile_enable(self.ctx, int(mask)), "profile_enable")

@@ -32,6 +32,7 @@ _CONFIG_DEFAULTS = (
     ("saving_interval", 60 * 30),
     ("callbacks", None),
     ("parallel", False),
+    ("dtype", "float64"),          # not in the reference: "float32" = single-precision E-step rate passes (engine.set_precision)
 )
 
 
