@@ -307,7 +307,7 @@ def solo_parity(args, traj, n_iter):
     quiet, stdout = open(os.devnull, "w"), sys.stdout
     sys.stdout = quiet
     try:
-        trials, params, config, c = build_problem(args.config, n_trials=args.n_trials)
+        trials, params, config, c = build_problem(args.config, n_trials=getattr(args, "n_trials", None))
         make_cholesky(trials, params, config)
         core.update_w(trials, params, config)
         core.update_v(trials, params, config)
@@ -346,8 +346,8 @@ def run_ours(args):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
 
     # ---- problem: every rank builds the same global initial state, then keeps its shard of trials -------------------
-    trials, params, config, c = build_problem(args.config, n_trials=args.n_trials)
-    if args.dtype == "f32":
+    trials, params, config, c = build_problem(args.config, n_trials=getattr(args, "n_trials", None))
+    if getattr(args, "dtype", "f64") == "f32":
         config["dtype"] = "float32"
     lo, hi = dist.shard_bounds(len(trials), world, rank)
     my_trials = trials[lo:hi]
@@ -515,7 +515,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64" if args.dtype == "f64" else "f32 (E-step rate passes; Gram / inverse / mean step, M- and H-step f64)",
+        "dtype": "f64" if getattr(args, "dtype", "f64") == "f64" else "f32 (E-step rate passes; Gram / inverse / mean step, M- and H-step f64)",
         "data": "synthetic", "config": workload_config(args.config, c, args.gpus),
         "split_ms": {"estep": split[0] / args.steps * 1e3, "mstep": split[1] / args.steps * 1e3,
                      "hstep": split[2] / args.steps * 1e3, "wall_per_step": wall / args.steps * 1e3,

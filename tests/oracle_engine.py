@@ -69,6 +69,9 @@ class OracleEngine:
     def flush_l2(self):
         pass
 
+    def set_precision(self, bits=64):
+        self.precision = int(bits)        # the stand-in always computes in double precision
+
     def timer_start(self):
         import time
 

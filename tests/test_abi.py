@@ -82,6 +82,8 @@ def test_host_surface_matches_reference_defaults():
 
     cfg = get_config(max_iter=7, bogus=1)
     ref = orc.default_config(max_iter=7)
+    extra = {k: cfg.pop(k) for k in list(cfg) if k not in ref}
+    assert extra == {"dtype": "float64"}          # the one key the reference does not have (single-precision switch)
     assert cfg == ref and "bogus" not in cfg
     p = get_params([dict(y=np.zeros((10, 4)))], 2, omega_bound=cfg["omega_bound"], lik="gaussian", history=0)
     assert p["xdim"] == 1 and p["rank"] == 50 and list(p["likelihood"]) == ["gaussian"] * 4
