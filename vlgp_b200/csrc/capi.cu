@@ -33,6 +33,7 @@ int vlgp_launch_estep_generic(vlgp_ctx *ctx, TrialSet *ts, int mode, int n_iter,
                               const int32_t *d_subset = nullptr, int n_subset = 0);
 int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled,
                                const int32_t *d_subset = nullptr, int n_subset = 0);
+int vlgp_launch_estep_long(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_bound, int method_vb, bool *handled);
 int vlgp_launch_mstep(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
                       double da_bound, double db_bound);
 int vlgp_mstep_job_setup(vlgp_ctx *ctx, TrialSet *ts, int n_iter, int use_hessian, double eps, double lr,
@@ -186,6 +187,7 @@ void free_set(TrialSet &ts, cudaStream_t stream = nullptr) {
     };
     F(ts.d_len); F(ts.d_start); F(ts.d_fidx); F(ts.d_Gptr); F(ts.d_ncolptr); F(ts.d_y);
     F(ts.d_mu); F(ts.d_v); F(ts.d_w); F(ts.d_dmu); F(ts.d_ra); F(ts.d_u); F(ts.d_minv);
+    F(ts.d_k3_tab); F(ts.d_k3_buf); F(ts.d_k3_bad);
     F(ts.d_M); F(ts.d_K); F(ts.d_hpart); F(ts.d_hout); F(ts.d_mompart); F(ts.d_x); F(ts.d_xb);
     for (auto &pf : ts.factors) {
         F(pf.d_G); F(pf.d_ncol); F(pf.d_piv);
@@ -941,6 +943,7 @@ static int estep_impl(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, i
         ProfScope ps(ctx, 0);
         bool handled = false;
         rc = vlgp_launch_estep_segments(ctx, ts, n_iter, dmu_bound, method_vb, &handled, d_sub, n_segs);
+        if (!rc && !handled && !d_sub) rc = vlgp_launch_estep_long(ctx, ts, n_iter, dmu_bound, method_vb, &handled);
         if (!rc && !handled) rc = vlgp_launch_estep_generic(ctx, ts, 0, n_iter, dmu_bound, method_vb, d_sub, n_segs);
     }
     if (d_sub) vlgp_dfree(ctx, d_sub);

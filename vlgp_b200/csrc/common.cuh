@@ -61,6 +61,11 @@ struct TrialSet {
     // general regressors (regress.cu): null for the all-ones bias column
     double *d_x = nullptr;             // nbin x xdim x N
     double *d_xb = nullptr;            // nbin x N : einsum(x, b), the offset of the linear predictor
+    // long-trial E-step (estep_long.cu): item tables, partial sums and inverses, allocated at the first call
+    bool k3_ready = false;
+    int k3_items = 0;
+    int *d_k3_tab = nullptr, *d_k3_bad = nullptr;
+    double *d_k3_buf = nullptr;
     int gen = 0;                       // generation of the slot: stale handles of freed sets are refused
 };
 

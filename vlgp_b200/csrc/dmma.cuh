@@ -62,3 +62,67 @@ __device__ __forceinline__ bool tile_spd_inverse(Tile &t, int lane) {
 }
 
 __host__ __device__ constexpr int tix(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// Blocked symmetric sweep of an SPD matrix of order 8 NB held by ONE warp as the lower block triangle of 8 x 8 tiles in
+// the accumulator layout (A[tix(i, j)], j <= i): on return the tiles hold -A^-1.  Block step kb: P = A_kk^-1 (scalar
+// sweep by shuffles), A_ik <- A_ik P, A_ij <- A_ij - A_ik P A_kj (i, j != kb) by DMMA, A_kk <- -P.  Returns false
+// (warp-uniform) if some pivot was not positive.  (Same algorithm as the H-step's per-segment kernel and the segment
+// E-step's factorisation; used by the long-trial E-step, csrc/estep_long.cu.)
+template <int NB>
+__device__ __forceinline__ bool tile_sweep(Tile (&A)[NB * (NB + 1) / 2], int lane) {
+    bool ok = true;
+#pragma unroll
+    for (int kb = 0; kb < NB; ++kb) {
+        Tile P = A[tix(kb, kb)];
+        ok = tile_spd_inverse(P, lane) && ok;
+        const double Pt0 = tform(P, 0, lane), Pt1 = tform(P, 1, lane);
+        const double Pn0 = nform(P, 0, lane), Pn1 = nform(P, 1, lane);
+        double V0[NB], V1[NB];
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (m == kb) continue;
+            if (m > kb) {
+                V0[m] = nform(A[tix(m, kb)], 0, lane);
+                V1[m] = nform(A[tix(m, kb)], 1, lane);
+            } else {
+                V0[m] = tform(A[tix(kb, m)], 0, lane);
+                V1[m] = tform(A[tix(kb, m)], 1, lane);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+            if (m == kb) continue;
+            Tile T{0.0, 0.0};
+            if (m > kb) {
+                dmma(T, V0[m], Pt0);
+                dmma(T, V1[m], Pt1);
+                A[tix(m, kb)] = T;
+            } else {
+                dmma(T, Pn0, V0[m]);
+                dmma(T, Pn1, V1[m]);
+                A[tix(kb, m)] = T;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (i == kb) continue;
+            double T0, T1;
+            if (i > kb) {
+                T0 = -nform(A[tix(i, kb)], 0, lane);
+                T1 = -nform(A[tix(i, kb)], 1, lane);
+            } else {
+                T0 = -tform(A[tix(kb, i)], 0, lane);
+                T1 = -tform(A[tix(kb, i)], 1, lane);
+            }
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                if (j == kb) continue;
+                dmma(A[tix(i, j)], T0, V0[j]);
+                dmma(A[tix(i, j)], T1, V1[j]);
+            }
+        }
+        A[tix(kb, kb)].x = -P.x;
+        A[tix(kb, kb)].y = -P.y;
+    }
+    return ok;
+}

@@ -232,11 +232,11 @@ __device__ __forceinline__ void trunc_exp2_tile(double x0, double x1, const doub
 // FUSED: the y term of stage 1 is left out (the fused pipeline keeps y a_l' in s.ya and subtracts the sum of rate x a_l),
 // the exponential reads its table from shared memory.
 template <int LT, int STAGE, bool FUSED = false>
-__device__ __forceinline__ void rate_tiles(const SegArgs &p, const Smem<LT> &s, Tile (&acc)[(LT + 7) / 8]) {
+__device__ __forceinline__ void rate_tiles_core(int W, int N, int NP, const double *Bx, const double *smu, const double *sv,
+                                                const double *etab, const uint8_t *ys, Tile (&acc)[(LT + 7) / 8]) {
     constexpr int KS = (2 * LT + 1 + 3) / 4;        // k4 steps of the x contraction
     constexpr int NOT = (LT + 7) / 8;               // output tiles of 8 latents
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
-    const int W = p.W, N = p.N, NP = p.np;
     {
         const int t = 8 * wid + r;
         const bool tin = t < W;
@@ -246,16 +246,15 @@ __device__ __forceinline__ void rate_tiles(const SegArgs &p, const Smem<LT> &s, 
             const int k = 4 * kk + q;
             double val = 0.0;
             if (tin) {
-                if (k < LT) val = s.mu[t * LT + k];
-                else if (k < 2 * LT) val = s.v[t * LT + k - LT];
+                if (k < LT) val = smu[t * LT + k];
+                else if (k < 2 * LT) val = sv[t * LT + k - LT];
                 else if (k == 2 * LT) val = 1.0;
             }
             afr[kk] = val;
         }
 #pragma unroll
         for (int o = 0; o < NOT; ++o) acc[o].x = acc[o].y = 0.0;
-        const double *Bx = s.a;
-        const uint8_t *yrow = s.ys + (tin ? t : 0) * N;
+        const uint8_t *yrow = ys + (tin ? t : 0) * N;
         const int brow = (STAGE == 1 ? 0 : LT) + r;
         // (build option VLGP_ESTEP_RATE_ILP2: two column tiles per step, four exponentials in flight per lane)
         const int nct = NP >> 3;
@@ -296,11 +295,16 @@ __device__ __forceinline__ void rate_tiles(const SegArgs &p, const Smem<LT> &s, 
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) dmma(x, afr[kk], Bx[(4 * kk + q) * NP + 8 * j + r]);
             double e0, e1;
-            if (FUSED) trunc_exp2_tile(x.x, x.y, s.etab, e0, e1);
+            if (FUSED) trunc_exp2_tile(x.x, x.y, etab, e0, e1);
             else trunc_exp2(x.x, x.y, e0, e1);
             tile_pair(j, e0, e1);
         }
     }
+}
+
+template <int LT, int STAGE, bool FUSED = false>
+__device__ __forceinline__ void rate_tiles(const SegArgs &p, const Smem<LT> &s, Tile (&acc)[(LT + 7) / 8]) {
+    rate_tiles_core<LT, STAGE, FUSED>(p.W, p.N, p.np, s.a, s.mu, s.v, s.etab, s.ys, acc);
 }
 
 // Single-precision rate pass for the fused pipeline (FAST == 2, BASELINE.json configs[2] "fp32"): the linear predictor,
