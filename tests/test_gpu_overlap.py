@@ -44,9 +44,11 @@ def _filled_set(eng, rng, lengths, N, L):
 
 @pytest.mark.parametrize("lengths", [[50] * 23, [50, 120, 64, 200, 50, 77]], ids=["segments", "ragged"])
 def test_estep_subset_touches_only_the_listed_members(eng, lengths):
-    """estep(subset=s) gives, on the listed members, bit for bit what the E-step over the whole set gives (members are
-    independent), and leaves every other member untouched -- both through the SMEM-resident segment kernel (equal
-    lengths <= 64) and through the any-length kernel."""
+    """estep(subset=s) gives, on the listed members, what the E-step over the whole set gives (members are independent),
+    and leaves every other member untouched -- both through the SMEM-resident segment kernel (equal lengths <= 64: bit
+    for bit) and through the any-length kernel.  (A whole set of unequal lengths now takes the long-trial kernel,
+    csrc/estep_long.cu, a subset the one-CTA-per-trial kernel: same algebra, different summation order, so the ragged
+    case compares to 1e-10 instead of bit for bit.)"""
     rng = np.random.default_rng(5)
     N, L = 17, 3
     _model(eng, N, L, rng, omega=[5e-3, 1e-2, 2e-3])
@@ -61,8 +63,13 @@ def test_estep_subset_touches_only_the_listed_members(eng, lengths):
         listed = np.zeros(part.nbin, dtype=bool)
         for i in subset:
             listed[part.starts[i]:part.starts[i] + part.lengths[i]] = True
+        exact = len(set(lengths)) == 1
+
+        def same(a, b):
+            return np.array_equal(a, b) if exact else np.max(np.abs(a - b)) <= 1e-10 * max(np.max(np.abs(b)), 1e-300)
+
         for k in ("mu", "v", "w", "dmu"):
-            assert np.array_equal(got[k][listed], ref[k][listed]), k
+            assert same(got[k][listed], ref[k][listed]), k
             assert np.array_equal(got[k][~listed], before[k][~listed]), k
         assert not np.array_equal(got["mu"][listed], before["mu"][listed])
         # the rest in a second call: together the two calls equal the full E-step
@@ -70,7 +77,7 @@ def test_estep_subset_touches_only_the_listed_members(eng, lengths):
         part.estep(4, 5.0, "VB", subset=rest)
         got = part.get_state()
         for k in ("mu", "v", "w", "dmu"):
-            assert np.array_equal(got[k], ref[k]), k
+            assert same(got[k], ref[k]), k
 
 
 def test_row_operations_argument_errors(eng):

@@ -41,6 +41,7 @@ struct Args {
     double dmu_bound;
     int *flags;
     int first, gram_only;
+    int dbg;                     // timing experiments only (VLGP_K3_DEBUG): 1 = Gram without its bulk copies
 };
 
 // operand of the tensor-path rate passes (as in estep_seg_kernel): rows a_l | a_l^2 / 2 | b | 0, columns padded with 0
@@ -60,9 +61,39 @@ __device__ __forceinline__ void stage_bx(const Args &p, double *Bx, double *etab
     if (tid < 32) etab[tid] = VLGP_EXP_T[tid];
 }
 
+// ---- TMA bulk copy (global -> shared) completed on an mbarrier --------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
 // ---- rate pass 1 + partial projections ------------------------------------------------------------------------------
 template <int LT>
-__global__ void __launch_bounds__(NT, 2) k3_a_kernel(Args p) {
+__global__ void __launch_bounds__(NT, 3) k3_a_kernel(Args p) {
     constexpr int NOT = (LT + 7) / 8;
     extern __shared__ __align__(16) unsigned char raw[];
     double *Bx = (double *)raw;
@@ -186,13 +217,20 @@ __global__ void __launch_bounds__(NT, 2) k3_c_kernel(Args p) {
     double *smu = etab + 32, *sv = smu + CH * LT;
     double *wsc = sv + CH * LT;                        // IB x LT : the item's weights
     double *mv = wsc + IB * LT;                        // LT x 64
+    double *Gs = mv + LT * 64;                         // 2 x CH x rank : staged rows of G_l (TMA destination)
     __shared__ int sbad[VLGP_MAX_L];
+    __shared__ __align__(8) uint64_t gbar[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, r = lane >> 2, q = lane & 3;
     const int item = blockIdx.x, trial = p.item_trial[item], t0 = p.item_t0[item];
     const int T = p.len[trial], rank = p.rank, N = p.N;
     const int64_t s0 = p.start[trial];
     const double *G = p.Gptr[p.fidx[trial]];
     const int nb_item = min(IB, T - t0);
+    if (tid == 0) {
+        mbar_init(&gbar[0], 1);
+        mbar_init(&gbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (!p.gram_only) {
         stage_bx<LT>(p, Bx, etab);
         for (int i = tid; i < LT * 64; i += NT) mv[i] = p.mvec[(size_t)trial * LT * 64 + i];
@@ -256,38 +294,60 @@ __global__ void __launch_bounds__(NT, 2) k3_c_kernel(Args p) {
         }
     }
     __syncthreads();
-    // Gram partials: the (latent, tile row i) strips -- i + 1 tiles each -- are dealt to the warps in snake order of
-    // decreasing cost; a strip's accumulators stay in registers over all k4 steps of the item.
-    const int n_strip = LT * NB;
-    for (int e = 0; e < n_strip; ++e) {
-        const int ph = e % (2 * NWARP);
-        const int owner = ph < NWARP ? ph : 2 * NWARP - 1 - ph;
-        if (owner != wid) continue;
-        const int l = e / NB, i = NB - 1 - (e - l * NB);
-        Tile A[NB];
+    // Gram partials.  The item's rows of G_l arrive in shared memory chunk by chunk (64 rows x rank doubles, contiguous in
+    // HBM / L2: one TMA bulk copy each, double-buffered over the (latent, chunk) steps); the NTL tiles of a latent are
+    // dealt round-robin to the 8 warps and stay in registers over the item's k4 steps.
+    constexpr int TPW = (NTL + NWARP - 1) / NWARP;
+    int ti[TPW], tj[TPW];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) A[j].x = A[j].y = 0.0;
-        const double *Gl = G + ((size_t)l * T + t0) * rank;
-        for (int k = 0; 4 * k < nb_item; ++k) {
-            const int t = 4 * k + q;
-            const bool tin = t < nb_item;
-            const double wt = tin ? wsc[t * LT + l] : 0.0;
-            const double *grow = Gl + (size_t)(tin ? t : 0) * rank;
-            const int ci = 8 * i + r;
-            const double gw = (tin && ci < rank) ? grow[ci] * wt : 0.0;
+    for (int m = 0; m < TPW; ++m) {
+        ti[m] = tj[m] = -1;
+        if (wid + NWARP * m < NTL) tri_decode(wid + NWARP * m, ti[m], tj[m]);
+    }
+    const int nch = (nb_item + CH - 1) / CH, nsteps = LT * nch;
+    auto issue = [&](int st) {
+        const int l = st / nch, c = st - l * nch;
+        const unsigned bytes = (unsigned)(min(CH, nb_item - CH * c) * rank * sizeof(double));
+        mbar_expect_tx(&gbar[st & 1], bytes);
+        tma_load_1d(Gs + (st & 1) * CH * rank, G + ((size_t)l * T + t0 + CH * c) * rank, bytes, &gbar[st & 1]);
+    };
+    if (tid == 0 && !(p.dbg & 1)) issue(0);
+    Tile A[TPW];
+    for (int st = 0; st < nsteps; ++st) {
+        const int l = st / nch, c = st - l * nch;
+        if (tid == 0 && st + 1 < nsteps && !(p.dbg & 1)) issue(st + 1);   // the other buffer was released by the barrier below
+        if (!(p.dbg & 1)) mbar_wait(&gbar[st & 1], (st >> 1) & 1);
+        const double *Gb = Gs + (st & 1) * CH * rank;
+        if (c == 0) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                if (j <= i) {
-                    const int cj = 8 * j + r;
-                    const double gj = (tin && cj < rank) ? grow[cj] : 0.0;
-                    dmma(A[j], gw, gj);
-                }
+            for (int m = 0; m < TPW; ++m) A[m].x = A[m].y = 0.0;
+        }
+        const int nbc = min(CH, nb_item - CH * c);
+        // k4 step k takes the bins 16 (k / 4) + k % 4 + {0, 4, 8, 12}: rows 4 apart are 200 doubles apart (rank = 50), so
+        // the four rows a warp reads fall on disjoint halves of the banks -- the natural choice t = 4 k + q is a 4-way
+        // conflict.  (A contraction does not care in which order its bins are taken.)
+#pragma unroll 4
+        for (int k = 0; 16 * (k >> 2) < nbc; ++k) {
+            const int t = 16 * (k >> 2) + (k & 3) + 4 * q;
+            const bool tin = t < nbc;
+            const double wt = tin ? wsc[(CH * c + t) * LT + l] : 0.0;
+            const double *grow = Gb + (tin ? t : 0) * rank;
+#pragma unroll
+            for (int m = 0; m < TPW; ++m) {
+                if (ti[m] < 0) continue;
+                const int ci = 8 * ti[m] + r, cj = 8 * tj[m] + r;
+                const double gi = (tin && ci < rank) ? grow[ci] * wt : 0.0;
+                const double gj = (tin && cj < rank) ? grow[cj] : 0.0;
+                dmma(A[m], gi, gj);
             }
         }
-        double2 *out = (double2 *)p.apart + (((size_t)item * LT + l) * NTL + tix(i, 0)) * 32 + lane;
+        if (c == nch - 1) {
+            double2 *out = (double2 *)p.apart + ((size_t)item * LT + l) * NTL * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < NB; ++j)
-            if (j <= i) out[j * 32] = make_double2(A[j].x, A[j].y);
+            for (int m = 0; m < TPW; ++m)
+                if (ti[m] >= 0) out[(wid + NWARP * m) * 32] = make_double2(A[m].x, A[m].y);
+        }
+        __syncthreads();
     }
 }
 
@@ -339,35 +399,6 @@ __global__ void __launch_bounds__(128) k3_factor_kernel(Args p, int LT) {
 }
 
 // ---- variances: Minv_l staged in shared memory by TMA bulk copies, double-buffered over the latents -------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
-            : "memory");
-    }
-}
-
 template <int NB>
 __global__ void __launch_bounds__(NT, 2) k3_var_kernel(Args p, int LT) {
     constexpr int LDM = 8 * NB + 4;
@@ -412,18 +443,23 @@ __global__ void __launch_bounds__(NT, 2) k3_var_kernel(Args p, int LT) {
                     const int c = 4 * k + q;
                     aop[k] = (tin && c < rank) ? grow[c] : 0.0;
                 }
+                // g' M g over the lower block triangle only (M is symmetric): per column block jt the diagonal block
+                // once and the blocks below it twice -- NB (NB + 1) DMMA per row tile instead of 2 NB^2
                 double acc = 0.0;
 #pragma unroll
                 for (int jt = 0; jt < NB; ++jt) {
-                    Tile Tt{0.0, 0.0};
+                    Tile Td{0.0, 0.0}, To{0.0, 0.0};
 #pragma unroll
-                    for (int k = 0; k < 2 * NB; ++k)
-                        if (4 * k < rank) dmma(Tt, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
+                    for (int k = 2 * jt; k < 2 * jt + 2; ++k)
+                        if (4 * k < rank) dmma(Td, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
+#pragma unroll
+                    for (int k = 2 * jt + 2; k < 2 * NB; ++k)
+                        if (4 * k < rank) dmma(To, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
                     const int c = 8 * jt + c0;
                     const double g0 = (tin && c < rank) ? grow[c] : 0.0;
                     const double g1 = (tin && c + 1 < rank) ? grow[c + 1] : 0.0;
-                    acc = fma(Tt.x, g0, acc);
-                    acc = fma(Tt.y, g1, acc);
+                    acc = fma(fma(2.0, To.x, Td.x), g0, acc);
+                    acc = fma(fma(2.0, To.y, Td.y), g1, acc);
                 }
                 acc += __shfl_xor_sync(FULL, acc, 1);
                 acc += __shfl_xor_sync(FULL, acc, 2);
@@ -440,7 +476,7 @@ int launch(vlgp_ctx *ctx, TrialSet *ts, Args &p, int n_iter, int method_vb) {
     constexpr int LDM = 8 * NB + 4;
     const int tasks = p.n_trials * LT;
     const size_t smem_a = ((size_t)p.kp * p.np + 32 + 3 * CH * LT + NWARP * LT * 64) * sizeof(double);
-    const size_t smem_c = ((size_t)p.kp * p.np + 32 + 2 * CH * LT + IB * LT + LT * 64) * sizeof(double);
+    const size_t smem_c = ((size_t)p.kp * p.np + 32 + 2 * CH * LT + IB * LT + LT * 64 + 2 * CH * p.rank) * sizeof(double);
     const size_t smem_v = (size_t)2 * 8 * NB * LDM * sizeof(double);
     CK(cudaFuncSetAttribute(k3_a_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     CK(cudaFuncSetAttribute(k3_c_kernel<LT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
@@ -537,6 +573,7 @@ int vlgp_launch_estep_long(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_b
     p.ya = p.mvec + tasks * 64;
     p.bad = ts->d_k3_bad;
     p.dmu_bound = dmu_bound; p.flags = ctx->d_flags;
+    p.dbg = getenv("VLGP_K3_DEBUG") ? atoi(getenv("VLGP_K3_DEBUG")) : 0;
     // (a, a^2) and (b, 1 / noise) pairs, as for the segment kernel
     if (!ctx->d_ppack) CK(cudaMalloc(&ctx->d_ppack, (size_t)(VLGP_MAX_L + 1) * N * sizeof(double2)));
     p.pa = (const double2 *)ctx->d_ppack;
@@ -544,7 +581,7 @@ int vlgp_launch_estep_long(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double dmu_b
     segk::pack_params_kernel<<<(L * N + 255) / 256, 256, 0, ctx->stream>>>(L * N, N, ctx->d_a, ctx->d_b, ctx->d_noise,
                                                                            (double2 *)p.pa, (double2 *)p.pb);
     CKL();
-    const size_t smem_c = ((size_t)p.kp * p.np + 32 + 2 * CH * L + IB * L + L * 64) * sizeof(double);
+    const size_t smem_c = ((size_t)p.kp * p.np + 32 + 2 * CH * L + IB * L + L * 64 + 2 * CH * p.rank) * sizeof(double);
     if (smem_c > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
     int rc = NB == 4 ? launch_nb<4>(ctx, ts, p, n_iter, method_vb) : launch_nb<7>(ctx, ts, p, n_iter, method_vb);
     if (rc == VLGP_OK) *handled = true;
