@@ -13,6 +13,8 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "config2"
 n_em = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 n_launch = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 trials, params, config, c = bench.build_problem(cfg)
+if os.environ.get("VLGP_TIME_NTRIALS"):
+    trials = trials[:int(os.environ["VLGP_TIME_NTRIALS"])]
 make_cholesky(trials, params, config)
 core.update_w(trials, params, config)
 core.update_v(trials, params, config)

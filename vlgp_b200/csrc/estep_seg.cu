@@ -65,7 +65,7 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
     p.fused = fast && p.use_dmma && !getenv("VLGP_ESTEP_NO_FUSED");
     p.f32 = p.fused && ctx->estep_f32;                            // vlgp_set_precision(ctx, 32)
     const bool stage_y = ts->ydtype == VLGP_Y_U8 && !p.fused;     // the fused pipeline reads the counts once, in place
-    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total, p.f32);
+    size_t smem = seg_smem_bytes(L, N, W, p.g_total, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total, p.f32, p.fused);
     bool big = false;
     for (int l = 0; l < L; ++l)
         if (p.nc[l] > 16) big = true;
@@ -79,7 +79,7 @@ int vlgp_launch_estep_segments(vlgp_ctx *ctx, TrialSet *ts, int n_iter, double d
             p.ldg[l] = ctx->rank;
         }
         big = true;                          // the NBMAX = 4 instantiations carry the in-place path
-        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total, p.f32);
+        smem = seg_smem_bytes(L, N, W, 0, p.m_total, p.tpb, stage_y, p.kp, p.np, p.col_total, p.f32, p.fused);
     }
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return VLGP_OK;
     int rc = VLGP_OK;

@@ -83,7 +83,7 @@ struct Smem {
         part = d;                                 // rate passes: tpb x W x LT partial sums ...
         vec = d;                                  // ... aliased with the per-latent vectors (3 x 64) of the r x r phases
                                                   // (fused path: NWARP x col_total partial projections + col_total)
-        d += max(max(p.tpb * W * LT, LT * 192), (NWARP + 1) * p.col_total);
+        d += max(max(max(p.tpb * W * LT, LT * 192), (NWARP + 1) * p.col_total), p.fused ? (W * N + 55) / 8 : 0);
         ya = d; d += W * LT;                      // fused path: y a_l' per (bin, latent), constant during the launch's iterations
         etab = d; d += 32;                        // 2^(j/32) (common.cuh: VLGP_EXP_T)
         pois = (uint8_t *)d;
@@ -92,9 +92,10 @@ struct Smem {
 };
 
 __host__ __device__ inline size_t seg_smem_bytes(int LT, int N, int W, int g_total, int m_total, int tpb, bool y_u8,
-                                                 int kp, int np, int col_total, bool f32 = false) {
+                                                 int kp, int np, int col_total, bool f32 = false, bool fused = false) {
     size_t un = (size_t)tpb * W * LT > (size_t)LT * 192 ? (size_t)tpb * W * LT : (size_t)LT * 192;
     if ((size_t)(NWARP + 1) * col_total > un) un = (size_t)(NWARP + 1) * col_total;
+    if (fused && (size_t)(W * N + 55) / 8 > un) un = (size_t)(W * N + 55) / 8;      // fused path: count tile staged here
     size_t par = (size_t)2 * LT * N + 2 * N > (size_t)kp * np ? (size_t)2 * LT * N + 2 * N : (size_t)kp * np;
     if (f32) par = (size_t)LT * N + (N + 2) / 2;
     size_t d = par + g_total + m_total + (size_t)6 * W * LT + 32 + un;
@@ -1211,7 +1212,22 @@ __global__ void __launch_bounds__(NT, (NBMAX <= 2 ? 3 : 2)) estep_seg_kernel(Seg
             s.dmu[i] = 0.0;
         }
         if (FAST && p.fused) {
-            if (8 * (tid >> 5) < W) ya_tiles<LT, FAST == 2>(p, s, (const uint8_t *)p.y + bin0 * N);
+            // The count tile is read once per segment (y a_l' below): staged through the partial-sum region with
+            // 128-bit loads (the buffer starts at the source's offset from a 16-byte boundary, so body chunks are
+            // aligned on both sides).  Read in place by the row-tile warps it costs one HBM round trip per column tile
+            // on a cold L2 -- with few segments per GPU (8-GPU shards) that was 0.8 ms of a 2.1 ms launch.
+            const uint8_t *ysrc = (const uint8_t *)p.y + bin0 * N;
+            const int mis = (int)((uintptr_t)ysrc & 15), nby = W * N;
+            uint8_t *ybuf = (uint8_t *)(((uintptr_t)s.part + 15) & ~(uintptr_t)15) + mis;
+            const int head = min(nby, (16 - mis) & 15);
+            for (int i = tid; i < head; i += NT) ybuf[i] = ysrc[i];
+            const int nvec = (nby - head) >> 4;
+            const uint4 *src4 = (const uint4 *)(ysrc + head);
+            uint4 *dst4 = (uint4 *)(ybuf + head);
+            for (int i = tid; i < nvec; i += NT) dst4[i] = src4[i];
+            for (int i = head + 16 * nvec + tid; i < nby; i += NT) ybuf[i] = ysrc[i];
+            __syncthreads();
+            if (8 * (tid >> 5) < W) ya_tiles<LT, FAST == 2>(p, s, ybuf);
         } else if (p.ydtype == VLGP_Y_U8) {
             const uint8_t *ysrc = (const uint8_t *)p.y + bin0 * N;
             for (int i = tid; i < W * N; i += NT) s.ys[i] = ysrc[i];
