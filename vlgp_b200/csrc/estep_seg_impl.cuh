@@ -804,18 +804,23 @@ __device__ __forceinline__ void variance_rows_nb(const SegArgs &p, const Smem<LT
         const int c = 4 * k + q;
         aop[k] = (tin && c < nc) ? grow[c] : 0.0;
     }
+    // g' Minv g over the lower block triangle only (Minv is symmetric): per column block the diagonal block once and the
+    // blocks below it twice -- NB (NB + 1) DMMA per row tile instead of 2 NB^2
     double acc = 0.0;
 #pragma unroll
     for (int jt = 0; jt < NB; ++jt) {
-        Tile T{0.0, 0.0};
+        Tile Td{0.0, 0.0}, To{0.0, 0.0};
 #pragma unroll
-        for (int k = 0; k < 2 * NB; ++k)
-            if (4 * k < nc) dmma(T, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
+        for (int k = 2 * jt; k < 2 * jt + 2; ++k)
+            if (4 * k < nc) dmma(Td, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
+#pragma unroll
+        for (int k = 2 * jt + 2; k < 2 * NB; ++k)
+            if (4 * k < nc) dmma(To, aop[k], M[(4 * k + q) * LDM + 8 * jt + r]);
         const int c = 8 * jt + c0;
         const double g0 = (tin && c < nc) ? grow[c] : 0.0;
         const double g1 = (tin && c + 1 < nc) ? grow[c + 1] : 0.0;
-        acc = fma(T.x, g0, acc);
-        acc = fma(T.y, g1, acc);
+        acc = fma(fma(2.0, To.x, Td.x), g0, acc);
+        acc = fma(fma(2.0, To.y, Td.y), g1, acc);
     }
     acc += __shfl_xor_sync(FULL, acc, 1);
     acc += __shfl_xor_sync(FULL, acc, 2);
