@@ -92,6 +92,11 @@ VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, 
 /* Initial posterior means on the device (vlgp/preprocess.py:36-41: mu = FactorAnalysis.transform(y) per trial):
  * mu[bin] = ((y[bin] - mean) P) Cz with mean (N), P = Wpsi' (N x L) and Cz = cov_z (L x L) of the factor model fitted
  * on the host (sklearn FactorAnalysis.transform evaluates the two products in this order). */
+/* Start copying the listed state arrays (bit 0 mu, 1 v, 2 w, 3 dmu) to pinned host memory on a copy stream, behind what is
+ * enqueued so far; a later vlgp_trials_get_state_parts of one of them is served from that copy unless the set's state has
+ * been written in between.  vem() calls this after the E-step of its last iteration (vlgp/core.py:307-326 downloads
+ * nothing: its trial dicts ARE the state), so the transfer runs under the M- and H-step. */
+VLGP_API int vlgp_trials_prefetch_state(vlgp_ctx *ctx, int set_id, int which_mask);
 VLGP_API int vlgp_trials_project_y(vlgp_ctx *ctx, int set_id, const double *mean, const double *P, const double *Cz);
 /* Per-trial-block variants (which: 0 mu, 1 v, 2 w, 3 dmu [get only]; parts[i]: rows[i] x L float64, C-contiguous):
  * gather / scatter through the pinned double-buffered pipeline, so segment views are read and written in place. */

@@ -68,6 +68,13 @@ t0 = time.perf_counter()
 core.vem(segs, params, config)
 dt = time.perf_counter() - t0
 sys.stdout = sys.__stdout__
+for rep in range(3):
+    sys.stdout = open(os.devnull, "w")
+    t0 = time.perf_counter()
+    core.vem(segs, params, config)
+    dt = time.perf_counter() - t0
+    sys.stdout = sys.__stdout__
+    print("vem() again: %.2f ms" % (dt * 1e3), {k: [round(x * 1e3, 2) for x in v] for k, v in config["runtime"].items() if k != "it"})
 print("vem() whole call: %.2f ms" % (dt * 1e3), {k: [round(x * 1e3, 2) for x in v] for k, v in config["runtime"].items() if k != "it"})
 with Session(segs, params) as s2:
     sys.stdout = open(os.devnull, "w")

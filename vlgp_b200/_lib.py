@@ -91,6 +91,7 @@ EXPORTS = {
     "vlgp_peak_hbm": (C.c_int, [ctx_p, C.c_uint64, c_double_p]),
     "vlgp_flush_l2": (C.c_int, [ctx_p]),
     "vlgp_set_precision": (C.c_int, [ctx_p, C.c_int]),
+    "vlgp_trials_prefetch_state": (C.c_int, [ctx_p, C.c_int, C.c_int]),
     "vlgp_profile_enable": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_profile_get": (C.c_int, [ctx_p, C.c_int, c_double_p, c_i64_p]),
 }

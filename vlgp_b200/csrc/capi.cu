@@ -270,6 +270,10 @@ int vlgp_destroy(vlgp_ctx *ctx) {
     F(ctx->d_poisson); F(ctx->d_a); F(ctx->d_b); F(ctx->d_noise); F(ctx->d_da); F(ctx->d_db);
     F(ctx->d_bpart); F(ctx->d_bstat);
     F(ctx->d_mpart); F(ctx->d_mstat); F(ctx->d_ymom); F(ctx->d_ppack); F(ctx->d_gshared); F(ctx->d_flags); F(ctx->d_smslots); F(ctx->d_small); F(ctx->d_flush);
+    if (ctx->stream_copy) { cudaStreamSynchronize(ctx->stream_copy); cudaStreamDestroy(ctx->stream_copy); }
+    if (ctx->h_prefetch) cudaFreeHost(ctx->h_prefetch);
+    if (ctx->ev_prefetch_go) cudaEventDestroy(ctx->ev_prefetch_go);
+    if (ctx->ev_prefetch_done) cudaEventDestroy(ctx->ev_prefetch_done);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (int i = 0; i < 2; ++i) {
@@ -531,6 +535,10 @@ int vlgp_trials_free(vlgp_ctx *ctx, int set_id) {
     if (!ts) return vlgp_fail(ctx, VLGP_ERR_ARG, "trials_free: bad set %d", set_id);
     CK(cudaSetDevice(ctx->device));
     SETTLE();
+    if (ctx->prefetch_set == set_id) {            // a prefetch of this set's state may still be in flight
+        if (ctx->stream_copy) CK(cudaStreamSynchronize(ctx->stream_copy));
+        ctx->prefetch_set = -1;
+    }
     free_set(*ts, ctx->stream);
     return VLGP_OK;
 }
@@ -754,6 +762,24 @@ static double *state_array(TrialSet *ts, int which) {
     }
 }
 
+// Scatter of a prefetched array (pinned, already on the host) into the caller's blocks.
+static int scatter_prefetched(vlgp_ctx *ctx, const double *src, int n_parts, void *const *parts, const std::vector<int64_t> &off) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+    for (int i = 0; i + 1 < n_parts && nthreads > 1; ++i) {          // overlapping blocks: in order, last one wins
+        const unsigned char *a0 = (const unsigned char *)parts[i], *a1 = a0 + (size_t)(off[i + 1] - off[i]) * 8;
+        const unsigned char *b0 = (const unsigned char *)parts[i + 1], *b1 = b0 + (size_t)(off[i + 2] - off[i + 1]) * 8;
+        if (a0 < b1 && b0 < a1) nthreads = 1;
+    }
+    auto work = [&](int t) {
+        const int p0 = (int)((int64_t)n_parts * t / nthreads), p1 = (int)((int64_t)n_parts * (t + 1) / nthreads);
+        for (int p = p0; p < p1; ++p) memcpy(parts[p], src + off[p], (size_t)(off[p + 1] - off[p]) * sizeof(double));
+    };
+    if (nthreads == 1) work(0);
+    else vlgp_host_parallel_for(nthreads, work);
+    return VLGP_OK;
+}
+
 static int state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, void *const *parts, const int64_t *rows,
                        bool to_device) {
     TrialSet *ts = get_set(ctx, set_id);
@@ -762,11 +788,54 @@ static int state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, void *
     REQUIRE(dev != nullptr && (which != 3 || !to_device), "trials_state_parts: bad array selector %d", which);
     CK(cudaSetDevice(ctx->device));
     if (to_device) SETTLE();
+    if (to_device) ts->state_version++;
     std::vector<int64_t> off(n_parts + 1, 0);
     for (int i = 0; i < n_parts; ++i) off[i + 1] = off[i] + rows[i] * (int64_t)ctx->L;
     REQUIRE(off[n_parts] == ts->nbin * (int64_t)ctx->L, "trials_state_parts: blocks hold %lld rows, the set has %lld bins",
             (long long)(off[n_parts] / ctx->L), (long long)ts->nbin);
+    if (!to_device && ctx->prefetch_set == set_id && ts->prefetch_version == ts->state_version &&
+        (ts->prefetch_mask & (1 << which)) && ctx->h_prefetch) {
+        CK(cudaEventSynchronize(ctx->ev_prefetch_done));
+        const double *src = (const double *)((unsigned char *)ctx->h_prefetch + (size_t)which * ts->nbin * ctx->L * sizeof(double));
+        return scatter_prefetched(ctx, src, n_parts, parts, off);
+    }
     return pipeline_copy(ctx, dev, sizeof(double), n_parts, parts, off, to_device);
+}
+
+// Starts copying the listed state arrays (bit 0 mu, 1 v, 2 w, 3 dmu) to pinned host memory on a copy stream, behind
+// everything enqueued so far on the main stream.  A later vlgp_trials_get_state_parts of one of them is then served
+// from that copy -- provided no entry point has written the set's state in between (otherwise it is ignored).  vem()
+// issues this after the E-step of its last iteration: the transfer runs under the M- and H-step.
+int vlgp_trials_prefetch_state(vlgp_ctx *ctx, int set_id, int which_mask) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && which_mask > 0 && which_mask < 16, "trials_prefetch_state: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ts->nbin * ctx->L * sizeof(double);
+    if (ctx->prefetch_cap < 4 * bytes) {
+        if (ctx->h_prefetch) {
+            CK(cudaStreamSynchronize(ctx->stream_copy));
+            CK(cudaFreeHost(ctx->h_prefetch));
+            ctx->h_prefetch = nullptr;
+        }
+        CK(cudaMallocHost(&ctx->h_prefetch, 4 * bytes));
+        ctx->prefetch_cap = 4 * bytes;
+    }
+    if (!ctx->stream_copy) {
+        CK(cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_prefetch_go, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_prefetch_done, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ctx->ev_prefetch_go, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_prefetch_go, 0));
+    for (int k = 0; k < 4; ++k)
+        if (which_mask & (1 << k))
+            CK(cudaMemcpyAsync((unsigned char *)ctx->h_prefetch + k * bytes, state_array(ts, k), bytes, cudaMemcpyDeviceToHost,
+                               ctx->stream_copy));
+    CK(cudaEventRecord(ctx->ev_prefetch_done, ctx->stream_copy));
+    ctx->prefetch_set = set_id;
+    ts->prefetch_mask = which_mask;
+    ts->prefetch_version = ts->state_version;
+    return VLGP_OK;
 }
 
 int vlgp_trials_set_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, const double *const *parts,
@@ -785,6 +854,7 @@ int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, const dou
     CK(cudaSetDevice(ctx->device));
     SETTLE();
     const size_t bytes = (size_t)ts->nbin * ctx->L * sizeof(double);
+    ts->state_version++;
     if (mu) CK(cudaMemcpyAsync(ts->d_mu, mu, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (v) CK(cudaMemcpyAsync(ts->d_v, v, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (w) CK(cudaMemcpyAsync(ts->d_w, w, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -939,6 +1009,7 @@ static int estep_impl(vlgp_ctx *ctx, int set_id, int n_iter, double dmu_bound, i
         if (rc) return rc;
     }
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    ts->state_version++;
     {
         ProfScope ps(ctx, 0);
         bool handled = false;
@@ -983,6 +1054,7 @@ int vlgp_trials_copy_rows(vlgp_ctx *ctx, int set_id, int which_mask, const int64
     }
     CK(cudaSetDevice(ctx->device));
     SETTLE();
+    ts->state_version++;
     int64_t *d_idx = nullptr;
     std::vector<int64_t> both((size_t)2 * n);
     std::copy(src, src + n, both.begin());
@@ -1007,6 +1079,7 @@ int vlgp_update_w(vlgp_ctx *ctx, int set_id) {
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     SETTLE();
+    ts->state_version++;
     rc = vlgp_launch_estep_generic(ctx, ts, 1, 1, 0.0, 0);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1020,6 +1093,7 @@ int vlgp_update_v(vlgp_ctx *ctx, int set_id, int *n_failed) {
     CK(cudaSetDevice(ctx->device));
     SETTLE();
     CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    ts->state_version++;
     rc = vlgp_launch_estep_generic(ctx, ts, 2, 1, 0.0, 1);
     if (rc) return rc;
     ctx->counters[1] += (int64_t)ts->n_trials * ctx->L;
@@ -1184,6 +1258,7 @@ extern "C" int vlgp_trials_project_y(vlgp_ctx *ctx, int set_id, const double *me
     REQUIRE(ts && ts->d_y && mean && P && Cz, "trials_project_y: bad arguments (y must be set)");
     CK(cudaSetDevice(ctx->device));
     SETTLE();
+    ts->state_version++;
     const size_t N = ctx->N, L = ctx->L;
     double *d = nullptr;
     CK(vlgp_dalloc(ctx, &d, (N + N * L + L * L) * sizeof(double)));
@@ -1205,6 +1280,7 @@ static int latent_affine_impl(vlgp_ctx *ctx, int set_id, const double *shift, co
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts, "latent_affine: bad set %d", set_id);
     if (!shift && !M) return VLGP_OK;
+    ts->state_version++;
     if (listed && n_rows == 0) return VLGP_OK;
     if (listed) {
         REQUIRE(rows && n_rows > 0, "latent_affine_rows: bad arguments");

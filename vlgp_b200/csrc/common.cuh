@@ -66,6 +66,10 @@ struct TrialSet {
     int k3_items = 0;
     int *d_k3_tab = nullptr, *d_k3_bad = nullptr;
     double *d_k3_buf = nullptr;
+    // state prefetch (vlgp_trials_prefetch_state): mu | v | w | dmu copied to ctx->h_prefetch behind the E-step; valid
+    // while no entry point has written the state since (state_version)
+    uint64_t state_version = 0, prefetch_version = ~0ull;
+    int prefetch_mask = 0;
     int gen = 0;                       // generation of the slot: stale handles of freed sets are refused
 };
 
@@ -116,6 +120,11 @@ struct vlgp_ctx {
     int *h_flags = nullptr;      // pinned
     double *h_pin = nullptr;     // pinned 4 KB staging for tiny D2H/H2D
     double *d_small = nullptr;   // 4 KB device staging
+    void *h_prefetch = nullptr;                   // pinned: one set's mu | v | w | dmu, filled by a copy stream
+    size_t prefetch_cap = 0;
+    int prefetch_set = -1;                        // handle of the set it belongs to
+    cudaStream_t stream_copy = nullptr;
+    cudaEvent_t ev_prefetch_go = nullptr, ev_prefetch_done = nullptr;
     void *h_stage[2] = {nullptr, nullptr};        // pinned double buffer of the y upload pipeline
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     // comm

@@ -529,6 +529,13 @@ class TrialSet:
                                              C.byref(rounds)), "hstep_optimize")
         return np.exp(res), fval, nfev, task, rounds.value
 
+    def prefetch_state(self, which=("mu", "v", "w", "dmu")):
+        """Start the device-to-host copy of the listed state arrays behind what is enqueued so far; a following
+        get_state_parts is served from it unless the state was written in between (include/vlgp_b200.h)."""
+        lib, ctx = self._lib()
+        mask = sum(1 << ("mu", "v", "w", "dmu").index(k) for k in which)
+        self.eng._ck(lib.vlgp_trials_prefetch_state(ctx, self.id, int(mask)), "prefetch_state")
+
     def posterior_cov(self, trial, latent, reg=1e-6):
         """(T, T) posterior covariance inv(inv(G G' + reg I) + diag(w)) of one latent of one member of the set."""
         lib, ctx = self._lib()
