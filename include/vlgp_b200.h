@@ -233,6 +233,15 @@ VLGP_API int vlgp_comm_attach_shm(vlgp_ctx *ctx, void *handle);
  * instead of an NCCL launch in between.  *enabled = 0 (and nothing changes) when some rank cannot map some peer. */
 VLGP_API int vlgp_comm_enable_p2p(vlgp_ctx *ctx, int *enabled);
 
+/* ---- GPFA branch (vlgp/gpfa.py:20-56; reached through gpfa.fit and api.fastfit) --------------------------------------
+ * vlgp_gpfa_estep: mu <- A B^-1 (y - d) of every equal-length segment of the set (vlgp/gpfa.py:37-45, before the mean
+ * subtraction), evaluated as P h with h = bigC' bigR^-1 (y - d) and P = (I + bigK S)^-1 bigK formed by the caller:
+ * C is L x N, d N, rho W x N (1 / noise applied to (bin, neuron)), PT the transpose of P, (L W) x (L W), vector index
+ * l W + t.  vlgp_gpfa_stats: Z1'Z1 ((L+1)^2), Z1'Y ((L+1) x N) and sum y^2 (N) with Z1 = [mu, 1] -- the normal
+ * equations of the lstsq M-step (vlgp/gpfa.py:49-53,83-88). */
+VLGP_API int vlgp_gpfa_estep(vlgp_ctx *ctx, int set_id, const double *C, const double *d, const double *rho, const double *PT);
+VLGP_API int vlgp_gpfa_stats(vlgp_ctx *ctx, int set_id, double *ZtZ, double *ZtY, double *yy);
+
 /* ---- arithmetic of the E-step rate passes (BASELINE.json configs[2]: "fp32") ----------------------------------------
  * bits = 64 (default): everything in double precision, results match the reference (vlgp/core.py:68-113) to 1e-10.
  * bits = 32: the rate passes of the segment E-step (linear predictor, exp link, sums over neurons -- the bulk of the

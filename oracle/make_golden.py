@@ -426,6 +426,29 @@ def golden_vem_regressors(ref):
     print("vem_regressors.npz", len(out))
 
 
+def golden_gpfa(ref):
+    """vlgp/gpfa.py: em() on stacked segments -- identity noise (what prepare() passes) and a non-uniform initial R (which
+    exposes the reference's time-major bigR against its neuron-major bigC) -- and sekernel."""
+    import vlgp.gpfa as rgpfa
+    from vlgp.gp import sekernel
+
+    rng = np.random.default_rng(21)
+    out = {}
+    for case, (m, n, ydim, zdim, iters, uniform) in {"eye": (12, 20, 8, 2, 3, True), "noise": (9, 25, 7, 3, 4, False),
+                                                     "one": (6, 50, 12, 2, 1, True)}.items():
+        y = rng.poisson(1.0, (m, n, ydim)).astype(float)
+        C = rng.standard_normal((zdim, ydim))
+        d = y.mean(axis=(0, 1))[None, :]
+        R = np.eye(ydim) if uniform else np.diag(0.5 + rng.random(ydim))
+        K = sekernel(np.arange(n) * 1.0, 1.0, 3.0)
+        z, C2, d2, R2 = rgpfa.em(y.copy(), C.copy(), d.copy(), R.copy(), K, iters)
+        pre = case + "_"
+        out.update({pre + "y": y, pre + "C": C, pre + "d": d, pre + "R": R, pre + "K": K, pre + "iters": iters,
+                    pre + "out_z": z, pre + "out_C": C2, pre + "out_d": d2, pre + "out_R": R2})
+    np.savez_compressed(os.path.join(OUT, "gpfa.npz"), **out)
+    print("gpfa.npz", len(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -433,7 +456,7 @@ def main():
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
                golden_fit_fixed_omega, golden_vem_options, golden_api_extras,
-               golden_fit_options, golden_fit_overlap, golden_vem_regressors):
+               golden_fit_options, golden_fit_overlap, golden_vem_regressors, golden_gpfa):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)
 

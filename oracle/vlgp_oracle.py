@@ -477,3 +477,46 @@ def cut_trial_starts(length, window, rng_multinomial=np.random.multinomial):
     start = np.cumsum(np.full(nseg, window, dtype=int)) - window
     shift = np.cumsum(np.append([0], rng_multinomial(overlap, np.ones(nseg - 1) / (nseg - 1))))
     return start - shift
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# GPFA branch (vlgp/gpfa.py:20-56)
+# --------------------------------------------------------------------------------------------------------------------
+def sekernel(x, var, scale, jitter=1e-6):
+    """vlgp/gp.py:165-171."""
+    x = np.asarray(x, dtype=float).reshape(-1, 1) / scale
+    return var * np.exp(-0.5 * (x - x.T) ** 2) + np.eye(x.shape[0]) * jitter
+
+
+def gpfa_em(y, C, d, R, K, max_iter):
+    """Restates gpfa.em (vlgp/gpfa.py:20-56) without its (n ydim)^2 Kronecker matrices: E-step through the push-through
+    identity z = (I + bigK S)^-1 bigK bigC' bigR^-1 (y - d), M-step lstsq through its normal equations.  Keeps the
+    reference's two quirks: bigR is built once from the R passed in (:31), and it is ordered (time, neuron) against the
+    (neuron, time) order of bigC and the residual (:30,41-42), i.e. noise R[(j n + t) % ydim] for neuron j at bin t."""
+    y = np.asarray(y, dtype=float)
+    m, n, ydim = y.shape
+    C = np.array(C, dtype=float)
+    zdim = C.shape[0]
+    d = np.asarray(d, dtype=float).reshape(1, ydim)
+    Y = y.reshape(-1, ydim)
+    bigK = np.kron(np.eye(zdim), K)
+    idx = (np.arange(ydim)[:, None] * n + np.arange(n)[None, :]) % ydim
+    rho = 1.0 / np.diag(R)[idx]                                        # [j, t]
+    z = np.zeros((m, n, zdim))
+    t = np.arange(n)
+    for _ in range(max_iter):
+        h = np.einsum("lj,jt,stj->slt", C, rho, y - d[None, :])
+        Q = np.einsum("lj,kj,jt->lkt", C, C, rho)
+        S = np.zeros((zdim * n, zdim * n))
+        for l in range(zdim):
+            for k in range(zdim):
+                S[l * n + t, k * n + t] = Q[l, k]
+        P = np.linalg.solve(np.eye(zdim * n) + bigK @ S, bigK)
+        z = (h.reshape(m, -1) @ P.T).reshape(m, zdim, n).transpose(0, 2, 1)
+        z = z - z.mean(axis=(0, 1), keepdims=True)
+        Z1 = np.column_stack([z.reshape(-1, zdim), np.ones(m * n)])
+        coef, r, *_ = np.linalg.lstsq(Z1, Y, rcond=None)
+        C, d = coef[:-1, :], coef[[-1], :]
+        R = np.diag(r ** 2)
+        C = C / np.linalg.norm(C)
+    return z, C, d, R

@@ -680,6 +680,55 @@ def test_posterior_cov_and_sample_posterior(vl):
         assert 0.6 < np.median(ratio) < 1.4
 
 
+@pytest.mark.parametrize("case", ["eye", "noise", "one"])
+def test_gpfa_em_golden(vl, case):
+    """GPFA branch: gpfa.em on the device (csrc/gpfa.cu) against the reference's em() (vlgp/gpfa.py:20-56), including a
+    non-uniform initial R, which exposes the reference's (time, neuron) ordering of bigR."""
+    from vlgp_b200 import gpfa
+
+    g = load_golden("gpfa")
+    p = case + "_"
+    z, C, d, R = gpfa.em(g[p + "y"], g[p + "C"], g[p + "d"], g[p + "R"], g[p + "K"], int(g[p + "iters"]))
+    for got, key in ((z, "z"), (C, "C"), (d, "d"), (R, "R")):
+        assert relerr(got, g[p + "out_" + key]) < 1e-9, key
+    assert relerr(gpfa.sekernel(np.arange(g[p + "K"].shape[0]) * 1.0, 1.0, 3.0), g[p + "K"]) < 1e-15
+
+
+def test_gpfa_fit_and_fastfit_config2_shape(vl):
+    """gpfa.fit on a config-2-shaped problem (window 50, 100 neurons, 5 latents) against the oracle's em on the same
+    prepared inputs; infer() against the E-step it restates; api.fastfit runs end to end and leaves a posterior."""
+    import vlgp_b200
+    from vlgp_b200 import gpfa
+    from vlgp_b200.synth import make_trials
+    from oracle import vlgp_oracle as orc
+
+    trials = make_trials(8, 200, 100, 5, seed=4)
+    np.random.seed(0)
+    y, C0, d0, R0, K = gpfa.prepare(copy.deepcopy(trials), 5, dt=1.0, var=1.0, scale=8.0)
+    assert y.shape == (32, 50, 100) and K.shape == (50, 50)
+    zr, Cr, dr, Rr = orc.gpfa_em(y, C0, d0, R0, K, 3)
+    z, C, d, R = gpfa.em(y, C0, d0, R0, K, 3)
+    for got, ref in ((z, zr), (C, Cr), (d, dr), (R, Rr)):
+        assert relerr(got, ref) < 1e-9
+    np.random.seed(0)
+    y2, z2, C2, d2, R2 = gpfa.fit(copy.deepcopy(trials), 5, dt=1.0, var=1.0, scale=8.0, max_iter=3)
+    assert relerr(z2, zr) < 1e-9 and relerr(C2, Cr) < 1e-9
+    # infer: one short trial, against the dense expression of vlgp/gpfa.py:59-76
+    tr = dict(y=trials[0]["y"][:30].astype(float), mu=np.zeros((30, 5)), K=gpfa.sekernel(np.arange(30) * 1.0, 1.0, 8.0))
+    Rn = np.diag(0.5 + np.random.default_rng(1).random(100))
+    gpfa.infer([tr], C, np.abs(d) + 0.1, Rn)
+    n, ydim, zdim = 30, 100, 5
+    bigC, bigK, bigR = np.kron(C.T, np.eye(n)), np.kron(np.eye(zdim), tr["K"]), np.kron(np.eye(n), Rn)
+    A = bigK @ bigC.T
+    zz = A @ np.linalg.solve(bigC @ A + bigR, (tr["y"] - (np.abs(d) + 0.1)).T.reshape(-1, 1))
+    assert relerr(tr["mu"], zz.reshape((zdim, -1)).T) < 1e-9
+    # fastfit: GPFA then vLGP inference from it
+    np.random.seed(0)
+    tf = copy.deepcopy(trials)
+    assert vlgp_b200.api.fastfit(tf, 5, dt=1.0, var=1.0, scale=8.0, max_iter=2) is None
+    assert all(np.isfinite(t["mu"]).all() and t["mu"].shape == (200, 5) and (t["v"] > 0).all() for t in tf)
+
+
 def test_reference_api_smoke(vl):
     """The reference's own API test (tests/test_api.py:4-38 there) with `import vlgp_b200 as vlgp`: integer counts from
     np.random.poisson, an extra user key per trial, fit with every default, then transform on the fitted trials."""

@@ -316,3 +316,15 @@ def test_transform_new_trials_pipeline():
     orc.estep(new, params, config, n_iter=config["max_iter"])
     for k in ("mu", "v", "w"):
         assert relerr(np.stack([t[k] for t in new]), g["new_" + k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("case", ["eye", "noise", "one"])
+def test_gpfa_em(case):
+    """GPFA branch (vlgp/gpfa.py:20-56): the oracle's Kronecker-free restatement against the reference's em() -- identity
+    noise, a non-uniform initial R (the reference's bigR ordering), a single iteration."""
+    g = load_golden("gpfa")
+    p = case + "_"
+    z, C, d, R = orc.gpfa_em(g[p + "y"], g[p + "C"], g[p + "d"], g[p + "R"], g[p + "K"], int(g[p + "iters"]))
+    for got, key in ((z, "z"), (C, "C"), (d, "d"), (R, "R")):
+        assert relerr(got, g[p + "out_" + key]) < 1e-11, key
+    assert relerr(orc.sekernel(np.arange(g[p + "K"].shape[0]) * 1.0, 1.0, 3.0), g[p + "K"]) < 1e-15

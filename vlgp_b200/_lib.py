@@ -90,6 +90,8 @@ EXPORTS = {
     "vlgp_peak_fp64": (C.c_int, [ctx_p, c_double_p, c_double_p]),
     "vlgp_peak_hbm": (C.c_int, [ctx_p, C.c_uint64, c_double_p]),
     "vlgp_flush_l2": (C.c_int, [ctx_p]),
+    "vlgp_gpfa_estep": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "vlgp_gpfa_stats": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "vlgp_set_precision": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_trials_prefetch_state": (C.c_int, [ctx_p, C.c_int, C.c_int]),
     "vlgp_profile_enable": (C.c_int, [ctx_p, C.c_int]),

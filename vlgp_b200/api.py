@@ -14,7 +14,7 @@ from .gp import make_cholesky
 from .preprocess import get_params, get_config, fill_trials, fill_params, initialize
 from .util import cut_trials
 
-__all__ = ["fit", "sample_posterior", "posterior_cov", "transform"]
+__all__ = ["fit", "sample_posterior", "posterior_cov", "transform", "map2vi", "fastfit", "resume"]
 
 logger = logging.getLogger(__name__)
 
@@ -193,3 +193,39 @@ def sample_posterior(trial, params, nsamples, reg=1e-6):
     for k in range(nfactors):
         out[:, :, k] = np.random.multivariate_normal(mu[:, k], cov[k], size=nsamples)
     return out
+
+
+def map2vi(trials, C, d, **kwargs):
+    """vLGP inference started from a GPFA solution: loading ``C``, bias ``log(d)``, then five E-step iterations on the
+    uncut trials (vlgp/api.py:79-105).  Like the reference it updates ``trials`` in place and returns what ``resume``
+    returns, i.e. None."""
+    n_factors = trials[0]["mu"].shape[-1]
+    config = get_config(**kwargs)
+    logger.info("\n".join(["{} : {}".format(k, v) for k, v in config.items()]))
+    config["callbacks"] = config["callbacks"] or []
+    kwargs["omega_bound"] = config["omega_bound"]
+    params = get_params(trials, n_factors, **kwargs)
+    params["a"] = C
+    params["b"] = np.log(d)
+    make_cholesky(trials, params, config)
+    update_w(trials, params, config)
+    update_v(trials, params, config)
+    config["max_iter"] = 5
+    return resume(trials, params, config)
+
+
+def fastfit(trials, n_factors, dt, var, scale, max_iter=20, **kwargs):
+    """GPFA (MAP) fit followed by vLGP inference from it (vlgp/api.py:108-119)."""
+    from . import gpfa
+
+    omega = np.full(n_factors, 0.5 / ((scale / dt) ** 2))
+    y, C, d, R, K = gpfa.prepare(trials, n_factors, dt=dt, var=var, scale=scale)
+    z, C, d, R = gpfa.em(y, C, d, R, K, max_iter)
+    return map2vi(trials, C, d, omega=omega, **kwargs)
+
+
+def resume(trials, params, config):
+    """Full-trial inference under the given parameters (vlgp/api.py:122-125)."""
+    _echo("Inferring")
+    infer(trials, params, config)
+    _echo("Done")

@@ -529,6 +529,23 @@ class TrialSet:
                                              C.byref(rounds)), "hstep_optimize")
         return np.exp(res), fval, nfev, task, rounds.value
 
+    def gpfa_estep(self, C, d, rho, P):
+        """mu <- P h for every (equal-length) segment, h = bigC' bigR^-1 (y - d) (vlgp/gpfa.py:37-45; csrc/gpfa.cu)."""
+        lib, ctx = self._lib()
+        C = np.ascontiguousarray(C, dtype=np.float64)
+        d = np.ascontiguousarray(np.ravel(d), dtype=np.float64)
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        PT = np.ascontiguousarray(np.asarray(P, dtype=np.float64).T)
+        self.eng._ck(lib.vlgp_gpfa_estep(ctx, self.id, dptr(C), dptr(d), dptr(rho), dptr(PT)), "gpfa_estep")
+
+    def gpfa_stats(self):
+        """(Z1'Z1, Z1'Y, sum y^2) with Z1 = [mu, 1] over all bins of the set (csrc/gpfa.cu)."""
+        lib, ctx = self._lib()
+        L1, N = self.eng.L + 1, self.eng.N
+        ztz, zty, yy = np.empty((L1, L1)), np.empty((L1, N)), np.empty(N)
+        self.eng._ck(lib.vlgp_gpfa_stats(ctx, self.id, dptr(ztz), dptr(zty), dptr(yy)), "gpfa_stats")
+        return ztz, zty, yy
+
     def prefetch_state(self, which=("mu", "v", "w", "dmu")):
         """Start the device-to-host copy of the listed state arrays behind what is enqueued so far; a following
         get_state_parts is served from it unless the state was written in between (include/vlgp_b200.h)."""

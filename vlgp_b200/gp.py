@@ -16,6 +16,13 @@ from .engine import get_engine
 __all__ = ["make_cholesky", "optimize", "optimze1d"]
 
 
+def sekernel(x, var, scale, jitter=1e-6):
+    """Squared-exponential covariance ``var * exp(-(x_i - x_j)^2 / (2 scale^2)) + jitter * I`` (vlgp/gp.py:165-171; used by
+    the GPFA branch only)."""
+    x = np.asarray(x, dtype=float).reshape(-1, 1) / scale
+    return var * np.exp(-0.5 * (x - x.T) ** 2) + np.eye(x.shape[0]) * jitter
+
+
 def make_cholesky(trials, params, config=None):
     """params['cholesky'] = {length: (zdim, length, rank)} for every unique trial length (REPLACES the dict)."""
     eng = get_engine()
