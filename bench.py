@@ -121,6 +121,13 @@ def run_reference(args):
     c = CONFIGS[args.config]
     full_trials = c["n_trials"]
     sample = max(1, min(args.cpu_sample_trials, full_trials))
+    # keep the whole --steps K --warmup W run within a few minutes: about 0.8-1.4 s per trial and EM iteration on one
+    # host core for the named workloads, so the sample shrinks when many steps are asked for (linear extrapolation in
+    # trials either way; `linearity` below evidences it)
+    budget_s = 240.0
+    per_trial_s = 1.4 * (c["N"] / 100.0) * ((c["T"] if isinstance(c["T"], int) else sum(c["T"]) / 2) / 1000.0)
+    while sample > 2 and (args.steps + args.warmup + 2) * sample * per_trial_s > budget_s:
+        sample -= 1
     probe = {}
     sec, nseg, _ = cpu_em_iteration_time(args.config, sample, args.steps, args.warmup, all_threads_probe=probe)
     # evidence for the linear extrapolation in the number of trials: one more iteration on half the sample
