@@ -38,7 +38,10 @@ struct MstatArgs {
     int last;                    // accumulate the noise moments
 };
 
-constexpr int MS_U = 2;          // bins per thread per tile: MS_U independent exp chains in flight
+#ifndef VLGP_MS_U
+#define VLGP_MS_U 2
+#endif
+constexpr int MS_U = VLGP_MS_U;          // bins per thread per tile: MS_U independent exp chains in flight
 constexpr int MS_TB_MAX = 128;   // bins per SMEM tile (= MS_U * J <= 128)
 
 template <int LT, bool FIRST, bool XB = false>
