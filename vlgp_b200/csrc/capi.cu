@@ -577,16 +577,21 @@ int vlgp_trials_set_y_parts(vlgp_ctx *ctx, int set_id, int n_parts, const void *
     for (int i = 0; i < n_parts; ++i) total += rows[i];
     REQUIRE(total == ts->nbin, "trials_set_y_parts: parts hold %lld rows, the set has %lld bins", (long long)total,
             (long long)ts->nbin);
-    const size_t STAGE = (size_t)8 << 20;          // bytes per pinned staging buffer
+    static const size_t STAGE = [] {              // bytes per pinned staging chunk (the buffers hold 8 MiB)
+        const char *e = getenv("VLGP_YSTAGE_KB");
+        size_t kb = e ? (size_t)atol(e) : 0;
+        return (kb >= 64 && kb <= 8192) ? kb << 10 : (size_t)8 << 20;
+    }();
     if (!ctx->h_stage[0]) {
-        CK(cudaMallocHost(&ctx->h_stage[0], STAGE));
-        CK(cudaMallocHost(&ctx->h_stage[1], STAGE));
+        CK(cudaMallocHost(&ctx->h_stage[0], (size_t)8 << 20));
+        CK(cudaMallocHost(&ctx->h_stage[1], (size_t)8 << 20));
         CK(cudaEventCreateWithFlags(&ctx->stage_ev[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->stage_ev[1], cudaEventDisableTiming));
     }
     // the float64 -> uint8 conversion streams 8 bytes per entry at ~6 GB/s per thread (hostpack.cpp): up to 16 threads
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nthreads = (int)std::min<unsigned>(hw ? hw : 4, src_dtype == VLGP_Y_F64 ? 16 : 8);
+    static const int thr_env = getenv("VLGP_HOST_THREADS") ? atoi(getenv("VLGP_HOST_THREADS")) : 0;
+    const int nthreads = thr_env > 0 ? thr_env : (int)std::min<unsigned>(hw ? hw : 4, src_dtype == VLGP_Y_F64 ? 16 : 8);
 
     // Flatten the parts into one virtual element range [0, total * N) so that chunks need not align with parts.
     std::vector<int64_t> part_off(n_parts + 1, 0);
@@ -673,7 +678,8 @@ static int pipeline_copy(vlgp_ctx *ctx, void *dev, size_t esz, int n_parts, void
     const int64_t nelem = part_off[n_parts];
     const int64_t chunk = (int64_t)(STAGE / esz);
     const unsigned hw = std::thread::hardware_concurrency();
-    int nthreads = (int)std::min<unsigned>(hw ? hw : 4, 8);
+    static const int thr_env = getenv("VLGP_HOST_THREADS") ? atoi(getenv("VLGP_HOST_THREADS")) : 0;
+    int nthreads = thr_env > 0 ? thr_env : (int)std::min<unsigned>(hw ? hw : 4, 8);
     if (!to_device) {
         // Overlapping destination blocks (segments of a trial whose length is not a multiple of the window are
         // overlapping views): scatter with one thread so that the blocks are written in order and the last one wins,
