@@ -228,6 +228,40 @@ def test_update_w_v_and_long_trial_estep_golden(vl):
         assert np.max(np.abs(np.stack([t[k] for t in trials]) - g["infer_" + k])) < STEP_TOL * np.max(np.abs(scale)), k
 
 
+@pytest.mark.parametrize("rank,lengths", [(30, [300, 77, 513]), (50, [64, 256, 257, 1000]), (8, [120, 120])])
+def test_long_trial_estep_vs_oracle(vl, rank, lengths):
+    """Long-trial E-step kernels (csrc/estep_long.cu) against the oracle: item boundaries (lengths that are / are not
+    multiples of the 64-bin chunks and 256-bin items), the 32-column instantiation (rank <= 32) next to the 56-column one,
+    several trials per length, MAP as well as VB."""
+    from vlgp_b200 import core
+    from oracle import vlgp_oracle as orc
+
+    rng = np.random.default_rng(rank)
+    N, L = 40, 4
+    params = dict(a=0.15 * rng.standard_normal((L, N)), b=np.full((1, N), np.log(0.1)), noise=np.ones(N),
+                  omega=np.exp(rng.uniform(np.log(2e-3), np.log(3e-2), L)), sigma=np.ones(L),
+                  likelihood=np.array(["poisson"] * N), zdim=L, ydim=N, xdim=1, rank=rank, gp_noise=1e-4, dt=1)
+    trials = []
+    for n in lengths:
+        trials.append(dict(y=rng.poisson(0.15, (n, N)).astype(float), x=np.ones((n, 1, N)),
+                           mu=0.2 * rng.standard_normal((n, L)), v=np.zeros((n, L)), w=np.zeros((n, L)),
+                           dmu=np.zeros((n, L))))
+    params["cholesky"] = orc.make_cholesky(sorted(set(lengths)), params["omega"], params["sigma"], rank)
+    for method in ("VB", "MAP"):
+        cfg = _cfg(Eniter=4, method=method)
+        t_ref, t_dev = copy.deepcopy(trials), copy.deepcopy(trials)
+        orc.update_w(t_ref, params)
+        orc.update_v(t_ref, params, cfg)
+        for a, b in zip(t_dev, t_ref):
+            a["w"], a["v"] = b["w"].copy(), b["v"].copy()
+        orc.estep(t_ref, copy.deepcopy(params), cfg)
+        core.estep(t_dev, copy.deepcopy(params), cfg)
+        for a, b in zip(t_dev, t_ref):
+            for k in ("mu", "v", "w", "dmu"):
+                scale = b["mu"] if k == "dmu" else b[k]
+                assert np.max(np.abs(a[k] - b[k])) <= 1e-9 * max(np.max(np.abs(scale)), 1e-300), (method, k, a[k].shape)
+
+
 def test_vem_three_iterations_golden(vl):
     from vlgp_b200 import core
     from vlgp_b200.gp import make_cholesky
