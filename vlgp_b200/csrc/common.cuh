@@ -152,7 +152,8 @@ int vlgp_fail(vlgp_ctx *ctx, int code, const char *fmt, ...);
 // raised in vlgp_create): a Session per vem() call then costs microseconds of allocator time instead of milliseconds.
 template <typename T>
 static inline cudaError_t vlgp_dalloc(vlgp_ctx *ctx, T **p, size_t bytes) {
-    return cudaMallocAsync((void **)p, bytes, ctx->stream);
+    // 256 bytes of slack: bulk copies (TMA) round the tail of a range up to 16 bytes
+    return cudaMallocAsync((void **)p, bytes + 256, ctx->stream);
 }
 template <typename T>
 static inline cudaError_t vlgp_dfree(vlgp_ctx *ctx, T *p) {

@@ -17,6 +17,7 @@
 // and iteration shared by the variance and the next mean step), same rate-pass tile loop (rate_tiles_core).  Sums over
 // partials are taken in item order: results are deterministic.
 #include "estep_seg_impl.cuh"
+#include "tma.cuh"
 
 namespace k3 {
 
@@ -59,36 +60,6 @@ __device__ __forceinline__ void stage_bx(const Args &p, double *Bx, double *etab
         Bx[i] = val;
     }
     if (tid < 32) etab[tid] = VLGP_EXP_T[tid];
-}
-
-// ---- TMA bulk copy (global -> shared) completed on an mbarrier --------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    unsigned done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
-            : "memory");
-    }
 }
 
 // ---- rate pass 1 + partial projections ------------------------------------------------------------------------------

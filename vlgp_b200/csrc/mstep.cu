@@ -9,6 +9,7 @@
 // The rate is computed once per iteration and every neuron is updated from it (vlgp/core.py:174-176).
 #include "common.cuh"
 #include "p2p.cuh"
+#include "tma.cuh"
 
 // regress.cu: general regressors
 int vlgp_launch_xb(vlgp_ctx *ctx, TrialSet *ts);
@@ -200,6 +201,186 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
             for (int jj = 0; jj < p.J; ++jj) x += buf[jj * p.NC + nloc];
             if (s < NS) p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = x;
             else p.ypart[((size_t)blockIdx.x * (LT + 1) + (s - NS)) * p.N + n] = x;
+        }
+    }
+}
+
+// The same statistics for the iterations that need neither the y-moments (first) nor the noise moments (last): 23 of the
+// 25 Newton iterations of an M-step read only (mu, v).  Their rows are staged CB bins at a time by TMA bulk copies into
+// a ring of MT_STAGES shared-memory stages (one elected thread issues them, mbarrier completion), so the loop carries
+// no global loads, no address arithmetic and no bounds checks; a thread = (bin-pair lane j, neuron) takes the adjacent
+// bins (2 pr, 2 pr + 1), pr = j, j + J, ...: the two rows are 2 LT consecutive doubles, read with LT 128-bit broadcast
+// loads per array.  Per entry ~60 FP64 instructions and ~9 others (the general kernel above: ~67 and ~100, which on
+// this issue-bound pipe cost as much as the arithmetic).  Same per-entry arithmetic as mstep_stats_kernel; only the
+// assignment of bins to accumulators (the summation order over bins) differs.
+constexpr int MT_STAGES = 4;
+constexpr int MT_ROUNDS = 8;             // bin pairs per thread per stage
+
+template <int LT>
+__global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(MstatArgs p, int64_t per) {
+    constexpr int NS = nstat_of(LT);
+    extern __shared__ __align__(16) unsigned char mt_raw[];
+    const int J = p.J, CB = 2 * J * MT_ROUNDS;
+    double *stage = (double *)mt_raw;                                  // MT_STAGES x [mu: CB x LT | v: CB x LT]
+    double *etab = stage + (size_t)MT_STAGES * 2 * CB * LT;            // 32
+    uint64_t *bar = (uint64_t *)(etab + 32);                           // MT_STAGES
+    double *red = (double *)mt_raw;                                    // after the loop: 2 x blockDim
+    const int tid = threadIdx.x;
+    const int j = tid / p.NC;
+    const int nloc = tid - j * p.NC;
+    const int n = blockIdx.y * p.NC + nloc;
+    const bool active = j < J && n < p.N;
+    const int64_t b0 = (int64_t)blockIdx.x * per;
+    const int64_t b1 = b0 + per < p.nbin ? b0 + per : p.nbin;
+    const int nchunk = b1 > b0 ? (int)((b1 - b0 + CB - 1) / CB) : 0;
+
+    auto issue = [&](int c) {                     // one thread: bulk copies of chunk c into its stage
+        const int64_t t0 = b0 + (int64_t)c * CB;
+        const int nb = (int)((b1 - t0 < CB) ? (b1 - t0) : CB);
+        const unsigned bytes = (unsigned)(((size_t)nb * LT * sizeof(double) + 15) & ~(size_t)15);   // buffers are padded
+        double *dst = stage + (size_t)(c % MT_STAGES) * 2 * CB * LT;
+        uint64_t *b = bar + (c % MT_STAGES);
+        mbar_expect_tx(b, 2 * bytes);
+        tma_load_1d(dst, p.mu + t0 * LT, bytes, b);
+        tma_load_1d(dst + (size_t)CB * LT, p.v + t0 * LT, bytes, b);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < MT_STAGES; ++s) mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) etab[tid] = VLGP_EXP_T[tid];
+    __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < MT_STAGES && c < nchunk; ++c) issue(c);
+
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+    double al[LT], a2h[LT];
+    double bn = 0.0;
+    bool pois = false;
+    if (active) {
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            al[l] = p.a[l * p.N + n];
+            a2h[l] = 0.5 * (al[l] * al[l]);
+        }
+        bn = p.b[n];
+        pois = p.poisson[n] != 0;
+    }
+    const bool work = active && pois;
+
+    // exp(min(x, 10)) of two arguments, chains interleaved, table in shared memory (bitwise trunc_exp2)
+    auto exp2 = [&](double x0, double x1, double &e0, double &e1) {
+        x0 = x0 > 10.0 ? 10.0 : x0;
+        x1 = x1 > 10.0 ? 10.0 : x1;
+        x0 = x0 < -708.0 ? -708.0 : x0;
+        x1 = x1 < -708.0 ? -708.0 : x1;
+        const double shift = 6755399441055744.0;
+        const double m0 = fma(x0, VLGP_EXP_INV, shift), m1 = fma(x1, VLGP_EXP_INV, shift);
+        const int i0 = __double2loint(m0), i1 = __double2loint(m1);
+        const double tj0 = etab[i0 & 31], tj1 = etab[i1 & 31];
+        const double t0 = m0 - shift, t1 = m1 - shift;
+        double r0 = fma(t0, -VLGP_EXP_HI, x0), r1 = fma(t1, -VLGP_EXP_HI, x1);
+        r0 = fma(t0, -VLGP_EXP_LO, r0);
+        r1 = fma(t1, -VLGP_EXP_LO, r1);
+        double p0 = VLGP_EXP_C[0], p1 = VLGP_EXP_C[0];
+#pragma unroll
+        for (int k = 1; k < 6; ++k) {
+            p0 = fma(p0, r0, VLGP_EXP_C[k]);
+            p1 = fma(p1, r1, VLGP_EXP_C[k]);
+        }
+        p0 *= r0;
+        p1 *= r1;
+        const double q0 = fma(tj0, p0, tj0), q1 = fma(tj1, p1, tj1);
+        const int ex0 = max(i0 >> 5, -1022), ex1 = max(i1 >> 5, -1022);
+        e0 = __hiloint2double(__double2hiint(q0) + (ex0 << 20), __double2loint(q0));
+        e1 = __hiloint2double(__double2hiint(q1) + (ex1 << 20), __double2loint(q1));
+    };
+    auto accumulate = [&](const double *m, const double *vv, double rr) {
+        acc[NS - 3] += rr;
+        double s[LT];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            s[l] = fma(vv[l], al[l], m[l]);
+            acc[l] = fma(s[l], rr, acc[l]);
+        }
+        int q = LT;
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            const double rs = rr * s[l];
+#pragma unroll
+            for (int k = 0; k <= l; ++k) {
+                acc[q] = fma(rs, s[k], acc[q]);
+                ++q;
+            }
+            acc[q - 1] = fma(rr, vv[l], acc[q - 1]);
+        }
+    };
+    auto lin_of = [&](const double *m, const double *vv) {
+        double e = bn, h = 0.0;
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            e = fma(m[l], al[l], e);
+            h = fma(vv[l], a2h[l], h);
+        }
+        return e + h;
+    };
+
+    for (int c = 0; c < nchunk; ++c) {
+        const int st = c % MT_STAGES;
+        const int64_t t0 = b0 + (int64_t)c * CB;
+        const int nb = (int)((b1 - t0 < CB) ? (b1 - t0) : CB);
+        mbar_wait(bar + st, (unsigned)((c / MT_STAGES) & 1));
+        if (work) {
+            const double *smu = stage + (size_t)st * 2 * CB * LT;
+            const double *sv = smu + (size_t)CB * LT;
+            const int npair = nb >> 1;
+#pragma unroll 1
+            for (int pr = j; pr < npair; pr += J) {
+                double m[2 * LT], vv[2 * LT];
+                const double2 *m2 = (const double2 *)(smu + (size_t)pr * 2 * LT);
+                const double2 *v2 = (const double2 *)(sv + (size_t)pr * 2 * LT);
+#pragma unroll
+                for (int q = 0; q < LT; ++q) {
+                    const double2 x = m2[q], y = v2[q];
+                    m[2 * q] = x.x;
+                    m[2 * q + 1] = x.y;
+                    vv[2 * q] = y.x;
+                    vv[2 * q + 1] = y.y;
+                }
+                double r0, r1;
+                exp2(lin_of(m, vv), lin_of(m + LT, vv + LT), r0, r1);
+                accumulate(m, vv, r0);
+                accumulate(m + LT, vv + LT, r1);
+            }
+            if ((nb & 1) && (npair % J) == j) {       // odd bin at the very end of the bin range
+                double m[LT], vv[LT];
+#pragma unroll
+                for (int l = 0; l < LT; ++l) {
+                    m[l] = smu[(size_t)(nb - 1) * LT + l];
+                    vv[l] = sv[(size_t)(nb - 1) * LT + l];
+                }
+                double r0, r1;
+                const double x = lin_of(m, vv);
+                exp2(x, x, r0, r1);
+                accumulate(m, vv, r0);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && c + MT_STAGES < nchunk) issue(c + MT_STAGES);
+    }
+    // reduce over the J bin lanes of this CTA (as in mstep_stats_kernel); the stages are free now
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double *buf = red + (s & 1) * blockDim.x;
+        buf[tid] = work ? acc[s] : 0.0;
+        __syncthreads();
+        if (j == 0 && n < p.N) {
+            double x = 0.0;
+            for (int jj = 0; jj < J; ++jj) x += buf[jj * p.NC + nloc];
+            p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = x;
         }
     }
 }
@@ -476,6 +657,8 @@ struct MstepJob {
     int n_iter = 0, next_it = 0;
     bool general_x = false;
     TrialSet *ts = nullptr;
+    size_t smem_tma = 0;         // mstep_stats_tma_kernel: dynamic shared memory (0: not usable for this shape)
+    int64_t per_tma = 0;         // its bins per CTA (even, so that every chunk starts on a 16-byte boundary)
 };
 
 template <int LT>
@@ -558,6 +741,17 @@ int mstep_setup_t(vlgp_ctx *ctx, TrialSet *ts, MstepJob &job, int n_iter, int us
     job.n_iter = n_iter; job.next_it = 0;
     job.general_x = ts->d_x != nullptr;
     job.ts = ts;
+    {   // TMA-staged kernel for the iterations between the first and the last
+        const size_t cb = (size_t)2 * J * MT_ROUNDS;
+        const size_t ring = ((size_t)MT_STAGES * 2 * cb * LT + 32 + MT_STAGES) * sizeof(double);
+        const size_t redb = 2 * (size_t)nt * sizeof(double);
+        job.smem_tma = ring > redb ? ring : redb;
+        job.per_tma = (((ts->nbin + gx - 1) / gx) + 1) & ~(int64_t)1;
+        if (job.smem_tma > (size_t)200 << 10 || getenv("VLGP_MSTEP_NO_TMA")) job.smem_tma = 0;
+        else if (job.smem_tma > (size_t)48 << 10)
+            CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)job.smem_tma));
+    }
     return VLGP_OK;
 }
 
@@ -582,6 +776,8 @@ int mstep_iter_t(vlgp_ctx *ctx, MstepJob &job, int it) {
                 mstep_stats_kernel<LT, false, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
         } else if (it == 0) {
             mstep_stats_kernel<LT, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
+        } else if (it < job.n_iter - 1 && job.smem_tma) {
+            mstep_stats_tma_kernel<LT><<<job.grid, job.nt, job.smem_tma, ctx->stream>>>(sa, job.per_tma);
         } else {
             mstep_stats_kernel<LT, false><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
         }
