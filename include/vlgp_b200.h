@@ -97,6 +97,16 @@ VLGP_API int vlgp_trials_set_state(vlgp_ctx *ctx, int set_id, const double *mu, 
  * been written in between.  vem() calls this after the E-step of its last iteration (vlgp/core.py:307-326 downloads
  * nothing: its trial dicts ARE the state), so the transfer runs under the M- and H-step. */
 VLGP_API int vlgp_trials_prefetch_state(vlgp_ctx *ctx, int set_id, int which_mask);
+/* The same with caller-owned page-locked destinations: dst[k] != NULL sends array k (nbin x L doubles) straight into that
+ * block instead of the context's staging area.  vlgp_trials_prefetch_take waits for the copy and reports whether block k
+ * holds the set's CURRENT array (nothing has written the state since): the host code then hands views of the block out
+ * as trial["w"] / trial["dmu"] -- the reference rebinds those keys to new arrays in every E-step (vlgp/core.py:117-120)
+ * -- with no further copy.  vlgp_host_alloc / vlgp_host_free: page-locked blocks for that purpose. */
+VLGP_API int vlgp_trials_prefetch_state_into(vlgp_ctx *ctx, int set_id, int which_mask, double *const *dst);
+VLGP_API int vlgp_trials_prefetch_take(vlgp_ctx *ctx, int set_id, int which, int *valid);
+VLGP_API int vlgp_trials_prefetch_wait(vlgp_ctx *ctx, int set_id);   /* the prefetch has landed; its blocks may be reused */
+VLGP_API int vlgp_host_alloc(void **p, size_t bytes);
+VLGP_API int vlgp_host_free(void *p);
 VLGP_API int vlgp_trials_project_y(vlgp_ctx *ctx, int set_id, const double *mean, const double *P, const double *Cz);
 /* Per-trial-block variants (which: 0 mu, 1 v, 2 w, 3 dmu [get only]; parts[i]: rows[i] x L float64, C-contiguous):
  * gather / scatter through the pinned double-buffered pipeline, so segment views are read and written in place. */

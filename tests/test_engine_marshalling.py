@@ -126,3 +126,57 @@ def test_row_ops_switch(ts, monkeypatch):
     assert ts.row_ops is False
     monkeypatch.setenv("VLGP_ALIASED_WINDOWS", "1")
     assert ts.row_ops is True
+
+
+def test_pinned_pool_recycles_blocks_with_their_last_view():
+    """engine.PinnedPool with malloc / free standing in for the page-locked allocator: an array handed out over a block
+    keeps the block out of the pool while ANY view of it lives, the block comes back afterwards and is reused, and a
+    closed pool frees instead of keeping."""
+    import gc
+
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+
+    class _Lib:
+        allocs, frees = [], []
+
+        def vlgp_host_alloc(self, pp, nbytes):
+            addr = libc.malloc(nbytes)
+            C.cast(pp, C.POINTER(C.c_void_p))[0] = addr
+            self.allocs.append(addr)
+            return 0
+
+        def vlgp_host_free(self, p):
+            self.frees.append(p.value)
+            libc.free(p)
+            return 0
+
+    lib = _Lib()
+    pool = E.PinnedPool(lib)
+    nbytes = 40 * 3 * 8
+    addr = pool.take(nbytes)
+    assert addr == lib.allocs[0]
+    a = pool.as_array(addr, nbytes, (40, 3))
+    a[...] = np.arange(120.0).reshape(40, 3)
+    views = list(a.reshape(4, 10, 3))
+    del a
+    gc.collect()
+    assert pool.free == {} or not pool.free.get(nbytes)          # views alive: the block is still out
+    assert views[3][9, 2] == 119.0
+    keep = views[1]
+    del views
+    gc.collect()
+    assert not pool.free.get(nbytes)
+    del keep
+    gc.collect()
+    assert pool.free[nbytes] == [addr]                           # back in the pool
+    assert pool.take(nbytes) == addr and len(lib.allocs) == 1    # reused, nothing new allocated
+    pool.give_back(addr, nbytes)
+    b = pool.as_array(pool.take(nbytes), nbytes, (40, 3))
+    pool.close()
+    assert lib.frees == []                                       # nothing idle to free ...
+    del b
+    gc.collect()
+    assert lib.frees == [addr]                                   # ... and a block returning to a closed pool is freed

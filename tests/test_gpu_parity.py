@@ -396,6 +396,26 @@ def test_estep_mstep_vs_oracle_seeded(vl, N, L, lik):
         assert np.max(np.abs(params[k] - p_ref[k])) < STEP_TOL * np.max(np.abs(p_ref[k[1]])), k
 
 
+@pytest.mark.parametrize("N,L,T,window", [(100, 5, 45, 15), (30, 3, 150, 50), (200, 10, 75, 25), (600, 2, 63, 21),
+                                          (7, 1, 33, 11)])
+def test_mstep_tma_staged_statistics_vs_oracle(vl, N, L, T, window):
+    """The TMA-staged statistics kernel of the middle Newton iterations (csrc/mstep.cu) on awkward geometries: odd
+    bin counts (a single bin left over at the end of the range), ranges shorter than one stage, one and many bin
+    lanes per CTA, more neurons than one CTA holds.  Reference: vlgp/core.py:129-249."""
+    from vlgp_b200 import core
+    from oracle import vlgp_oracle as orc
+
+    segs, params = _problem(23, 3, T, N, L, None, window=window)
+    cfg = _cfg(Eniter=2, Mniter=6)
+    s_ref, p_ref = copy.deepcopy(segs), copy.deepcopy(params)
+    orc.mstep(s_ref, p_ref, cfg)
+    core.mstep(segs, params, cfg)
+    for k in ("a", "b", "noise"):
+        assert relerr(params[k], p_ref[k]) < STEP_TOL, k
+    for k in ("da", "db"):
+        assert np.max(np.abs(params[k] - p_ref[k])) < STEP_TOL * np.max(np.abs(p_ref[k[1]])), k
+
+
 def test_estep_config2_shape_subset_vs_oracle(vl):
     """BASELINE config 2 shape (T=1000 trials cut in 50-bin windows, N=100, L=5): all 5120 segments run on the GPU; a
     random subset of 6 segments is checked against the oracle, and every segment against invariants."""
@@ -824,6 +844,56 @@ def test_overlapped_m_and_h_step_is_bit_identical(vl):
         ref_segs, ref_params = _problem(78, 2, 100, 8, 2)
         core.mstep(ref_segs, ref_params, _cfg(Mniter=3))
         assert np.array_equal(a_dev, ref_params["a"])
+
+
+def test_vem_download_through_prefetched_pinned_blocks(vl, monkeypatch):
+    """vem() starts the download of its result behind the last E-step; w and dmu arrive in page-locked blocks that become
+    the trial arrays (vlgp_trials_prefetch_state_into / _take).  Same values as the plain download, the reference's
+    aliasing (mu, v in place; w, dmu rebound: vlgp/core.py:117-120), blocks recycled once their arrays are gone, and a
+    prefetch made stale by a later write of the state is not used."""
+    import gc
+    from vlgp_b200 import core, engine
+    from vlgp_b200.gp import make_cholesky
+
+    pool = engine.get_engine().pinned
+    returned = []
+    monkeypatch.setattr(pool, "give_back", lambda addr, nbytes, _orig=pool.give_back: (returned.append(addr),
+                                                                                       _orig(addr, nbytes))[1])
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VLGP_PREFETCH", mode)
+        segs, params = _problem(91, 4, 150, 17, 3)
+        cfg = _cfg(max_iter=2, min_iter=2, Eniter=4, Mniter=4)
+        make_cholesky(segs, params, cfg)
+        mu_before = [s["mu"] for s in segs]
+        w_before = [s["w"] for s in segs]
+        core.vem(segs, params, cfg)
+        assert all(a is b for a, b in zip(mu_before, (s["mu"] for s in segs)))          # in place
+        assert not any(a is b for a, b in zip(w_before, (s["w"] for s in segs)))        # rebound
+        out[mode] = {k: np.stack([s[k] for s in segs]) for k in ("mu", "v", "w", "dmu")}
+        if mode == "1":
+            held = segs                                    # keeps the pinned-backed arrays alive
+            assert segs[0]["w"].flags.writeable and not segs[0]["w"].flags.owndata
+    for k in ("mu", "v", "w", "dmu"):
+        assert np.array_equal(out["1"][k], out["0"][k]), k
+    # the two blocks go back to the pool with their last view
+    assert returned == []
+    del held, segs
+    gc.collect()
+    assert len(returned) == 2 and returned[0] != returned[1]
+    # a stale prefetch is ignored: write the state after the prefetch, then pull
+    monkeypatch.setenv("VLGP_PREFETCH", "1")
+    segs, params = _problem(92, 2, 100, 9, 2)
+    cfg = _cfg(Eniter=3)
+    make_cholesky(segs, params, cfg)
+    with core.Session(segs, params) as s:
+        s.ts.estep(3)
+        s.ts.prefetch_state(direct=("w", "dmu"))
+        s.ts.estep(1)                                      # the state moves on
+        assert s.ts.take_prefetched("w") is None
+        s.pull(segs)
+        ref = s.ts.get_state(("w",))["w"]
+    assert np.array_equal(np.concatenate([sg["w"] for sg in segs]), ref)
 
 
 def test_errors_are_loud(vl):

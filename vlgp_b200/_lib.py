@@ -94,6 +94,11 @@ EXPORTS = {
     "vlgp_gpfa_stats": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "vlgp_set_precision": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_trials_prefetch_state": (C.c_int, [ctx_p, C.c_int, C.c_int]),
+    "vlgp_trials_prefetch_state_into": (C.c_int, [ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vlgp_trials_prefetch_take": (C.c_int, [ctx_p, C.c_int, C.c_int, c_int_p]),
+    "vlgp_trials_prefetch_wait": (C.c_int, [ctx_p, C.c_int]),
+    "vlgp_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "vlgp_host_free": (C.c_int, [C.c_void_p]),
     "vlgp_profile_enable": (C.c_int, [ctx_p, C.c_int]),
     "vlgp_profile_get": (C.c_int, [ctx_p, C.c_int, c_double_p, c_i64_p]),
 }

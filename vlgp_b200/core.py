@@ -246,7 +246,7 @@ class Session:
         ``rebind`` are rebound as well: constrain_loading="svd" REPLACES every trial["mu"] (vlgp/core.py:404-405), so
         from then on the segments' posterior means no longer reach the trials they were cut from."""
         L = self.eng.L
-        fresh = {}
+        fresh, landed = {}, {}
         for k in which:
             done = False
             if k in ("mu", "v") and k not in rebind:
@@ -256,9 +256,16 @@ class Session:
                 except (KeyError, TypeError, ValueError):
                     done = False
             if not done:
-                fresh[k] = np.empty((self.ts.nbin, L))
+                take = getattr(self.ts, "take_prefetched", None)
+                got = take(k) if take is not None else None       # the block a prefetch filled IS the new array
+                if got is not None:
+                    landed[k] = got
+                else:
+                    fresh[k] = np.empty((self.ts.nbin, L))
         if fresh:
             self.ts.get_state_parts(**{k: [a] for k, a in fresh.items()})
+        fresh.update(landed)
+        if fresh:
             for k, a in fresh.items():
                 views = _row_views(a, self.ts.starts, self.ts.lengths)
                 if k in ("mu", "v") and k not in rebind:
@@ -488,12 +495,12 @@ def _em_iteration(s: Session, trials, params, config, last=False):
             logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
     t1 = time.perf_counter()
     _constrain_latent_dev(s, params, config)
-    if last and os.environ.get("VLGP_PREFETCH") and hasattr(ts, "prefetch_state"):
-        # vem's last iteration: the posterior is final here (the M- and H-step only read it), so its download to the
-        # host can start now and run under them; the pull() that ends vem finds it in pinned memory.  Opt-in: measured
-        # on B200 it does not shorten vem() (33.9 vs 34.9 ms) -- the pull is bound by the host's first-touch page
-        # faults on the fresh w / dmu blocks it hands out, not by the transfer.
-        ts.prefetch_state()
+    if last and os.environ.get("VLGP_PREFETCH", "1") not in ("", "0") and hasattr(ts, "prefetch_state"):
+        # vem's last iteration: the posterior is final here (the M- and H-step only read it), so its download starts now
+        # on a copy stream and runs under them.  w and dmu -- keys the reference rebinds to new arrays -- land in
+        # page-locked blocks that pull() hands out as those arrays (no staging copy, no page faults of a fresh block);
+        # mu and v land in the context's staging area and are scattered into the caller's arrays by pull().
+        ts.prefetch_state(direct=("w", "dmu") + tuple(_rebound_keys(config)))
     if (config["Mniter"] >= 1 and config["Hstep"] and config.get("overlap_mh", True)
             and not os.environ.get("VLGP_NO_OVERLAP")):
         # The M-step (reads mu, v, y; writes a, b, noise) and the H-step (reads mu, w; writes sigma, omega) of one

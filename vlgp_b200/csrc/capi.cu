@@ -809,7 +809,8 @@ static int state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, void *
     if (!to_device && ctx->prefetch_set == set_id && ts->prefetch_version == ts->state_version &&
         (ts->prefetch_mask & (1 << which)) && ctx->h_prefetch) {
         CK(cudaEventSynchronize(ctx->ev_prefetch_done));
-        const double *src = (const double *)((unsigned char *)ctx->h_prefetch + (size_t)which * ts->nbin * ctx->L * sizeof(double));
+        const double *src = ts->prefetch_ext[which] ? ts->prefetch_ext[which] :
+            (const double *)((unsigned char *)ctx->h_prefetch + (size_t)which * ts->nbin * ctx->L * sizeof(double));
         return scatter_prefetched(ctx, src, n_parts, parts, off);
     }
     return pipeline_copy(ctx, dev, sizeof(double), n_parts, parts, off, to_device);
@@ -819,7 +820,7 @@ static int state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, void *
 // everything enqueued so far on the main stream.  A later vlgp_trials_get_state_parts of one of them is then served
 // from that copy -- provided no entry point has written the set's state in between (otherwise it is ignored).  vem()
 // issues this after the E-step of its last iteration: the transfer runs under the M- and H-step.
-int vlgp_trials_prefetch_state(vlgp_ctx *ctx, int set_id, int which_mask) {
+int vlgp_trials_prefetch_state_into(vlgp_ctx *ctx, int set_id, int which_mask, double *const *dst) {
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts && which_mask > 0 && which_mask < 16, "trials_prefetch_state: bad arguments");
     CK(cudaSetDevice(ctx->device));
@@ -840,15 +841,60 @@ int vlgp_trials_prefetch_state(vlgp_ctx *ctx, int set_id, int which_mask) {
     }
     CK(cudaEventRecord(ctx->ev_prefetch_go, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_prefetch_go, 0));
-    for (int k = 0; k < 4; ++k)
-        if (which_mask & (1 << k))
-            CK(cudaMemcpyAsync((unsigned char *)ctx->h_prefetch + k * bytes, state_array(ts, k), bytes, cudaMemcpyDeviceToHost,
-                               ctx->stream_copy));
+    for (int k = 0; k < 4; ++k) {
+        ts->prefetch_ext[k] = nullptr;
+        if (!(which_mask & (1 << k))) continue;
+        void *to = (unsigned char *)ctx->h_prefetch + k * bytes;
+        if (dst && dst[k]) to = ts->prefetch_ext[k] = dst[k];
+        CK(cudaMemcpyAsync(to, state_array(ts, k), bytes, cudaMemcpyDeviceToHost, ctx->stream_copy));
+    }
     CK(cudaEventRecord(ctx->ev_prefetch_done, ctx->stream_copy));
     ctx->prefetch_set = set_id;
     ts->prefetch_mask = which_mask;
     ts->prefetch_version = ts->state_version;
     return VLGP_OK;
+}
+
+int vlgp_trials_prefetch_state(vlgp_ctx *ctx, int set_id, int which_mask) {
+    return vlgp_trials_prefetch_state_into(ctx, set_id, which_mask, nullptr);
+}
+
+// Waits for the prefetch; *valid = 1 when array `which` was copied into the caller's own block (dst[which] of
+// vlgp_trials_prefetch_state_into) and the set's state has not been written since: the block then IS the download.
+int vlgp_trials_prefetch_take(vlgp_ctx *ctx, int set_id, int which, int *valid) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts && valid && which >= 0 && which < 4, "trials_prefetch_take: bad arguments");
+    *valid = 0;
+    if (ctx->prefetch_set != set_id || ts->prefetch_version != ts->state_version || !(ts->prefetch_mask & (1 << which)) ||
+        !ts->prefetch_ext[which])
+        return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_prefetch_done));
+    *valid = 1;
+    return VLGP_OK;
+}
+
+// Blocks until the set's prefetch (if any) has landed: its destination blocks may then be reused.
+int vlgp_trials_prefetch_wait(vlgp_ctx *ctx, int set_id) {
+    TrialSet *ts = get_set(ctx, set_id);
+    REQUIRE(ts, "trials_prefetch_wait: bad set %d", set_id);
+    if (ctx->prefetch_set != set_id || !ctx->ev_prefetch_done) return VLGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_prefetch_done));
+    for (int k = 0; k < 4; ++k) ts->prefetch_ext[k] = nullptr;
+    ts->prefetch_mask = 0;
+    return VLGP_OK;
+}
+
+// Page-locked host memory for blocks that a prefetch fills directly (the Python side hands them out as the arrays of
+// trial["w"] / trial["dmu"], vlgp_b200/engine.py::PinnedPool).
+int vlgp_host_alloc(void **p, size_t bytes) {
+    if (!p || bytes == 0) return VLGP_ERR_ARG;
+    return cudaHostAlloc(p, bytes, cudaHostAllocPortable) == cudaSuccess ? VLGP_OK : VLGP_ERR_CUDA;
+}
+
+int vlgp_host_free(void *p) {
+    return (!p || cudaFreeHost(p) == cudaSuccess) ? VLGP_OK : VLGP_ERR_CUDA;
 }
 
 int vlgp_trials_set_state_parts(vlgp_ctx *ctx, int set_id, int which, int n_parts, const double *const *parts,

@@ -70,6 +70,7 @@ struct TrialSet {
     // while no entry point has written the state since (state_version)
     uint64_t state_version = 0, prefetch_version = ~0ull;
     int prefetch_mask = 0;
+    double *prefetch_ext[4] = {nullptr, nullptr, nullptr, nullptr};   // caller-owned pinned destinations (or the context's area)
     int gen = 0;                       // generation of the slot: stale handles of freed sets are refused
 };
 

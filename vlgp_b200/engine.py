@@ -98,6 +98,7 @@ class Engine:
         self.world_size = 1
         self.rank_id = 0
         self.peer_memory = False
+        self.pinned = PinnedPool(self.lib)
 
     # -- plumbing ---------------------------------------------------------------------------------------------------
     def _ck(self, rc, what):
@@ -109,6 +110,7 @@ class Engine:
         if getattr(self, "ctx", None):
             self.lib.vlgp_destroy(self.ctx)
             self.ctx = None
+            self.pinned.close()
 
     def __del__(self):  # pragma: no cover
         try:
@@ -272,6 +274,56 @@ class Engine:
         return ms.value, n.value
 
 
+class PinnedPool:
+    """Page-locked host blocks that a state prefetch fills directly and that are then handed out AS the arrays of
+    trial["w"] / trial["dmu"] (the reference rebinds those keys to new arrays in every E-step, vlgp/core.py:117-120):
+    the download of those two arrays costs the host nothing -- no staging copy, no first-touch page faults of a fresh
+    np.empty block.  A block returns to the pool when the last NumPy view of it is garbage-collected (a finalizer on the
+    ctypes buffer every view has as its base), so a loop of vem() calls cycles through the same two or four blocks."""
+
+    MAX_KEPT = 8
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.free = {}              # nbytes -> [address, ...]
+        self.closed = False
+
+    def take(self, nbytes):
+        """Address of a page-locked block of ``nbytes`` bytes, or None when it cannot be had."""
+        lst = self.free.get(nbytes)
+        if lst:
+            return lst.pop()
+        p = C.c_void_p()
+        if self.lib.vlgp_host_alloc(C.byref(p), int(nbytes)) != 0 or not p.value:
+            return None
+        return p.value
+
+    def give_back(self, addr, nbytes):
+        lst = self.free.setdefault(nbytes, [])
+        if self.closed or sum(len(v) for v in self.free.values()) >= self.MAX_KEPT:
+            try:
+                self.lib.vlgp_host_free(C.c_void_p(addr))
+            except Exception:      # noqa: BLE001 -- interpreter shutdown
+                pass
+        else:
+            lst.append(addr)
+
+    def as_array(self, addr, nbytes, shape):
+        """float64 array over the block; the block goes back to the pool when the array and all its views are gone."""
+        import weakref
+
+        buf = (C.c_char * nbytes).from_address(addr)
+        weakref.finalize(buf, self.give_back, addr, nbytes)
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+    def close(self):
+        self.closed = True
+        for lst in self.free.values():
+            for addr in lst:
+                self.lib.vlgp_host_free(C.c_void_p(addr))
+        self.free = {}
+
+
 class TrialSet:
     """Device-resident copy of a list of trials (or segments): y, mu, v, w, dmu and the prior factors per length."""
 
@@ -290,11 +342,19 @@ class TrialSet:
         self.d2h_bytes = 0
         self.y_stored = None          # dtype code of y in HBM once uploaded (1 = uint8 counts, 0 = float64)
         self.general_x = False        # True once regressors other than the all-ones bias column were uploaded
+        self._pinned = {}             # key -> address of the page-locked block a prefetch is filling / has filled
 
     def free(self):
         if self.id is not None and self.eng.ctx:
-            self.eng._ck(self.eng.lib.vlgp_trials_free(self.eng.ctx, self.id), "trials_free")
+            self.eng._ck(self.eng.lib.vlgp_trials_free(self.eng.ctx, self.id), "trials_free")   # waits for a prefetch
         self.id = None
+        self._drop_pinned()
+
+    def _drop_pinned(self):
+        nbytes = self.nbin * self.eng.L * 8
+        for addr in self._pinned.values():
+            self.eng.pinned.give_back(addr, nbytes)
+        self._pinned = {}
 
     def __enter__(self):
         return self
@@ -546,12 +606,44 @@ class TrialSet:
         self.eng._ck(lib.vlgp_gpfa_stats(ctx, self.id, dptr(ztz), dptr(zty), dptr(yy)), "gpfa_stats")
         return ztz, zty, yy
 
-    def prefetch_state(self, which=("mu", "v", "w", "dmu")):
+    def prefetch_state(self, which=("mu", "v", "w", "dmu"), direct=()):
         """Start the device-to-host copy of the listed state arrays behind what is enqueued so far; a following
-        get_state_parts is served from it unless the state was written in between (include/vlgp_b200.h)."""
+        get_state_parts is served from it unless the state was written in between (include/vlgp_b200.h).  Arrays listed
+        in ``direct`` go straight into page-locked blocks of their own that ``take_prefetched`` turns into the result
+        arrays (no further host copy)."""
         lib, ctx = self._lib()
-        mask = sum(1 << ("mu", "v", "w", "dmu").index(k) for k in which)
-        self.eng._ck(lib.vlgp_trials_prefetch_state(ctx, self.id, int(mask)), "prefetch_state")
+        names = ("mu", "v", "w", "dmu")
+        mask = sum(1 << names.index(k) for k in which)
+        if self._pinned:                                   # an earlier prefetch of this set: wait for it, recycle
+            self.eng._ck(lib.vlgp_trials_prefetch_wait(ctx, self.id), "prefetch_wait")
+            self._drop_pinned()
+        nbytes = self.nbin * self.eng.L * 8
+        dst = (C.c_void_p * 4)()
+        for k in direct:
+            if k in which:
+                addr = self.eng.pinned.take(nbytes)
+                if addr is not None:
+                    self._pinned[k] = addr
+                    dst[names.index(k)] = addr
+        self.eng._ck(lib.vlgp_trials_prefetch_state_into(ctx, self.id, int(mask), dst), "prefetch_state")
+
+    def take_prefetched(self, key):
+        """(nbin, L) array over the page-locked block a prefetch filled with the CURRENT array ``key``, or None (no
+        such prefetch, or the state has been written since).  The caller owns the array; the block returns to the pool
+        with its last view."""
+        addr = self._pinned.get(key)
+        if addr is None or self.id is None:
+            return None
+        lib, ctx = self._lib()
+        valid = C.c_int()
+        self.eng._ck(lib.vlgp_trials_prefetch_take(ctx, self.id, ("mu", "v", "w", "dmu").index(key), C.byref(valid)),
+                     "prefetch_take")
+        if not valid.value:
+            return None
+        del self._pinned[key]
+        nbytes = self.nbin * self.eng.L * 8
+        self.d2h_bytes += nbytes
+        return self.eng.pinned.as_array(addr, nbytes, (self.nbin, self.eng.L))
 
     def posterior_cov(self, trial, latent, reg=1e-6):
         """(T, T) posterior covariance inv(inv(G G' + reg I) + diag(w)) of one latent of one member of the set."""
