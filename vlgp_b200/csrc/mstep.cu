@@ -216,13 +216,18 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_kernel(Msta
 constexpr int MT_STAGES = 4;
 constexpr int MT_ROUNDS = 8;             // bin pairs per thread per stage
 
-template <int LT>
+// MODE 0: middle iterations (no counts needed); 1: first iteration (adds the y-moments mu'y, sum y); 2: last iteration
+// (adds the noise moments sum e, sum e^2 of e = y - eta).  Modes 1 and 2 also stage the uint8 count tile of the chunk
+// (CB x N bytes, one more bulk copy per stage) and run for Gaussian channels too; they need all neurons in one CTA.
+template <int LT, int MODE>
 __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(MstatArgs p, int64_t per) {
     constexpr int NS = nstat_of(LT);
     extern __shared__ __align__(16) unsigned char mt_raw[];
     const int J = p.J, CB = 2 * J * MT_ROUNDS;
-    double *stage = (double *)mt_raw;                                  // MT_STAGES x [mu: CB x LT | v: CB x LT]
-    double *etab = stage + (size_t)MT_STAGES * 2 * CB * LT;            // 32
+    const size_t ybytes = MODE ? (((size_t)CB * p.N + 15) & ~(size_t)15) : 0;      // count tile of one stage
+    const size_t stage_doubles = (size_t)2 * CB * LT + ybytes / sizeof(double);
+    double *stage = (double *)mt_raw;                                  // MT_STAGES x [mu: CB x LT | v: CB x LT | y: CB x N u8]
+    double *etab = stage + (size_t)MT_STAGES * stage_doubles;          // 32
     uint64_t *bar = (uint64_t *)(etab + 32);                           // MT_STAGES
     double *red = (double *)mt_raw;                                    // after the loop: 2 x blockDim
     const int tid = threadIdx.x;
@@ -238,11 +243,13 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
         const int64_t t0 = b0 + (int64_t)c * CB;
         const int nb = (int)((b1 - t0 < CB) ? (b1 - t0) : CB);
         const unsigned bytes = (unsigned)(((size_t)nb * LT * sizeof(double) + 15) & ~(size_t)15);   // buffers are padded
-        double *dst = stage + (size_t)(c % MT_STAGES) * 2 * CB * LT;
+        const unsigned yb = MODE ? (unsigned)(((size_t)nb * p.N + 15) & ~(size_t)15) : 0u;
+        double *dst = stage + (size_t)(c % MT_STAGES) * stage_doubles;
         uint64_t *b = bar + (c % MT_STAGES);
-        mbar_expect_tx(b, 2 * bytes);
+        mbar_expect_tx(b, 2 * bytes + yb);
         tma_load_1d(dst, p.mu + t0 * LT, bytes, b);
         tma_load_1d(dst + (size_t)CB * LT, p.v + t0 * LT, bytes, b);
+        if (MODE) tma_load_1d(dst + (size_t)2 * CB * LT, (const uint8_t *)p.y + t0 * p.N, yb, b);
     };
     if (tid == 0) {
         for (int s = 0; s < MT_STAGES; ++s) mbar_init(bar + s, 1);
@@ -253,9 +260,11 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
     if (tid == 0)
         for (int c = 0; c < MT_STAGES && c < nchunk; ++c) issue(c);
 
-    double acc[NS];
+    double acc[NS], yacc[MODE == 1 ? LT + 1 : 1];
 #pragma unroll
     for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < (MODE == 1 ? LT + 1 : 1); ++s) yacc[s] = 0.0;
     double al[LT], a2h[LT];
     double bn = 0.0;
     bool pois = false;
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
         bn = p.b[n];
         pois = p.poisson[n] != 0;
     }
-    const bool work = active && pois;
+    const bool work = active && (pois || MODE != 0);
 
     // exp(min(x, 10)) of two arguments, chains interleaved, table in shared memory (bitwise trunc_exp2)
     auto exp2 = [&](double x0, double x1, double &e0, double &e1) {
@@ -317,14 +326,27 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
             acc[q - 1] = fma(rr, vv[l], acc[q - 1]);
         }
     };
-    auto lin_of = [&](const double *m, const double *vv) {
+    auto lin_of = [&](const double *m, const double *vv, double &eta) {
         double e = bn, h = 0.0;
 #pragma unroll
         for (int l = 0; l < LT; ++l) {
             e = fma(m[l], al[l], e);
             h = fma(vv[l], a2h[l], h);
         }
+        eta = e;
         return e + h;
+    };
+    auto moments = [&](const double *m, double yv, double eta) {       // modes 1 / 2 only
+        if (MODE == 1) {
+#pragma unroll
+            for (int l = 0; l < LT; ++l) yacc[l] = fma(m[l], yv, yacc[l]);
+            yacc[MODE == 1 ? LT : 0] += yv;
+        }
+        if (MODE == 2) {
+            const double e = yv - eta;
+            acc[NS - 2] += e;
+            acc[NS - 1] = fma(e, e, acc[NS - 1]);
+        }
     };
 
     for (int c = 0; c < nchunk; ++c) {
@@ -333,8 +355,9 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
         const int nb = (int)((b1 - t0 < CB) ? (b1 - t0) : CB);
         mbar_wait(bar + st, (unsigned)((c / MT_STAGES) & 1));
         if (work) {
-            const double *smu = stage + (size_t)st * 2 * CB * LT;
+            const double *smu = stage + (size_t)st * stage_doubles;
             const double *sv = smu + (size_t)CB * LT;
+            const uint8_t *sy = (const uint8_t *)(sv + (size_t)CB * LT);
             const int npair = nb >> 1;
 #pragma unroll 1
             for (int pr = j; pr < npair; pr += J) {
@@ -349,10 +372,17 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
                     vv[2 * q] = y.x;
                     vv[2 * q + 1] = y.y;
                 }
-                double r0, r1;
-                exp2(lin_of(m, vv), lin_of(m + LT, vv + LT), r0, r1);
-                accumulate(m, vv, r0);
-                accumulate(m + LT, vv + LT, r1);
+                double r0, r1, eta0, eta1;
+                const double x0 = lin_of(m, vv, eta0), x1 = lin_of(m + LT, vv + LT, eta1);
+                if (MODE) {
+                    moments(m, (double)sy[(size_t)(2 * pr) * p.N + n], eta0);
+                    moments(m + LT, (double)sy[(size_t)(2 * pr + 1) * p.N + n], eta1);
+                }
+                if (MODE == 0 || pois) {
+                    exp2(x0, x1, r0, r1);
+                    accumulate(m, vv, r0);
+                    accumulate(m + LT, vv + LT, r1);
+                }
             }
             if ((nb & 1) && (npair % J) == j) {       // odd bin at the very end of the bin range
                 double m[LT], vv[LT];
@@ -361,10 +391,13 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
                     m[l] = smu[(size_t)(nb - 1) * LT + l];
                     vv[l] = sv[(size_t)(nb - 1) * LT + l];
                 }
-                double r0, r1;
-                const double x = lin_of(m, vv);
-                exp2(x, x, r0, r1);
-                accumulate(m, vv, r0);
+                double r0, r1, eta0;
+                const double x = lin_of(m, vv, eta0);
+                if (MODE) moments(m, (double)sy[(size_t)(nb - 1) * p.N + n], eta0);
+                if (MODE == 0 || pois) {
+                    exp2(x, x, r0, r1);
+                    accumulate(m, vv, r0);
+                }
             }
         }
         __syncthreads();
@@ -373,14 +406,16 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
     // reduce over the J bin lanes of this CTA (as in mstep_stats_kernel); the stages are free now
     __syncthreads();
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NS + (MODE == 1 ? LT + 1 : 0); ++s) {
         double *buf = red + (s & 1) * blockDim.x;
-        buf[tid] = work ? acc[s] : 0.0;
+        const double val = s < NS ? acc[s < NS ? s : 0] : yacc[MODE == 1 ? (s >= NS ? s - NS : 0) : 0];
+        buf[tid] = work ? val : 0.0;
         __syncthreads();
         if (j == 0 && n < p.N) {
             double x = 0.0;
             for (int jj = 0; jj < J; ++jj) x += buf[jj * p.NC + nloc];
-            p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = x;
+            if (s < NS) p.part[((size_t)blockIdx.x * NS + s) * p.N + n] = x;
+            else p.ypart[((size_t)blockIdx.x * (LT + 1) + (s - NS)) * p.N + n] = x;
         }
     }
 }
@@ -658,7 +693,8 @@ struct MstepJob {
     bool general_x = false;
     TrialSet *ts = nullptr;
     size_t smem_tma = 0;         // mstep_stats_tma_kernel: dynamic shared memory (0: not usable for this shape)
-    int64_t per_tma = 0;         // its bins per CTA (even, so that every chunk starts on a 16-byte boundary)
+    size_t smem_tma_y = 0;       // the same for its first / last-iteration modes, which also stage the count tile
+    int64_t per_tma = 0;         // its bins per CTA (a multiple of 16, so that every chunk starts on a 16-byte boundary)
 };
 
 template <int LT>
@@ -741,16 +777,31 @@ int mstep_setup_t(vlgp_ctx *ctx, TrialSet *ts, MstepJob &job, int n_iter, int us
     job.n_iter = n_iter; job.next_it = 0;
     job.general_x = ts->d_x != nullptr;
     job.ts = ts;
-    {   // TMA-staged kernel for the iterations between the first and the last
+    {   // TMA-staged kernel
         const size_t cb = (size_t)2 * J * MT_ROUNDS;
-        const size_t ring = ((size_t)MT_STAGES * 2 * cb * LT + 32 + MT_STAGES) * sizeof(double);
         const size_t redb = 2 * (size_t)nt * sizeof(double);
-        job.smem_tma = ring > redb ? ring : redb;
-        job.per_tma = (((ts->nbin + gx - 1) / gx) + 1) & ~(int64_t)1;
-        if (job.smem_tma > (size_t)200 << 10 || getenv("VLGP_MSTEP_NO_TMA")) job.smem_tma = 0;
-        else if (job.smem_tma > (size_t)48 << 10)
-            CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        auto need = [&](size_t ybytes) {
+            const size_t ring = ((size_t)MT_STAGES * (2 * cb * LT + ybytes / sizeof(double)) + 32 + MT_STAGES) * sizeof(double);
+            return ring > redb ? ring : redb;
+        };
+        job.smem_tma = need(0);
+        job.smem_tma_y = need((cb * (size_t)N + 15) & ~(size_t)15);
+        job.per_tma = (((ts->nbin + gx - 1) / gx) + 15) & ~(int64_t)15;
+        const size_t cap = (size_t)200 << 10;
+        if (job.smem_tma > cap || getenv("VLGP_MSTEP_NO_TMA")) job.smem_tma = 0;
+        // the first / last-iteration modes read the counts: uint8 storage, all neurons in one CTA
+        if (!job.smem_tma || job.smem_tma_y > cap || nchunk != 1 || ts->ydtype != VLGP_Y_U8 || n_iter < 2 ||
+            getenv("VLGP_MSTEP_NO_TMA_Y"))
+            job.smem_tma_y = 0;
+        if (job.smem_tma > (size_t)48 << 10)
+            CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)job.smem_tma));
+        if (job.smem_tma_y > (size_t)48 << 10) {
+            CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)job.smem_tma_y));
+            CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)job.smem_tma_y));
+        }
     }
     return VLGP_OK;
 }
@@ -774,10 +825,14 @@ int mstep_iter_t(vlgp_ctx *ctx, MstepJob &job, int it) {
                 mstep_stats_kernel<LT, true, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
             else
                 mstep_stats_kernel<LT, false, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
+        } else if (it == 0 && job.smem_tma_y) {
+            mstep_stats_tma_kernel<LT, 1><<<job.grid, job.nt, job.smem_tma_y, ctx->stream>>>(sa, job.per_tma);
         } else if (it == 0) {
             mstep_stats_kernel<LT, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
         } else if (it < job.n_iter - 1 && job.smem_tma) {
-            mstep_stats_tma_kernel<LT><<<job.grid, job.nt, job.smem_tma, ctx->stream>>>(sa, job.per_tma);
+            mstep_stats_tma_kernel<LT, 0><<<job.grid, job.nt, job.smem_tma, ctx->stream>>>(sa, job.per_tma);
+        } else if (job.smem_tma_y) {
+            mstep_stats_tma_kernel<LT, 2><<<job.grid, job.nt, job.smem_tma_y, ctx->stream>>>(sa, job.per_tma);
         } else {
             mstep_stats_kernel<LT, false><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
         }
