@@ -521,7 +521,8 @@ def run_ours(args):
               "ms_total": h_ms, "launches_timed": h_n, "evaluations": h_evals, "dmma_per_segment_evaluation": dmma_per_seg}
     m_flops = float(S_local * W) * N * (10 * L + L * L + 20 + 4)
     m_bytes = float(S_local * W) * (N * 1 + 2 * L * 8)
-    roof_m = {"bound": "fp64", "kernel": "mstep_stats", "achieved": m_flops * m_n / (m_ms * 1e-3) / 1e12 if m_ms else None,
+    roof_m = {"bound": "fp64", "kernel": "mstep_stats_tma (TMA-staged (mu, v) rows / count tile; average over the Newton "
+              "iterations of one M-step)", "achieved": m_flops * m_n / (m_ms * 1e-3) / 1e12 if m_ms else None,
               "peak": peak, "unit": "TFLOP/s", "frac": (m_flops * m_n / (m_ms * 1e-3) / 1e12 / peak) if (m_ms and peak) else None,
               "ms_per_launch": m_ms / max(m_n, 1), "launches_timed": m_n,
               "hbm_view": {"algorithmic_GBps": m_bytes * m_n / (m_ms * 1e-3) / 1e9 if m_ms else None,

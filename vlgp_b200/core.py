@@ -495,11 +495,14 @@ def _em_iteration(s: Session, trials, params, config, last=False):
             logger.error("E-step: %d r x r systems were not positive definite (update skipped)", nfail)
     t1 = time.perf_counter()
     _constrain_latent_dev(s, params, config)
-    if last and os.environ.get("VLGP_PREFETCH", "1") not in ("", "0") and hasattr(ts, "prefetch_state"):
-        # vem's last iteration: the posterior is final here (the M- and H-step only read it), so its download starts now
-        # on a copy stream and runs under them.  w and dmu -- keys the reference rebinds to new arrays -- land in
+    if last and os.environ.get("VLGP_PREFETCH", "0") not in ("", "0") and hasattr(ts, "prefetch_state"):
+        # vem's last iteration: the posterior is final here (the M- and H-step only read it), so its download can start
+        # now on a copy stream and run under them.  w and dmu -- keys the reference rebinds to new arrays -- land in
         # page-locked blocks that pull() hands out as those arrays (no staging copy, no page faults of a fresh block);
         # mu and v land in the context's staging area and are scattered into the caller's arrays by pull().
+        # Opt-in (VLGP_PREFETCH=1): measured on B200 boxes it saves 0.8 ms per vem() call (34.6 -> 33.8 ms) once the
+        # page-locked blocks exist, but page-locking them (60 MB at config 2) costs ~235 ms the first time -- a loss for
+        # a single fit(), a gain only for a loop of hundreds of vem() calls.
         ts.prefetch_state(direct=("w", "dmu") + tuple(_rebound_keys(config)))
     if (config["Mniter"] >= 1 and config["Hstep"] and config.get("overlap_mh", True)
             and not os.environ.get("VLGP_NO_OVERLAP")):
