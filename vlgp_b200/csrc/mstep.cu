@@ -219,7 +219,7 @@ constexpr int MT_ROUNDS = 8;             // bin pairs per thread per stage
 // MODE 0: middle iterations (no counts needed); 1: first iteration (adds the y-moments mu'y, sum y); 2: last iteration
 // (adds the noise moments sum e, sum e^2 of e = y - eta).  Modes 1 and 2 also stage the uint8 count tile of the chunk
 // (CB x N bytes, one more bulk copy per stage) and run for Gaussian channels too; they need all neurons in one CTA.
-template <int LT, int MODE, bool ESTRIN = false>
+template <int LT, int MODE>
 __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(MstatArgs p, int64_t per) {
     constexpr int NS = nstat_of(LT);
     extern __shared__ __align__(16) unsigned char mt_raw[];
@@ -293,28 +293,15 @@ __global__ void __launch_bounds__((LT <= 5) ? 512 : 256) mstep_stats_tma_kernel(
         double r0 = fma(t0, -VLGP_EXP_HI, x0), r1 = fma(t1, -VLGP_EXP_HI, x1);
         r0 = fma(t0, -VLGP_EXP_LO, r0);
         r1 = fma(t1, -VLGP_EXP_LO, r1);
-        double q0, q1;
-        if (ESTRIN) {      // same polynomial, evaluated as (a r^2 + b) r^2 + c: dependent chain of 4 instead of 7
-            const double s0 = r0 * r0, s1 = r1 * r1;
-            const double a0 = fma(VLGP_EXP_C[0], r0, VLGP_EXP_C[1]), a1 = fma(VLGP_EXP_C[0], r1, VLGP_EXP_C[1]);
-            const double b0_ = fma(VLGP_EXP_C[2], r0, VLGP_EXP_C[3]), b1_ = fma(VLGP_EXP_C[2], r1, VLGP_EXP_C[3]);
-            const double c0 = fma(VLGP_EXP_C[4], r0, VLGP_EXP_C[5]), c1 = fma(VLGP_EXP_C[4], r1, VLGP_EXP_C[5]);
-            const double tr0 = tj0 * r0, tr1 = tj1 * r1;
-            const double u0 = fma(fma(a0, s0, b0_), s0, c0), u1 = fma(fma(a1, s1, b1_), s1, c1);
-            q0 = fma(tr0, u0, tj0);
-            q1 = fma(tr1, u1, tj1);
-        } else {
-            double p0 = VLGP_EXP_C[0], p1 = VLGP_EXP_C[0];
+        double p0 = VLGP_EXP_C[0], p1 = VLGP_EXP_C[0];
 #pragma unroll
-            for (int k = 1; k < 6; ++k) {
-                p0 = fma(p0, r0, VLGP_EXP_C[k]);
-                p1 = fma(p1, r1, VLGP_EXP_C[k]);
-            }
-            p0 *= r0;
-            p1 *= r1;
-            q0 = fma(tj0, p0, tj0);
-            q1 = fma(tj1, p1, tj1);
+        for (int k = 1; k < 6; ++k) {
+            p0 = fma(p0, r0, VLGP_EXP_C[k]);
+            p1 = fma(p1, r1, VLGP_EXP_C[k]);
         }
+        p0 *= r0;
+        p1 *= r1;
+        const double q0 = fma(tj0, p0, tj0), q1 = fma(tj1, p1, tj1);
         const int ex0 = max(i0 >> 5, -1022), ex1 = max(i1 >> 5, -1022);
         e0 = __hiloint2double(__double2hiint(q0) + (ex0 << 20), __double2loint(q0));
         e1 = __hiloint2double(__double2hiint(q1) + (ex1 << 20), __double2loint(q1));
@@ -807,12 +794,8 @@ int mstep_setup_t(vlgp_ctx *ctx, TrialSet *ts, MstepJob &job, int n_iter, int us
             getenv("VLGP_MSTEP_NO_TMA_Y"))
             job.smem_tma_y = 0;
         if (job.smem_tma > (size_t)48 << 10)
-        {
             CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)job.smem_tma));
-            CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)job.smem_tma));
-        }
         if (job.smem_tma_y > (size_t)48 << 10) {
             CK(cudaFuncSetAttribute(mstep_stats_tma_kernel<LT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)job.smem_tma_y));
@@ -847,9 +830,7 @@ int mstep_iter_t(vlgp_ctx *ctx, MstepJob &job, int it) {
         } else if (it == 0) {
             mstep_stats_kernel<LT, true><<<job.grid, job.nt, job.smem, ctx->stream>>>(sa);
         } else if (it < job.n_iter - 1 && job.smem_tma) {
-            static const bool estrin = getenv("VLGP_MSTEP_ESTRIN") != nullptr;      // experiment
-            if (estrin) mstep_stats_tma_kernel<LT, 0, true><<<job.grid, job.nt, job.smem_tma, ctx->stream>>>(sa, job.per_tma);
-            else mstep_stats_tma_kernel<LT, 0><<<job.grid, job.nt, job.smem_tma, ctx->stream>>>(sa, job.per_tma);
+            mstep_stats_tma_kernel<LT, 0><<<job.grid, job.nt, job.smem_tma, ctx->stream>>>(sa, job.per_tma);
         } else if (job.smem_tma_y) {
             mstep_stats_tma_kernel<LT, 2><<<job.grid, job.nt, job.smem_tma_y, ctx->stream>>>(sa, job.per_tma);
         } else {
