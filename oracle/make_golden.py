@@ -225,7 +225,13 @@ def golden_fit(ref):
     trials = make_trials(10, 200, 30, 3, seed=0)
     out["y"] = np.stack([t["y"] for t in trials]).astype(np.uint8)
     np.random.seed(0)
-    res = ref.fit(trials, 3, max_iter=3, min_iter=3)
+    traj = {"omega": [], "sigma": []}
+
+    def record(trials_, params_, config_):      # vem calls this after every H-step (vlgp/core.py:339-343)
+        traj["omega"].append(np.array(params_["omega"], dtype=float))
+        traj["sigma"].append(np.array(params_["sigma"], dtype=float))
+
+    res = ref.fit(trials, 3, max_iter=3, min_iter=3, callbacks=[record])
     out["mu"] = np.stack([t["mu"] for t in res["trials"]])
     out["v"] = np.stack([t["v"] for t in res["trials"]])
     out["w"] = np.stack([t["w"] for t in res["trials"]])
@@ -233,6 +239,10 @@ def golden_fit(ref):
         out[k] = np.array(res["params"][k])
     for k in ("a", "b", "omega"):
         out["initial_" + k] = np.array(res["params"]["initial"][k])
+    # omega / sigma as the reference's H-step left them after each EM iteration: lets a test run the default fit with
+    # this trajectory injected, so that everything around the optimiser is compared without the pivot-tie sensitivity
+    out["omega_traj"] = np.stack(traj["omega"])
+    out["sigma_traj"] = np.stack(traj["sigma"])
     np.savez_compressed(os.path.join(OUT, "fit_tutorial.npz"), **out)
     print("fit_tutorial.npz", len(out))
 

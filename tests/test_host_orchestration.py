@@ -63,6 +63,28 @@ def test_fit_with_hstep_matches_the_reference(monkeypatch):
     assert len(res["config"]["hstep_nfev"]) == 3 and all(len(x) == 3 for x in res["config"]["hstep_nfev"])
 
 
+def test_default_fit_with_the_reference_omega_trajectory(monkeypatch):
+    """The DEFAULT fit (H-step on) with the reference's omega of every iteration injected in place of the optimiser's:
+    the host code's handling of everything around it (factors rebuilt from the new omega, M-step overlapped with the
+    H-step, final inference with the final factors) equals the reference to rounding."""
+    import vlgp_b200 as vlgp
+    from conftest import inject_hyperparameter_trajectory
+    from vlgp_b200.synth import make_trials
+
+    install(monkeypatch)
+    g = load_golden("fit_tutorial")
+    state = inject_hyperparameter_trajectory(monkeypatch, g["omega_traj"], g["sigma_traj"])
+    trials = make_trials(10, 200, 30, 3, seed=0)
+    np.random.seed(0)
+    res = vlgp.fit(trials, 3, max_iter=3, min_iter=3)
+    assert state["it"] == 3
+    assert np.array_equal(res["params"]["omega"], g["omega"])
+    for k in ("a", "b", "noise"):
+        assert relerr(res["params"][k], g[k]) < 1e-9, k
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([t[k] for t in res["trials"]]), g[k]) < 1e-9, k
+
+
 def test_vem_aliasing_callbacks_and_sequential_order(monkeypatch):
     from vlgp_b200 import core, preprocess
     from vlgp_b200.gp import make_cholesky
