@@ -247,6 +247,29 @@ def golden_fit(ref):
     print("fit_tutorial.npz", len(out))
 
 
+def golden_fit_wide_window(ref):
+    """fit() with window=100 (the H-step's wide path, csrc/hstep_wide.cu): outputs and the omega of every iteration."""
+    out = {}
+    trials = make_trials(4, 200, 12, 2, seed=5)
+    out["y"] = np.stack([t["y"] for t in trials]).astype(np.uint8)
+    np.random.seed(0)
+    traj = {"omega": [], "sigma": []}
+
+    def record(trials_, params_, config_):
+        traj["omega"].append(np.array(params_["omega"], dtype=float))
+        traj["sigma"].append(np.array(params_["sigma"], dtype=float))
+
+    res = ref.fit(trials, 2, window=100, max_iter=3, min_iter=3, callbacks=[record])
+    for k in ("mu", "v", "w"):
+        out[k] = np.stack([t[k] for t in res["trials"]])
+    for k in ("a", "b", "noise", "omega", "sigma"):
+        out[k] = np.array(res["params"][k])
+    out["omega_traj"] = np.stack(traj["omega"])
+    out["sigma_traj"] = np.stack(traj["sigma"])
+    np.savez_compressed(os.path.join(OUT, "fit_wide_window.npz"), **out)
+    print("fit_wide_window.npz", len(out))
+
+
 def golden_fit_fixed_omega(ref):
     """fit() with Hstep=False: omega stays at its initial value, so the prior factors (and their pivot sets) are the
     same on both sides and the whole chain initialise -> update_w/v -> cut -> vem -> infer can be compared tightly."""
@@ -465,7 +488,7 @@ def main():
     import vlgp.preprocess, vlgp.core, vlgp.gp, vlgp.math, vlgp.util  # noqa: F401,E401
     only = sys.argv[1:]
     for fn in (golden_ichol, golden_estep, golden_mstep, golden_hstep, golden_update_wv, golden_vem, golden_fit,
-               golden_fit_fixed_omega, golden_vem_options, golden_api_extras,
+               golden_fit_fixed_omega, golden_fit_wide_window, golden_vem_options, golden_api_extras,
                golden_fit_options, golden_fit_overlap, golden_vem_regressors, golden_gpfa):
         if not only or fn.__name__.replace("golden_", "") in only:
             fn(ref)

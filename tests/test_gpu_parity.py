@@ -168,6 +168,61 @@ def test_hstep_whole_golden(vl):
     assert relerr(Gd @ Gd.transpose(0, 2, 1), g["G_after"] @ g["G_after"].transpose(0, 2, 1)) < 1e-5
 
 
+@pytest.mark.parametrize("W", [72, 100, 131])
+def test_hstep_objective_wide_window_vs_oracle(vl, W):
+    """Windows of more than 64 bins (the reference takes any window, vlgp/gp.py:65-123): the shared-memory kernels of
+    csrc/hstep_wide.cu against the oracle's literal restatement of gp.elbo / construct_posterior_cov."""
+    from vlgp_b200.core import Session
+    from oracle import vlgp_oracle as orc
+
+    rng = np.random.default_rng(W)
+    S, L = 5, 2
+    t = np.arange(W, dtype=float)
+    mu = np.stack([np.stack([np.sin(2 * np.pi * (l + 1) * t / 60 + rng.uniform(0, 6)) for l in range(L)], axis=1)
+                   + 0.1 * rng.standard_normal((W, L)) for _ in range(S)])
+    w = rng.uniform(0.05, 3.0, size=(S, W, L))
+    segs = [dict(y=np.zeros((W, 2)), mu=mu[i].copy(), w=w[i].copy(), v=np.zeros((W, L))) for i in range(S)]
+    params = dict(a=np.zeros((L, 2)), b=np.zeros((1, 2)), noise=np.ones(2), omega=np.full(L, 1e-2), sigma=np.ones(L),
+                  likelihood=np.array(["poisson"] * 2), zdim=L, ydim=2, xdim=1, rank=50, gp_noise=1e-4, dt=1)
+    with Session(segs, params, upload_factors=False) as s:
+        s.ts.hstep_prepare()
+        for l in range(L):
+            for om in (2e-3, 1e-2, 4e-2):
+                hyper = np.array([1.0, om, 1e-4])
+                ll, dll, info = s.ts.hstep_objective(l, hyper)
+                f, g = orc.hstep_objective(np.log(hyper), t, mu[:, :, l].T, w[:, :, l].T)
+                assert info == 0
+                assert abs(ll + f) < 1e-9 * abs(f), (W, l, om)
+                assert abs(dll + g[1]) < 1e-7 * max(abs(g[1]), 1.0), (W, l, om)
+
+
+def test_fit_wide_window_golden(vl, monkeypatch):
+    """fit(..., window=100) -- refused before this round -- against the reference.  Free-running: omega itself at 1e-5
+    (the optimiser's sensitivity, as in test_fit_tutorial_golden).  With the reference's omega of every iteration
+    injected AND the oracle's prior factors (at these omega the device's incomplete Cholesky breaks an exact pivot tie
+    the other way, which alone moves mu by 5e-3): everything at 1e-7."""
+    from conftest import inject_hyperparameter_trajectory, use_oracle_prior_factors
+    from vlgp_b200.synth import make_trials
+
+    g = load_golden("fit_wide_window")
+    trials = make_trials(4, 200, 12, 2, seed=5)
+    assert np.array_equal(np.stack([t["y"] for t in trials]), g["y"])
+    np.random.seed(0)
+    res = vl.fit(trials, 2, window=100, max_iter=3, min_iter=3)
+    assert relerr(res["params"]["omega"], g["omega"]) < 1e-5
+    assert relerr(np.stack([t["mu"] for t in res["trials"]]), g["mu"]) < 5e-4
+    state = inject_hyperparameter_trajectory(monkeypatch, g["omega_traj"], g["sigma_traj"])
+    use_oracle_prior_factors(monkeypatch)
+    trials = make_trials(4, 200, 12, 2, seed=5)
+    np.random.seed(0)
+    res = vl.fit(trials, 2, window=100, max_iter=3, min_iter=3)
+    assert state["it"] == 3
+    for k in ("mu", "v", "w"):
+        assert relerr(np.stack([t[k] for t in res["trials"]]), g[k]) < 1e-7, k
+    for k in ("a", "b", "noise"):
+        assert relerr(res["params"][k], g[k]) < 1e-7, k
+
+
 def test_hstep_native_optimizer_against_scipy_on_the_device_objective(vl, monkeypatch):
     """vlgp_hstep_optimize (all L-BFGS-B rounds inside one native call, csrc/hstep_opt.cu) against scipy's own setulb
     driven from Python (VLGP_HSTEP_SCIPY=1) on the SAME device objective: without the collapse rule the two must ask

@@ -34,9 +34,9 @@ def fit(trials, n_factors, **kwargs):
     kwargs["omega_bound"] = config["omega_bound"]
     params = get_params(trials, n_factors, **kwargs)
     # limits of the device kernels, checked before any work is done (the reference has none of them)
-    if config["Hstep"] and config["window"] and int(config["window"]) > 64 and config["max_iter"] > 0:
-        raise ValueError("window=%d with Hstep=True: the H-step kernels hold a window of at most 64 bins "
-                         "(pass Hstep=False or a window <= 64)" % int(config["window"]))
+    if config["Hstep"] and config["window"] and int(config["window"]) > 160 and config["max_iter"] > 0:
+        raise ValueError("window=%d with Hstep=True: the H-step kernels hold a window of at most 160 bins "
+                         "(pass Hstep=False or a window <= 160)" % int(config["window"]))
     if int(params["zdim"]) > 12:
         raise ValueError("n_factors=%d: the device kernels are instantiated for at most 12 latents" % int(params["zdim"]))
 

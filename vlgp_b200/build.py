@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libvlgp_b200.so")
-SOURCES = ["capi.cu", "hostpack.cpp", "comm.cu", "shmcomm.cu", "ichol.cu", "estep.cu", "estep_long.cu", "estep_seg.cu", "estep_seg_v_fast.cu", "estep_seg_v_gen.cu", "estep_seg_v_big.cu", "estep_seg_v_bigfast.cu", "estep_seg_v_fast32.cu", "estep_seg_v_bigfast32.cu", "mstep.cu", "hstep.cu", "hstep_dmma.cu", "hstep_opt.cu", "p2p.cu", "regress.cu", "postcov.cu", "gpfa.cu"]
+SOURCES = ["capi.cu", "hostpack.cpp", "comm.cu", "shmcomm.cu", "ichol.cu", "estep.cu", "estep_long.cu", "estep_seg.cu", "estep_seg_v_fast.cu", "estep_seg_v_gen.cu", "estep_seg_v_big.cu", "estep_seg_v_bigfast.cu", "estep_seg_v_fast32.cu", "estep_seg_v_bigfast32.cu", "mstep.cu", "hstep.cu", "hstep_dmma.cu", "hstep_wide.cu", "hstep_opt.cu", "p2p.cu", "regress.cu", "postcov.cu", "gpfa.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

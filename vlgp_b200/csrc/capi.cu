@@ -1254,7 +1254,7 @@ int vlgp_hstep_prepare(vlgp_ctx *ctx, int set_id) {
     TrialSet *ts = get_set(ctx, set_id);
     REQUIRE(ts, "hstep_prepare: bad set %d", set_id);
     REQUIRE(ts->min_len == ts->max_len, "hstep_prepare: all segments must have the same length (vlgp/gp.py:77-80)");
-    REQUIRE(ts->max_len <= VLGP_MAX_W, "hstep_prepare: window %d > %d", ts->max_len, VLGP_MAX_W);
+    REQUIRE(ts->max_len <= VLGP_MAX_W_H, "hstep_prepare: window %d > %d", ts->max_len, VLGP_MAX_W_H);
     CK(cudaSetDevice(ctx->device));
     return vlgp_launch_hstep_prepare(ctx, ts);
 }

@@ -13,6 +13,7 @@
 #define VLGP_MAX_RANK 64     // rank of the prior factor (reference hard-codes 50, vlgp/preprocess.py:75)
 #define VLGP_MAX_XDIM 8      // regressors per neuron (xdim = max(history, 1), vlgp/preprocess.py:59)
 #define VLGP_MAX_W 64        // window length handled by the SMEM-resident segment kernels (reference default 50)
+#define VLGP_MAX_W_H 160     // window length of the H-step's wide path (hstep_wide.cu: one W x W matrix in shared memory)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // HBM layout of one trial set (SURVEY.md section 7 "data model"): all bins concatenated, time-major.

@@ -18,6 +18,8 @@
 #include "p2p.cuh"
 
 int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb, bool *handled);   // hstep_dmma.cu
+int vlgp_launch_hstep_moments_wide(vlgp_ctx *ctx, TrialSet *ts, int chunks, double *part);                // hstep_wide.cu
+int vlgp_launch_hstep_wide(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb);                            // hstep_wide.cu
 
 namespace {
 
@@ -258,8 +260,13 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
     if (!ts->d_K) CK(vlgp_dalloc(ctx, &ts->d_K, (size_t)VLGP_MAX_L * 2 * WW * sizeof(double)));
     if (!ts->d_hpart) CK(vlgp_dalloc(ctx, &ts->d_hpart, (size_t)VLGP_MAX_L * 2 * S * sizeof(double)));
     if (!ts->d_hout) CK(vlgp_dalloc(ctx, &ts->d_hout, (size_t)VLGP_MAX_L * 10 * sizeof(double)));
-    hstep_moment_kernel<<<dim3(chunks, L), NT, 0, ctx->stream>>>(S, W, L, ts->d_mu, part);
-    CKL();
+    if (W > VLGP_MAX_W) {              // wide window: shared-memory kernels of hstep_wide.cu
+        int rcw = vlgp_launch_hstep_moments_wide(ctx, ts, chunks, part);
+        if (rcw) return rcw;
+    } else {
+        hstep_moment_kernel<<<dim3(chunks, L), NT, 0, ctx->stream>>>(S, W, L, ts->d_mu, part);
+        CKL();
+    }
     reduce_parts_kernel2<<<(L * WW + 127) / 128, 128, 0, ctx->stream>>>(part, chunks, L * WW, ts->d_M);
     CKL();
     int rc = vlgp_allreduce_dev(ctx, ts->d_M, (size_t)L * WW, 0);
@@ -279,7 +286,7 @@ int vlgp_launch_hstep_prepare(vlgp_ctx *ctx, TrialSet *ts) {
         if (rc) return rc;
     }
     ts->h_nseg_total = nseg_all;
-    if (!ts->h_geometry) {
+    if (!ts->h_geometry && W <= VLGP_MAX_W) {
         // launch geometry of the per-segment fallback kernel (the DMMA kernel sizes its own grid), once per set
         int per_sm = 1;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_kernel, NT, 0));
@@ -302,7 +309,11 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
     // The K^-1 terms (one CTA per evaluation, latency-bound) run on a second stream concurrently with the per-segment
     // kernel; the DMMA kernel builds K itself, only the W > 56 fallback reads the K written by the global kernel.
     const bool dmma_ok = ts->max_len <= 56 && !getenv("VLGP_FORCE_SWEEP_HSTEP");
-    if (dmma_ok) {
+    const bool wide = W > VLGP_MAX_W;
+    if (wide) {
+        int rcw = vlgp_launch_hstep_wide(ctx, ts, eb);
+        if (rcw) return rcw;
+    } else if (dmma_ok) {
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
         hstep_global_kernel<<<n, NT, smem_g, ctx->stream2>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout, 0);
@@ -312,7 +323,7 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
         hstep_global_kernel<<<n, NT, smem_g, ctx->stream>>>(eb, W, ctx->dt, ts->d_M, ts->d_K, ts->d_hout, 1);
         CKL();
     }
-    {
+    if (!wide) {
         ProfScope ps(ctx, 2);
         bool handled = false;
         int rcd = vlgp_launch_hstep_segments_dmma(ctx, ts, eb, &handled);
@@ -323,7 +334,7 @@ int vlgp_launch_hstep_objective(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &e
             CKL();
         }
     }
-    if (dmma_ok) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (dmma_ok && !wide) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     // (tr, pd) sums over ranks: inside the final kernel through peer memory when enabled; else on the host through
     // shared memory when attached (they are consumed there), else NCCL
     const bool p2p = ctx->n_ranks > 1 && vlgp_p2p_enabled(ctx);

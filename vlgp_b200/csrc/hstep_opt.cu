@@ -83,7 +83,7 @@ VLGP_API int vlgp_hstep_optimize(vlgp_ctx *ctx, int set_id, int n_lat, const int
     REQUIRE(n_lat >= 1 && n_lat <= VLGP_MAX_L && latents && log_initial && log_bounds && mask && log_result,
             "hstep_optimize: bad arguments");
     REQUIRE(ts->min_len == ts->max_len, "hstep_optimize: all segments must have the same length (vlgp/gp.py:77-80)");
-    REQUIRE(ts->max_len <= VLGP_MAX_W, "hstep_optimize: window %d > %d", ts->max_len, VLGP_MAX_W);
+    REQUIRE(ts->max_len <= VLGP_MAX_W_H, "hstep_optimize: window %d > %d", ts->max_len, VLGP_MAX_W_H);
     for (int k = 0; k < n_lat; ++k)
         REQUIRE(latents[k] >= 0 && latents[k] < ctx->L, "hstep_optimize: latent %d out of range", latents[k]);
     CK(cudaSetDevice(ctx->device));
