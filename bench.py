@@ -507,13 +507,15 @@ def run_ours(args):
     # secondary rooflines: the H-step per-segment kernel runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64), the M-step
     # statistics kernel on the FP64 pipe; neither is HBM-bound (their GB/s are listed for completeness)
     nb = (W + 7) // 8
+    if 1 <= W - 8 * (nb - 1) <= 2 and 3 <= nb <= 7 and not os.environ.get("VLGP_HSTEP_NO_SCHUR"):
+        nb -= 1                                                    # bordered kernel: the sweep runs on the 8 (nb - 1) core rows
     dmma_per_seg = ((nb - 1) + (nb - 1) * nb // 2) * nb * 2      # per pivot block: nb-1 panel + nb(nb-1)/2 update tile products
     h_flops = 2.0 * 256.0 * dmma_per_seg * S_local * max(h_evals, 1)
     # useful work of one segment-evaluation: the W x W symmetric inverse (W^3 flops) plus d K d, the trace and the dK
     # contraction (4 W^2); the DMMA count above also multiplies the padding of W up to a multiple of 8
     h_useful = (float(W) ** 3 + 4.0 * W * W) * S_local * max(h_evals, 1)
     h_peak = peaks.get("dmma_tflops")
-    roof_h = {"bound": "tensor", "kernel": "hstep_segment_dmma (FP64 tensor pipe, DMMA)",
+    roof_h = {"bound": "tensor", "kernel": "hstep_segment_schur / hstep_segment_dmma (FP64 tensor pipe, DMMA)",
               "achieved": h_useful / (h_ms * 1e-3) / 1e12 if h_ms else None, "peak": h_peak,
               "unit": "TFLOP/s", "frac": (h_useful / (h_ms * 1e-3) / 1e12 / h_peak) if (h_ms and h_peak) else None,
               "flops": "useful: W^3 + 4 W^2 per segment-evaluation (symmetric inverse, d K d, trace, dK contraction)",

@@ -168,10 +168,12 @@ def test_hstep_whole_golden(vl):
     assert relerr(Gd @ Gd.transpose(0, 2, 1), g["G_after"] @ g["G_after"].transpose(0, 2, 1)) < 1e-5
 
 
-@pytest.mark.parametrize("W", [72, 100, 131])
-def test_hstep_objective_wide_window_vs_oracle(vl, W):
-    """Windows of more than 64 bins (the reference takes any window, vlgp/gp.py:65-123): the shared-memory kernels of
-    csrc/hstep_wide.cu against the oracle's literal restatement of gp.elbo / construct_posterior_cov."""
+@pytest.mark.parametrize("W", [17, 18, 26, 33, 40, 42, 49, 50, 56, 57, 64, 72, 100, 131])
+def test_hstep_objective_window_lengths_vs_oracle(vl, W):
+    """The H-step objective over window lengths that select every per-segment kernel: the bordered DMMA kernel (one or
+    two bins beyond a multiple of 8: 17, 18, 26, 33, 42, 49, 50), the plain DMMA kernel (40, 56), the register sweep
+    (57, 64) and the shared-memory kernels of csrc/hstep_wide.cu for windows of more than 64 bins (the reference takes
+    any window, vlgp/gp.py:65-123) -- against the oracle's literal restatement of gp.elbo / construct_posterior_cov."""
     from vlgp_b200.core import Session
     from oracle import vlgp_oracle as orc
 

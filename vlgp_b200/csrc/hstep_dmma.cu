@@ -174,6 +174,197 @@ __global__ void __launch_bounds__(WARPS * 32) hstep_segment_dmma_kernel(HEvalBat
     }
 }
 
+// Bordered variant for windows with one or two bins beyond a multiple of 8 (W = 50 = 6 x 8 + 2, the reference's default):
+// the q = W - 8 NBC border rows are eliminated FIRST, in scalar code, so that the blocked sweep runs on NBC = NB - 1 block
+// rows (240 instead of 351 DMMA at W = 50) and none of its tiles is padding.  With B = [[B11, B12], [B21, B22]]
+// (B22: 2 x 2, identity-padded when q = 1), X = B12 B22^-1 and the Schur complement S = B11 - X B21:
+//     B^-1 = [[S^-1, -S^-1 X], [-X' S^-1, B22^-1 + X' S^-1 X]],
+// and both outputs are ELEMENT-WISE sums over the tiles of S^-1 (no product with the border is formed):
+//     tr(B^-1)      = <S^-1, I + X X'> + tr(B22^-1)
+//     tr(B^-1 C)    = <S^-1, C11 - X C21 - C12 X' + X C22 X'> + tr(B22^-1 C22),      C = d dK d.
+// Per segment the warp builds seven 8 NBC-vectors in shared memory (u, v = the border columns of B; x1, x2 = columns of
+// X; and G, H = rows of C21 minus half of C22 X') and the tile loops read them by row / column index.
+template <int NBC>
+__global__ void __launch_bounds__(WARPS * 32) hstep_segment_schur_kernel(HEvalBatch eb, int nseg, int W, int L, double dt,
+                                                                         const double *__restrict__ w,
+                                                                         double *__restrict__ partall) {
+    const int ev = blockIdx.y, l = eb.latent[ev];
+    const double sigmasq = eb.sigmasq[ev], omega = eb.omega[ev], eps = eb.eps[ev];
+    double *part = partall + (size_t)ev * 2 * nseg;
+    constexpr int NT = NBC * (NBC + 1) / 2, WC = 8 * NBC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *Ks = (double2 *)smem_raw;                 // NT x 32 : K (core block) in tile / lane order
+    double2 *dKs = Ks + NT * 32;                       // NT x 32 : dK/dlog(omega)
+    double *bord = (double *)(dKs + NT * 32);          // 4 x WC : K(i, a), K(i, b), dK(a, i), dK(b, i)   (a = WC, b = WC + 1)
+    double *bsc = bord + 4 * WC;                       // 8 : K(a,a), K(a,b), K(b,b), dK(a,b)
+    double *vecs = bsc + 8;                            // WARPS x (7 WC + 8): d | u | v | x1 | x2 | G | H per warp
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r = lane >> 2, c0 = 2 * (lane & 3);
+    const int qb = W - WC;                             // 1 or 2 border rows
+
+    auto kern = [&](int i, int j, double &k, double &dk) {
+        const double dx = (double)(i - j) * dt, d2 = dx * dx;
+        const double ks = sigmasq * exp(-omega * d2);
+        k = ks + (i == j ? eps : 0.0);
+        dk = -ks * d2 * omega;
+    };
+    for (int t = wid; t < NT; t += WARPS) {
+        int i = 0;
+        while (tix(i + 1, 0) <= t) ++i;
+        const int j = t - tix(i, 0);
+        const int gi = 8 * i + r, gj = 8 * j + c0;
+        double2 kv, dv;
+        kern(gi, gj, kv.x, dv.x);
+        kern(gi, gj + 1, kv.y, dv.y);
+        Ks[t * 32 + lane] = kv;
+        dKs[t * 32 + lane] = dv;
+    }
+    for (int i = tid; i < WC; i += WARPS * 32) {
+        double k, dk;
+        kern(i, WC, k, dk);
+        bord[i] = k;
+        bord[2 * WC + i] = dk;
+        k = dk = 0.0;
+        if (qb > 1) kern(i, WC + 1, k, dk);
+        bord[WC + i] = k;
+        bord[3 * WC + i] = dk;
+    }
+    if (tid == 0) {
+        double k, dk;
+        kern(WC, WC, k, dk);
+        bsc[0] = k;
+        bsc[1] = bsc[3] = 0.0;
+        bsc[2] = 0.0;
+        if (qb > 1) {
+            kern(WC, WC + 1, k, dk);
+            bsc[1] = k;
+            bsc[3] = dk;
+            kern(WC + 1, WC + 1, k, dk);
+            bsc[2] = k;
+        }
+    }
+    __syncthreads();
+
+    double *dw = vecs + wid * (7 * WC + 8);
+    double *uu = dw + WC + 8, *vv = uu + WC, *x1 = vv + WC, *x2 = x1 + WC, *Gv = x2 + WC, *Hv = Gv + WC;
+    const int stride = gridDim.x * WARPS;
+    for (int seg = blockIdx.x * WARPS + wid; seg < nseg; seg += stride) {
+        __syncwarp();
+        for (int t = lane; t < WC + 2; t += 32)
+            dw[t] = t < W ? sqrt(fmax(w[((size_t)seg * W + t) * L + l], 0.0)) : 0.0;
+        __syncwarp();
+        // ---- border: B22^-1 = [[p, q], [q, rr]], X = B12 B22^-1, rows of C21 --------------------------------------
+        const double da = dw[WC], db = dw[WC + 1];                 // db = 0 when there is one border row
+        const double b00 = fma(da * bsc[0], da, 1.0), b01 = da * bsc[1] * db, b11 = fma(db * bsc[2], db, 1.0);
+        const double det = fma(b00, b11, -b01 * b01);
+        const bool okb = b00 > 0.0 && det > 0.0;                   // the two pivots of the border block
+        const double idet = 1.0 / det;
+        const double p = b11 * idet, q = -b01 * idet, rr = b00 * idet;
+        const double c01 = da * bsc[3] * db;
+        for (int t = lane; t < WC; t += 32) {
+            const double di = dw[t];
+            const double u = di * bord[t] * da, v = di * bord[WC + t] * db;
+            const double xa = fma(p, u, q * v), xb = fma(q, u, rr * v);
+            const double g = da * bord[2 * WC + t] * di, h = db * bord[3 * WC + t] * di;
+            uu[t] = u;
+            vv[t] = v;
+            x1[t] = xa;
+            x2[t] = xb;
+            Gv[t] = fma(-0.5 * c01, xb, g);
+            Hv[t] = fma(-0.5 * c01, xa, h);
+        }
+        __syncwarp();
+        // ---- S = B11 - u x1' - v x2' in tiles ----------------------------------------------------------------------
+        Tile A[NT];
+#pragma unroll
+        for (int i = 0; i < NBC; ++i) {
+            const double di = dw[8 * i + r], ui = uu[8 * i + r], vi = vv[8 * i + r];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double2 kv = Ks[tix(i, j) * 32 + lane];
+                const int cj = 8 * j + c0;
+                double ax = fma(di * kv.x, dw[cj], (i == j && r == c0) ? 1.0 : 0.0);
+                double ay = fma(di * kv.y, dw[cj + 1], (i == j && r == c0 + 1) ? 1.0 : 0.0);
+                ax = fma(-ui, x1[cj], ax);
+                ay = fma(-ui, x1[cj + 1], ay);
+                A[tix(i, j)].x = fma(-vi, x2[cj], ax);
+                A[tix(i, j)].y = fma(-vi, x2[cj + 1], ay);
+            }
+        }
+        bool ok = tile_sweep<NBC>(A, lane) && okb;            // tiles hold -S^-1
+        // ---- tr(B^-1) and (d B^-1 d) : dK ---------------------------------------------------------------------------
+        double tr = 0.0, pd = 0.0;
+#pragma unroll
+        for (int i = 0; i < NBC; ++i) {
+            const int ri = 8 * i + r;
+            const double di = dw[ri], x1i = x1[ri], x2i = x2[ri], Gi = Gv[ri], Hi = Hv[ri];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double2 dv = dKs[tix(i, j) * 32 + lane];
+                const double wgt = (i == j) ? 1.0 : 2.0;
+                const double sx = -wgt * A[tix(i, j)].x, sy = -wgt * A[tix(i, j)].y;      // S^-1 entries, weighted
+                const int cj = 8 * j + c0;
+                {
+                    const double x1j = x1[cj], x2j = x2[cj];
+                    double kap = di * dv.x * dw[cj];
+                    kap = fma(-x1i, Gv[cj], kap);
+                    kap = fma(-x2i, Hv[cj], kap);
+                    kap = fma(-x1j, Gi, kap);
+                    kap = fma(-x2j, Hi, kap);
+                    pd = fma(sx, kap, pd);
+                    tr = fma(sx, fma(x1i, x1j, x2i * x2j), tr);
+                }
+                {
+                    const double x1j = x1[cj + 1], x2j = x2[cj + 1];
+                    double kap = di * dv.y * dw[cj + 1];
+                    kap = fma(-x1i, Gv[cj + 1], kap);
+                    kap = fma(-x2i, Hv[cj + 1], kap);
+                    kap = fma(-x1j, Gi, kap);
+                    kap = fma(-x2j, Hi, kap);
+                    pd = fma(sy, kap, pd);
+                    tr = fma(sy, fma(x1i, x1j, x2i * x2j), tr);
+                }
+                if (i == j) {
+                    if (r == c0) tr += sx;
+                    if (r == c0 + 1) tr += sy;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tr += __shfl_xor_sync(FULL, tr, o);
+            pd += __shfl_xor_sync(FULL, pd, o);
+        }
+        if (lane == 0) {
+            tr += p + (qb > 1 ? rr : 0.0);
+            pd = fma(2.0 * q, c01, pd);
+            if (!ok) tr = pd = __longlong_as_double(0x7ff8000000000000LL);
+            part[seg] = tr;
+            part[nseg + seg] = pd;
+        }
+    }
+}
+
+template <int NBC>
+int launch_schur(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
+    constexpr int NT = NBC * (NBC + 1) / 2, WC = 8 * NBC;
+    const size_t smem = (size_t)2 * NT * 32 * sizeof(double2) + (4 * WC + 8 + WARPS * (7 * WC + 8)) * sizeof(double);
+    const int S = ts->n_trials;
+    if (ts->dmma_grid == 0) {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(hstep_segment_schur_kernel<NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hstep_segment_schur_kernel<NBC>, WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        ts->dmma_grid = per_sm * ctx->prop.multiProcessorCount;
+        if (ts->dmma_grid > (S + WARPS - 1) / WARPS) ts->dmma_grid = (S + WARPS - 1) / WARPS;
+    }
+    hstep_segment_schur_kernel<NBC><<<dim3(ts->dmma_grid, eb.n), WARPS * 32, smem, ctx->stream>>>(
+        eb, S, ts->max_len, ctx->L, ctx->dt, ts->d_w, ts->d_hpart);
+    CKL();
+    return VLGP_OK;
+}
+
 template <int NB, bool HALF_LAST>
 int launch_th(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatch &eb) {
     constexpr int NT = NB * (NB + 1) / 2;
@@ -210,6 +401,19 @@ int vlgp_launch_hstep_segments_dmma(vlgp_ctx *ctx, TrialSet *ts, const HEvalBatc
     if (getenv("VLGP_FORCE_SWEEP_HSTEP")) return VLGP_OK;
     const int NB = (ts->max_len + 7) / 8;
     int rc = VLGP_OK;
+    // one or two bins beyond a multiple of 8 (the default window of 50): bordered variant
+    const int qb = ts->max_len - 8 * (NB - 1);
+    if (qb <= 2 && NB >= 3 && NB <= 7 && !getenv("VLGP_HSTEP_NO_SCHUR")) {
+        switch (NB - 1) {
+            case 2: rc = launch_schur<2>(ctx, ts, eb); break;
+            case 3: rc = launch_schur<3>(ctx, ts, eb); break;
+            case 4: rc = launch_schur<4>(ctx, ts, eb); break;
+            case 5: rc = launch_schur<5>(ctx, ts, eb); break;
+            default: rc = launch_schur<6>(ctx, ts, eb); break;
+        }
+        if (rc == VLGP_OK) *handled = true;
+        return rc;
+    }
     switch (NB) {
         case 1: rc = launch_t<1>(ctx, ts, eb); break;
         case 2: rc = launch_t<2>(ctx, ts, eb); break;
