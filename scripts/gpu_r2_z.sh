@@ -7,9 +7,11 @@ timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | grep -vE "^Iteration|^Tr
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 ( time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2z_ref.json 2> gpurun_out/r2z_ref.err ) 2>&1 | grep real
 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err
+if [ -z "$SKIP_CONFIGS" ]; then
 python bench.py --config config4 --steps 10 --warmup 5 --no-cpu > gpurun_out/r2z_config4_1gpu.json 2>/dev/null
 python bench.py --config config3 --steps 5 --warmup 3 --no-cpu > gpurun_out/r2z_config3_f64.json 2>/dev/null
 python bench.py --config config3 --steps 5 --warmup 3 --no-cpu --dtype f32 > gpurun_out/r2z_config3_f32.json 2>/dev/null
+fi
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r2z_bench.json'))
@@ -24,8 +26,9 @@ PY
 python scripts/time_fit.py 20 2>&1 | head -2
 python scripts/time_infer.py config2 20 2>&1 | tail -1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r2z_launches.csv python scripts/profile_driver.py 8 > /dev/null 2>&1
-for k in mstep_stats_tma_kernel estep_seg_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 30 -c 1 -o gpurun_out/r2z_$k -f python scripts/profile_driver.py 7 > gpurun_out/r2z_ncu_$k.log 2>&1
+for ks in mstep_stats_tma_kernel:30 estep_seg_kernel:5 hstep_segment_schur_kernel:20; do
+  k=${ks%%:*}; skip=${ks##*:}
+  ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o gpurun_out/r2z_$k -f python scripts/profile_driver.py 7 > gpurun_out/r2z_ncu_$k.log 2>&1
   tail -1 gpurun_out/r2z_ncu_$k.log
 done
 ls gpurun_out | grep r2z | tr '\n' ' '
