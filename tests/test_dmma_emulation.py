@@ -4,6 +4,9 @@ HALF_LAST instantiation leaves out multiply exact zeros, so its result is the fu
 import importlib.util
 import os
 
+import numpy as np
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -14,10 +17,6 @@ def test_half_last_sweep_is_identical_to_the_full_sweep(capsys):
     mod.main()                                  # asserts inside: zero operands, identical tiles, inverse to 1e-12
     out = capsys.readouterr().out
     assert "W=50 NB=7: DMMA 378 -> 351" in out
-
-
-import numpy as np
-import pytest
 
 
 @pytest.mark.parametrize("W,q", [(50, 2), (49, 1), (18, 2), (17, 1)])
