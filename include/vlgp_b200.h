@@ -153,7 +153,10 @@ VLGP_API int vlgp_mstep_begin(vlgp_ctx *ctx, int set_id, int n_iter, int use_hes
 VLGP_API int vlgp_mstep_end(vlgp_ctx *ctx, int *n_fallback);
 
 /* ---- H-step objective: gp.construct_posterior_cov + gp.elbo (vlgp/gp.py:12-62,126-147) --------------------------- */
-/* Once per H-step (mu, w fixed during it): per-latent second moments of mu over the segments (all of length W). */
+/* Once per H-step (mu, w fixed during it): per-latent second moments of mu over the segments (all of length W).
+ * W <= 160: windows of up to 56 bins run on the FP64 tensor path (one warp per segment, bordered variant when W is one or
+ * two bins beyond a multiple of 8), 57..64 on a register sweep, 65..160 on the shared-memory kernels of
+ * csrc/hstep_wide.cu; VLGP_ERR_ARG beyond (the reference itself takes any window, vlgp/gp.py:65-123). */
 VLGP_API int vlgp_hstep_prepare(vlgp_ctx *ctx, int set_id);
 /* hyper = (sigma^2, omega, eps) (already exponentiated).  Returns ll and d ll / d log(omega) (the only slot the
  * reference's mask [0,1,0] keeps, vlgp/gp.py:16,85).  info != 0: K is not positive definite (vlgp/gp.py:17-20,132). */
